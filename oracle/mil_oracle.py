@@ -1,0 +1,653 @@
+"""CPU oracle for the MHIM-MIL per-bag aggregation hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``mhim-mil_b200/`` may import this file; only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs use it, and only as the checker or the timed CPU baseline.
+
+What it is: an independent restatement, as plain functions over tensors, of what the reference
+(DearCaat/MHIM-MIL @ 9d0c91a) computes on the path score -> (masked hard-instance) select ->
+attention-weighted pool.  Every function cites the reference file:line it follows.  It is dtype-
+generic (fp32 like the reference, or fp64 to measure rounding) and differentiable through
+``torch.autograd`` so gradients can be checked too.
+
+Parity pin: the reference ships no tests / golden vectors.  The oracle is
+pinned instead against OUTPUTS OF THE LIVE REFERENCE generated in the build container by
+``tests/golden/make_golden.py`` (committed next to its output) and, when ``/root/reference``
+exists, against the reference classes directly (``tests/test_oracle_vs_reference.py``).
+
+Weights are passed as ``dict[str, Tensor]`` with the reference's own ``state_dict`` keys.
+Batch is always 1 (as everywhere in the reference).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+
+# ----------------------------------------------------------------------------------------------
+# small helpers
+# ----------------------------------------------------------------------------------------------
+def apply_act(x: Tensor, name: Optional[str]) -> Tensor:
+    name = (name or "none").lower()
+    if name == "relu":
+        return torch.relu(x)
+    if name == "gelu":
+        return F.gelu(x)  # exact erf form, nn.GELU() default
+    if name == "tanh":
+        return torch.tanh(x)
+    if name == "sigmoid":
+        return torch.sigmoid(x)
+    if name == "none":
+        return x
+    raise ValueError(name)
+
+
+def affine(x: Tensor, w: Tensor, b: Optional[Tensor] = None) -> Tensor:
+    y = x @ w.transpose(-1, -2)
+    return y if b is None else y + b
+
+
+def layer_norm(x: Tensor, w: Tensor, b: Optional[Tensor], eps: float = 1e-5) -> Tensor:
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    y = (x - mu) / torch.sqrt(var + eps) * w
+    return y if b is None else y + b
+
+
+def softmax_pool(s: Tensor, h: Tensor) -> Tuple[Tensor, Tensor]:
+    """softmax over instances of s[L] and the weighted sum of h[L,H].  Returns (p[H], a[L])."""
+    a = torch.softmax(s, dim=0)
+    return a @ h, a
+
+
+def pool_partial(s: Tensor, h: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """One shard's softmax statistics: m=max s, l=sum e^(s-m), P=sum e^(s-m) h."""
+    m = s.max()
+    e = torch.exp(s - m)
+    return m, e.sum(), e @ h
+
+
+def merge_partials(ms: Sequence[Tensor], ls: Sequence[Tensor], Ps: Sequence[Tensor]) -> Tuple[Tensor, Tensor, Tensor]:
+    """Log-sum-exp merge of shard partials -> (m, l, p) with p already normalised."""
+    m = torch.stack(list(ms)).max()
+    w = [torch.exp(mi - m) for mi in ms]
+    l = sum(li * wi for li, wi in zip(ls, w))
+    P = sum(Pi * wi for Pi, wi in zip(Ps, w))
+    return m, l, P / l
+
+
+# ----------------------------------------------------------------------------------------------
+# a1 / a2 : plain ABMIL heads
+# ----------------------------------------------------------------------------------------------
+def abmil_dattention(sd: SD, x: Tensor, act: str = "relu", return_attn: bool = False,
+                     return_act: bool = False, return_img_feat: bool = False):
+    """modules/abmil.py:203-251 (DAttention.forward), mil_norm=None, pos=None, dropout off.
+
+    feature (:213) -> attention Linear/Tanh/Linear (:229) -> softmax over N (:231-232) ->
+    weighted sum (:234) -> classifier (:238).
+    """
+    if x.dim() == 2:
+        x = x.unsqueeze(0)
+    h = x[0]
+    if "feature.0.weight" in sd:
+        h = apply_act(affine(h, sd["feature.0.weight"], sd.get("feature.0.bias")), act)
+    u = torch.tanh(affine(h, sd["attention.0.weight"], sd.get("attention.0.bias")))
+    s = affine(u, sd["attention.2.weight"], sd.get("attention.2.bias"))[:, 0]
+    p, a = softmax_pool(s, h)
+    logits = affine(p[None], sd["classifier.weight"], sd.get("classifier.bias"))
+    out = [logits, p[None]] if return_img_feat else logits
+    if return_attn:
+        res = [out, a[None]]
+        if return_act:
+            res.append(h[None])
+        return res
+    return out
+
+
+def abmil_gated(sd: SD, x: Tensor, act: str = "relu") -> Tensor:
+    """modules/abmil.py:111-143 (AttentionGated.forward): tanh branch * sigmoid branch, Da=384."""
+    if x.dim() == 2:
+        x = x.unsqueeze(0)
+    h = apply_act(affine(x[0], sd["feature.0.weight"], sd.get("feature.0.bias")), act)
+    ga = torch.tanh(affine(h, sd["attention_a.0.weight"], sd.get("attention_a.0.bias")))
+    gb = torch.sigmoid(affine(h, sd["attention_b.0.weight"], sd.get("attention_b.0.bias")))
+    s = affine(ga * gb, sd["attention_c.weight"], sd.get("attention_c.bias"))[:, 0]
+    p, _ = softmax_pool(s, h)
+    return affine(p[None], sd["classifier.0.weight"], sd.get("classifier.0.bias"))
+
+
+# ----------------------------------------------------------------------------------------------
+# a3 : MHIM's pooling heads on pre-embedded h
+# ----------------------------------------------------------------------------------------------
+def mhim_attention_pool(sd: SD, h: Tensor, da_act: str = "gelu", prefix: str = "online_encoder.",
+                        no_norm: bool = False) -> Tuple[Tensor, Tensor]:
+    """modules/mhim_modules/baseline.py:8-41,88-110.  Bias-free Linear 512->128, act, Linear 128->1,
+    softmax over L, A @ h.  h is [L,512].  Returns (p[512], attn[L]) (raw logits if no_norm, :38-41).
+    """
+    u = apply_act(affine(h, sd[prefix + "attention.attention.0.weight"]), da_act)
+    s = affine(u, sd[prefix + "attention.attention.2.weight"])[:, 0]
+    p, a = softmax_pool(s, h)
+    return p, (s if no_norm else a)
+
+
+# ----------------------------------------------------------------------------------------------
+# a5 : attention -> score
+# ----------------------------------------------------------------------------------------------
+def pseudo_score(w_pred: Tensor, b_pred: Tensor, h: Tensor, attn: Tensor) -> Tensor:
+    """modules/mhim_modules/scoring.py:37-58: score_n = max_c softmax_c(a_n * (h_n . W_c) + b_0).
+
+    Note only bias[0] is added, to every class (:54), so it cancels in the softmax.
+    """
+    cam = (h * attn[:, None]) @ w_pred.t() + b_pred[0]          # [L,C]
+    return torch.softmax(cam, dim=1).max(dim=1).values
+
+
+def pseudo_score_trans(w_pred: Tensor, b_pred: Tensor, v: Tensor, attn: Tensor,
+                       w_out: Tensor, b_out: Tensor) -> Tensor:
+    """scoring.py:9-34: per-head v[8,n,64]*attn[8,n] -> [n,512] -> layer1.attn.to_out -> CAM."""
+    hds, n, d = v.shape
+    f = (v * attn[:, :, None]).permute(1, 0, 2).reshape(n, hds * d)
+    f = affine(f, w_out, b_out)
+    cam = f @ w_pred.t() + b_pred[0]
+    return torch.softmax(cam, dim=1).max(dim=1).values
+
+
+# ----------------------------------------------------------------------------------------------
+# a6 / a7 : masked hard-instance selection
+# ----------------------------------------------------------------------------------------------
+def topk_count(ps: int, ratio: float) -> int:
+    """k exactly as masking.py:61 computes it: python float product, numpy ceil, int()."""
+    return int(math.ceil(ps * ratio))
+
+
+def select_mask(ps: int, attn: Tensor, largest: bool, mask_ratio: float,
+                mask_ids_other: Optional[Tensor] = None, len_keep_other: Optional[int] = None,
+                topk_idx_other: Optional[Tensor] = None, random_ratio: float = 1.0,
+                select_inv: bool = False, msa_fusion: str = "vote") -> Tuple[int, Tensor]:
+    """modules/mhim_modules/masking.py:9-88.
+
+    Consumes torch's global RNG exactly where the reference does (randperm, :67).  The kept ids
+    are returned ascending (the reference builds them from a python set, :77-80, which iterates
+    ascending for the table sizes that occur at MHIM's mask ratios).
+    """
+    ps_eff = ps
+    ratio0 = mask_ratio
+    mask_ratio = mask_ratio / random_ratio                                   # :32
+    if mask_ratio > 1:                                                       # :33-35
+        random_ratio = ratio0
+        mask_ratio = 1.0
+    if mask_ids_other is not None and topk_idx_other is None:                # :37-40
+        topk_idx_other = mask_ids_other[:, len_keep_other:].squeeze()
+        ps_eff = ps - topk_idx_other.size(0)
+
+    if attn.dim() > 2:                                                       # multi-head [1,h,N]
+        if msa_fusion == "mean":                                             # :44-48
+            k = int(math.ceil(ps_eff * mask_ratio) // attn.size(1))
+            idx = torch.topk(attn, k, largest=largest).indices
+            idx = torch.unique(idx.flatten())
+        else:                                                                # vote, :49-59
+            k = topk_count(ps_eff, mask_ratio)
+            hidx = torch.topk(attn, k=k, sorted=False, largest=largest).indices
+            votes = torch.zeros_like(attn).scatter_(2, hidx, 1.0).sum(dim=1)
+            idx = torch.topk(votes, k=k, sorted=False).indices[0]
+    else:                                                                    # :60-63
+        k = topk_count(ps_eff, mask_ratio)
+        idx = torch.topk(attn, k, largest=largest).indices.squeeze(0)
+
+    if random_ratio < 1.0:                                                   # :66-71
+        perm = torch.randperm(idx.size(0), device=idx.device)
+        idx = idx[perm[: int(math.ceil(idx.size(0) * random_ratio))]]
+
+    if mask_ids_other is not None:                                           # :74-75
+        idx = torch.cat([idx, topk_idx_other]).unique()
+
+    len_keep = ps - idx.size(0)                                              # :77
+    keep_flag = torch.ones(ps, dtype=torch.bool, device=attn.device)
+    keep_flag[idx] = False
+    kept = torch.nonzero(keep_flag).flatten()                                # ascending complement
+    if select_inv:                                                           # :82-84
+        return ps - len_keep, torch.cat([idx, kept]).unsqueeze(0)
+    return len_keep, torch.cat([kept, idx]).unsqueeze(0)                     # :86
+
+
+def mask_gather(x: Tensor, mask_ids: Tensor, len_keep: int) -> Tensor:
+    """masking.py:91-110: rows of x[1,L,D] at the first len_keep ids."""
+    return x[:, mask_ids[0, :len_keep]]
+
+
+@dataclass
+class MHIMConfig:
+    """Constructor arguments of modules/mhim.py:22-27 that change the arithmetic."""
+    input_dim: int = 1024
+    mlp_dim: int = 512
+    mask_ratio: float = 0.0
+    n_classes: int = 2
+    temp_t: float = 1.0
+    act: str = "relu"
+    mask_ratio_h: float = 0.0
+    mrh_sche: Optional[Sequence[float]] = None
+    mask_ratio_hr: float = 0.0
+    mask_ratio_l: float = 0.0
+    da_act: str = "gelu"
+    baseline: str = "selfattn"
+    head: int = 8
+    attn2score: bool = True
+    merge_enable: bool = True
+    merge_k: int = 1
+    merge_mm: float = 0.9998
+    merge_ratio: float = 0.0
+    merge_test: bool = False
+
+
+def mhim_get_mask(cfg: MHIMConfig, ps: int, i: Optional[int], attn: Optional[Tensor],
+                  mrh: Optional[float] = None) -> Tuple[int, Optional[Tensor]]:
+    """modules/mhim.py:109-179 (select_inv=False, msa_fusion='vote' as set at :59-60)."""
+    len_keep, ids = ps, None
+    if attn is not None and cfg.mask_ratio > 0.0:                            # :124-128
+        len_keep, ids = select_mask(ps, attn, False, cfg.mask_ratio, random_ratio=0.001)
+    if attn is not None and cfg.mask_ratio_l > 0.0:                          # :133-149
+        if ids is None:
+            len_keep, ids = select_mask(ps, attn, False, cfg.mask_ratio_l)
+        else:
+            other = ids[:, len_keep:].squeeze()
+            len_keep, ids = select_mask(ps, attn, False, cfg.mask_ratio_l, mask_ids_other=ids,
+                                        len_keep_other=ps, topk_idx_other=other)
+    r_h = cfg.mask_ratio_h                                                   # :152-156
+    if cfg.mrh_sche is not None:
+        r_h = cfg.mrh_sche[i]
+    if mrh is not None:
+        r_h = mrh
+    if r_h > 0.0:                                                            # :158-177
+        if ids is None:
+            len_keep, ids = select_mask(ps, attn, True, r_h, len_keep_other=ps,
+                                        random_ratio=cfg.mask_ratio_hr)
+        else:
+            other = ids[:, len_keep:].squeeze()
+            len_keep, ids = select_mask(ps, attn, True, r_h, mask_ids_other=ids, len_keep_other=ps,
+                                        topk_idx_other=other, random_ratio=cfg.mask_ratio_hr)
+    return len_keep, ids
+
+
+# ----------------------------------------------------------------------------------------------
+# a8 : Merge / MCA
+# ----------------------------------------------------------------------------------------------
+def mca(sd: SD, x: Tensor, q_in: Tensor, prefix: str = "merge.attn.", heads: int = 8) -> Tensor:
+    """modules/mhim_modules/merge.py:43-65 with dropout off.  x [n,512], q_in [k,512] -> [k,512]."""
+    kv = affine(x, sd[prefix + "to_kv.weight"])
+    inner = kv.shape[-1] // 2
+    dh = inner // heads
+    kk, vv = kv[:, :inner], kv[:, inner:]
+    q = affine(q_in, sd[prefix + "to_q.weight"])
+    split = lambda t: t.reshape(t.shape[0], heads, dh).permute(1, 0, 2)      # [h, n, d]
+    qh, kh, vh = split(q), split(kk), split(vv)
+    dots = qh @ kh.transpose(-1, -2) * dh ** -0.5
+    out = torch.softmax(dots, dim=-1) @ vh                                   # [h, k, d]
+    out = out.permute(1, 0, 2).reshape(q_in.shape[0], inner)
+    return affine(out, sd[prefix + "to_out.0.weight"], sd[prefix + "to_out.0.bias"])
+
+
+def merge_tokens(sd: SD, x: Tensor, prefix: str = "merge.") -> Tensor:
+    """merge.py:131-144 without the EMA side effect: MCA(LN(x), LN(global_q)) -> [k,512]."""
+    nw, nb = sd[prefix + "norm.weight"], sd[prefix + "norm.bias"]
+    gq = sd[prefix + "global_q"][0]
+    return mca(sd, layer_norm(x, nw, nb), layer_norm(gq, nw, nb), prefix + "attn.")
+
+
+def merge_forward(sd: SD, x: Tensor, merge_ratio: float, training: bool, mm: float,
+                  prefix: str = "merge.") -> Tuple[Tensor, Optional[Tensor]]:
+    """merge.py:146-203 (mask_type='random').  x [L,512].
+
+    training: ids = argsort(rand(L)) (:163-165); first int(L*merge_ratio) kept in that random order
+    (:171-174), the rest merged into k tokens (:141); returns (cat(x_keep, z), new_global_q) where
+    new_global_q is the EMA the reference writes into global_q_mm (:127-129).
+    eval: cat(x, merge(x)) (:199).
+    """
+    if training:
+        L = x.shape[0]
+        n_keep = int(L * merge_ratio)
+        ids = torch.argsort(torch.rand(L, device=x.device), dim=0)
+        z = merge_tokens(sd, x[ids[n_keep:]], prefix)
+        gq = sd[prefix + "global_q"]
+        new_q = gq * mm + z.detach()[None].to(gq.dtype) * (1.0 - mm) if mm != 1.0 else None
+        return torch.cat([x[ids[:n_keep]], z], dim=0), new_q
+    return torch.cat([x, merge_tokens(sd, x, prefix)], dim=0), None
+
+
+# ----------------------------------------------------------------------------------------------
+# a13 : DSMIL
+# ----------------------------------------------------------------------------------------------
+def dsmil_bag(sd: SD, feats: Tensor, classes: Tensor, prefix: str, no_norm: bool = False,
+              v_has_dropout_slot: bool = True):
+    """dsmil.py:85-109 / baseline.py:131-152.  feats [N,512], classes [N,C] -> (pred[1,C], A[N,C], B[C,512]).
+
+    Critical instance per class = argmax over N (the reference sorts, :91 / :137, only to take row 0).
+    """
+    vkey = "v.1" if v_has_dropout_slot else "v.0"
+    V = torch.relu(affine(feats, sd[prefix + vkey + ".weight"], sd.get(prefix + vkey + ".bias")))
+    qnet = lambda t: torch.tanh(affine(torch.relu(affine(t, sd[prefix + "q.0.weight"], sd.get(prefix + "q.0.bias"))),
+                                       sd[prefix + "q.2.weight"], sd[prefix + "q.2.bias"]))
+    Q = qnet(feats)
+    crit = torch.sort(classes, 0, descending=True).indices[0]               # [C]
+    q_max = qnet(feats[crit])
+    logit = (Q @ q_max.t()) / math.sqrt(Q.shape[1])
+    A = torch.softmax(logit, dim=0)
+    B = A.t() @ V                                                            # [C,512]
+    w, b = sd[prefix + "fcc.weight"], sd.get(prefix + "fcc.bias")           # [C,C,512]
+    pred = torch.einsum("ock,ck->o", w, B)
+    if b is not None:
+        pred = pred + b
+    return pred[None], (logit if no_norm else A), B
+
+
+def milnet_forward(sd: SD, x: Tensor, act: str = "relu"):
+    """dsmil.py:142-172 (MILNet.forward), eval branch: (prediction_bag[1,C], max-instance logits[1,C])."""
+    h = apply_act(affine(x[0], sd["feature.0.weight"], sd.get("feature.0.bias")), act)
+    classes = affine(h, sd["i_classifier.weight"], sd.get("i_classifier.bias"))
+    pred, A, B = dsmil_bag(sd, h, classes, "b_classifier.")
+    return pred, classes.max(dim=0).values[None], A, B
+
+
+def mhim_dsmil_encoder(sd: SD, h: Tensor, cls_attn: bool = True, return_attn: bool = False,
+                       no_norm: bool = False, prefix: str = "online_encoder."):
+    """baseline.py:166-194 (DSMIL.attention/forward) on h [L,512]."""
+    classes = affine(h, sd[prefix + "i_classifier.0.weight"], sd[prefix + "i_classifier.0.bias"])
+    pred, A, B = dsmil_bag(sd, h, classes, prefix + "b_classifier.", no_norm=no_norm)
+    inst = classes.max(dim=0).values[None]
+    attn = None
+    if return_attn:
+        attn = (classes.max(dim=-1).values if cls_attn else A.max(dim=-1).values)[None]
+    return [pred, inst], B[None], attn
+
+
+# ----------------------------------------------------------------------------------------------
+# a11 / a12 : Nystrom attention, TransMIL, SAttention
+# ----------------------------------------------------------------------------------------------
+def pinv_iter(x: Tensor, iters: int = 6) -> Tensor:
+    """nystrom_attention.py:12-27.  x [h,m,m]; ONE global scalar normaliser over all heads (:18)."""
+    ax = x.abs()
+    z = x.transpose(-1, -2) / (ax.sum(-1).max() * ax.sum(-2).max())
+    eye = torch.eye(x.shape[-1], dtype=x.dtype, device=x.device)[None]
+    for _ in range(iters):
+        xz = x @ z
+        z = 0.25 * z @ (13 * eye - xz @ (15 * eye - xz @ (7 * eye - xz)))
+    return z
+
+
+def nystrom_attention(sd: SD, x: Tensor, prefix: str, heads: int = 8, m: int = 256, iters: int = 6,
+                      return_attn: bool = False, no_norm: bool = False):
+    """nystrom_attention.py:65-152, dropout off, attn_mask=None.  x [n,dim] -> out [n,dim]
+    (+ cls-row attention [h,n-1] and v[h,n-1,dh] when return_attn)."""
+    n, dim = x.shape
+    pad = (m - n % m) % m                                                    # :70-73 front zero-pad
+    if pad:
+        x = torch.cat([x.new_zeros(pad, dim), x], dim=0)
+    npad = x.shape[0]
+    qkv = affine(x, sd[prefix + "to_qkv.weight"])
+    inner = qkv.shape[-1] // 3
+    dh = inner // heads
+    split = lambda t: t.reshape(npad, heads, dh).permute(1, 0, 2)
+    q, k, v = (split(qkv[:, i * inner:(i + 1) * inner]) for i in range(3))
+    q = q * dh ** -0.5                                                       # :90
+    l = math.ceil(n / m)                                                     # :94
+    q_l = q.reshape(heads, m, l, dh).sum(2) / l                              # :95-109
+    k_l = k.reshape(heads, m, l, dh).sum(2) / l
+    s1 = q @ k_l.transpose(-1, -2)                                           # :114-116
+    s2 = q_l @ k_l.transpose(-1, -2)
+    s3 = q_l @ k.transpose(-1, -2)
+    a1, a2, a3 = s1.softmax(-1), s2.softmax(-1), s3.softmax(-1)              # :130
+    a2i = pinv_iter(a2, iters)                                               # :131
+    out = (a1 @ a2i) @ (a3 @ v)                                              # :132
+    rw = sd.get(prefix + "res_conv.weight")                                  # [h,1,ks,1]
+    if rw is not None:                                                       # :135-136
+        ks = rw.shape[2]
+        out = out + F.conv2d(v[None], rw, padding=(ks // 2, 0), groups=heads)[0]
+    out = out.permute(1, 0, 2).reshape(npad, inner)                          # :140
+    out = affine(out, sd[prefix + "to_out.0.weight"], sd[prefix + "to_out.0.bias"])[-n:]
+    if not return_attn:
+        return out
+    if no_norm:                                                              # :127-129,146-148
+        r = (s1[:, -n][:, None] @ pinv_iter(s2, iters)) @ s3
+    else:                                                                    # :144-145
+        r = (a1[:, -n][:, None] @ a2i) @ a3
+    return out, r[:, 0, -n + 1:], v[:, -n + 1:]
+
+
+def trans_layer(sd: SD, x: Tensor, prefix: str, heads: int = 8, need_attn: bool = False, no_norm: bool = False):
+    """transmil.py:38-48 / baseline.py:210-220: x + Nystrom(LayerNorm(x)), m = dim//2, 6 pinv iters."""
+    dim = x.shape[-1]
+    y = layer_norm(x, sd[prefix + "norm.weight"], sd[prefix + "norm.bias"])
+    r = nystrom_attention(sd, y, prefix + "attn.", heads=heads, m=dim // 2, return_attn=need_attn, no_norm=no_norm)
+    if need_attn:
+        return x + r[0], r[1], r[2]
+    return x + r
+
+
+def _ppeg_convs(sd: SD, grid: Tensor, prefix: str) -> Tensor:
+    c = grid.shape[1]
+    y = grid
+    for name, ks in (("proj", sd[prefix + "proj.weight"].shape[-1]), ("proj1", 5), ("proj2", 3)):
+        y = y + F.conv2d(grid, sd[prefix + name + ".weight"], sd.get(prefix + name + ".bias"),
+                         padding=ks // 2, groups=c)
+    return y
+
+
+def ppeg_transmil(sd: SD, x: Tensor, H: int, W: int, prefix: str = "pos_layer.") -> Tensor:
+    """transmil.py:57-64: x [1+H*W, C]; cls token passes through, the rest goes through 7/5/3 depthwise convs."""
+    cls, tok = x[:1], x[1:]
+    grid = tok.t().reshape(1, -1, H, W)
+    y = _ppeg_convs(sd, grid, prefix)
+    return torch.cat([cls, y.flatten(2)[0].t()], dim=0)
+
+
+def ppeg_selfpad(sd: SD, x: Tensor, prefix: str) -> Tensor:
+    """emb_position.py:92-120: wrap-pad to a square (min 7x7, zero-filled), convs, trim back. x [N,C]."""
+    N, C = x.shape
+    H = W = int(math.ceil(math.sqrt(N)))
+    add = H * W - N
+    x = torch.cat([x, x[:add]], dim=0)
+    if H < 7:
+        H = W = 7
+        zp = H * W - (N + add)
+        x = torch.cat([x, x.new_zeros(zp, C)], dim=0)
+        add += zp
+    y = _ppeg_convs(sd, x.t().reshape(1, C, H, W), prefix).flatten(2)[0].t()
+    return y[:-add] if add > 0 else y
+
+
+def transmil_forward(sd: SD, x: Tensor, act: str = "relu", heads: int = 8, return_attn: bool = False,
+                     return_act: bool = False):
+    """transmil.py:110-175 with dropout off, mil_norm=None, pos='ppeg'."""
+    h = apply_act(affine(x[0], sd["feature.0.weight"], sd.get("feature.0.bias")), act)
+    n0 = h.shape[0]
+    side = int(math.ceil(math.sqrt(n0)))
+    add = side * side - n0
+    h = torch.cat([h, h[:add]], dim=0)                                       # :124-127
+    h = torch.cat([sd["cls_token"][0], h], dim=0)                            # :130-132
+    attn: List[Tensor] = []
+    v = None
+    if return_attn:
+        h, a, v = trans_layer(sd, h, "layer1.", heads, need_attn=True)
+        attn.append((a[:, :-add] if add > 0 else a)[None])
+    else:
+        h = trans_layer(sd, h, "layer1.", heads)
+    h = ppeg_transmil(sd, h, side, side)
+    if return_attn:
+        h, a, _ = trans_layer(sd, h, "layer2.", heads, need_attn=True)
+        attn.append((a[:, :-add] if add > 0 else a)[None])
+    else:
+        h = trans_layer(sd, h, "layer2.", heads)
+    cls = layer_norm(h, sd["norm.weight"], sd["norm.bias"])[:1]
+    logits = affine(cls, sd["classifier.weight"], sd.get("classifier.bias"))
+    if return_attn:
+        out = [logits, attn]
+        if return_act:
+            out.append(v[None])
+        return out
+    return logits
+
+
+def sattention_forward(sd: SD, h: Tensor, heads: int = 8, return_attn: bool = False, return_act: bool = False,
+                       no_norm: bool = False, prefix: str = "online_encoder."):
+    """baseline.py:244-288 (pos_pos=0, pos='ppeg').  h [L,512] -> cls feature [1,512]."""
+    x = torch.cat([sd[prefix + "cls_token"][0], h], dim=0)
+    attn: List[Tensor] = []
+    v = None
+    if return_attn:
+        x, a, v = trans_layer(sd, x, prefix + "layer1.", heads, need_attn=True, no_norm=no_norm)
+        attn.append(a[None])
+    else:
+        x = trans_layer(sd, x, prefix + "layer1.", heads)
+    x = torch.cat([x[:1], ppeg_selfpad(sd, x[1:], prefix + "pos_embedding.")], dim=0)   # :265-266
+    if return_attn:
+        x, a, _ = trans_layer(sd, x, prefix + "layer2.", heads, need_attn=True, no_norm=no_norm)
+        attn.append(a[None])
+    else:
+        x = trans_layer(sd, x, prefix + "layer2.", heads)
+    cls = layer_norm(x, sd[prefix + "norm.weight"], sd[prefix + "norm.bias"])[:1]
+    if return_attn:
+        out = [cls, attn]
+        if return_act:
+            out.append(v[None])
+        return out
+    return cls
+
+
+# ----------------------------------------------------------------------------------------------
+# a4 / a9 / a10 : MHIM entry points
+# ----------------------------------------------------------------------------------------------
+def soft_target_ce(student: Tensor, teacher: Tensor, temp_t: float, temp_s: float = 1.0) -> Tensor:
+    """losses.py:26-44: mean over rows of -softmax(t/Tt) . log_softmax(s/Ts)."""
+    return (-(torch.softmax(teacher / temp_t, -1) * torch.log_softmax(student / temp_s, -1)).sum(-1)).mean()
+
+
+def mhim_embed(sd: SD, x: Tensor, act: str) -> Tensor:
+    """mhim.py:193/244/285/335: feature = Linear(D->512)+act on every row (dropout off)."""
+    return apply_act(affine(x[0], sd["feature.0.weight"], sd["feature.0.bias"]), act)
+
+
+def _encode(cfg: MHIMConfig, sd: SD, h: Tensor, return_attn=False, return_act=False, no_norm=False):
+    if cfg.baseline == "attn":
+        p, a = mhim_attention_pool(sd, h, cfg.da_act, no_norm=no_norm)
+        if return_attn:
+            out = [p[None], a[None]]
+            if return_act:
+                out.append(h[None])
+            return out
+        return p[None]
+    if cfg.baseline == "selfattn":
+        return sattention_forward(sd, h, cfg.head, return_attn, return_act, no_norm)
+    if cfg.baseline == "dsmil":
+        lg, B, attn = mhim_dsmil_encoder(sd, h, cls_attn=cfg.attn2score, return_attn=return_attn, no_norm=no_norm)
+        return (lg, B, attn) if return_attn else (lg, B)
+    raise ValueError(cfg.baseline)
+
+
+def mhim_forward_teacher(cfg: MHIMConfig, sd: SD, x: Tensor):
+    """mhim.py:181-227 (merge_test=False): returns (cls_feat, score)."""
+    h = mhim_embed(sd, x, cfg.act)
+    if cfg.baseline == "dsmil":                                              # :202-205
+        _, B, attn = _encode(cfg, sd, h, return_attn=True)
+        return B, attn
+    feat, attn, act = _encode(cfg, sd, h, return_attn=True, return_act=True)
+    if cfg.attn2score:                                                       # :215-222
+        wp, bp = sd["predictor.weight"], sd["predictor.bias"]
+        if cfg.baseline == "selfattn":
+            p = "online_encoder.layer1.attn.to_out.0."
+            score = pseudo_score_trans(wp, bp, act[0], attn[0][0], sd[p + "weight"], sd[p + "bias"])[None]
+        else:
+            score = pseudo_score(wp, bp, act[0], attn[0])[None]
+        return feat, score
+    if isinstance(attn, (list, tuple)):                                      # :224-225
+        attn = attn[0]
+    return feat, attn
+
+
+def mhim_forward_test(cfg: MHIMConfig, sd: SD, x: Tensor):
+    """mhim.py:229-272 with return_attn=False."""
+    h = mhim_embed(sd, x, cfg.act)
+    if cfg.merge_test:
+        h, _ = merge_forward(sd, h, cfg.merge_ratio, False, cfg.merge_mm)
+    if cfg.baseline == "dsmil":
+        return _encode(cfg, sd, h)
+    return affine(_encode(cfg, sd, h), sd["predictor.weight"], sd["predictor.bias"])
+
+
+def mhim_pure(cfg: MHIMConfig, sd: SD, x: Tensor):
+    """mhim.py:274-298: no masking, no merging."""
+    h = mhim_embed(sd, x, cfg.act)
+    if cfg.baseline == "dsmil":
+        return _encode(cfg, sd, h)[0]
+    return affine(_encode(cfg, sd, h), sd["predictor.weight"], sd["predictor.bias"])
+
+
+def mhim_forward(cfg: MHIMConfig, sd: SD, x: Tensor, attn: Tensor, teacher_cls_feat: Optional[Tensor],
+                 i: Optional[int] = None, training: bool = True):
+    """mhim.py:318-378: the student pass.  Returns (logits, cls_loss, ps, len_keep, new_global_q, mask_ids)."""
+    h = mhim_embed(sd, x, cfg.act)
+    ps = h.shape[0]
+    len_keep, ids = mhim_get_mask(cfg, ps, i, attn)                          # :341
+    h = h[ids[0, :len_keep]]                                                 # :342
+    h, new_q = merge_forward(sd, h, cfg.merge_ratio, training, cfg.merge_mm)  # :351
+    len_keep2 = h.shape[0]
+    if cfg.baseline == "dsmil":                                              # :355-364
+        logit, feat = _encode(cfg, sd, h)
+    else:
+        feat = _encode(cfg, sd, h)
+        logit = affine(feat, sd["predictor.weight"], sd["predictor.bias"])
+    loss = soft_target_ce(feat, teacher_cls_feat.detach(), cfg.temp_t) if teacher_cls_feat is not None else 0.0
+    return logit, loss, ps, len_keep2, new_q, ids
+
+
+# ----------------------------------------------------------------------------------------------
+# Analytic ABMIL backward -- what the streaming backward kernel implements.
+# ----------------------------------------------------------------------------------------------
+def abmil_backward_analytic(x: Tensor, W1: Tensor, b1: Tensor, Wa: Tensor, ba: Optional[Tensor], wc: Tensor,
+                            act: str, g_p: Tensor, Wb: Optional[Tensor] = None, bb: Optional[Tensor] = None):
+    """Gradients of p = softmax_N(s) @ h wrt the weights, given g_p = dL/dp.  x [N,D]; wc [Da].
+
+    Autograd of abmil.py:213-234 written out: g_s = a (h.g_p - p.g_p); g_h = a g_p + Wa^T g_u (+ Wb^T g_v);
+    g_pre = g_h * act'(pre); dW1 = g_pre^T x, etc.
+    """
+    pre = affine(x, W1, b1)
+    h = apply_act(pre, act)
+    ua = affine(h, Wa, ba)
+    t = torch.tanh(ua)
+    if Wb is not None:
+        vb = affine(h, Wb, bb)
+        sg = torch.sigmoid(vb)
+        gate = t * sg
+    else:
+        gate = t
+    s = gate @ wc
+    a = torch.softmax(s, 0)
+    p = a @ h
+    g_s = a * (h @ g_p - p @ g_p)
+    g_gate = g_s[:, None] * wc[None]
+    if Wb is not None:
+        g_u = g_gate * sg * (1 - t * t)
+        g_v = g_gate * t * sg * (1 - sg)
+    else:
+        g_u = g_gate * (1 - t * t)
+        g_v = None
+    g_h = a[:, None] * g_p[None] + g_u @ Wa
+    if Wb is not None:
+        g_h = g_h + g_v @ Wb
+    if act == "relu":
+        d = (pre > 0).to(pre.dtype)
+    elif act == "gelu":
+        d = 0.5 * (1 + torch.erf(pre / math.sqrt(2))) + pre * torch.exp(-0.5 * pre * pre) / math.sqrt(2 * math.pi)
+    else:
+        d = torch.ones_like(pre)
+    g_pre = g_h * d
+    out = {"W1": g_pre.t() @ x, "b1": g_pre.sum(0), "Wa": g_u.t() @ h, "ba": g_u.sum(0), "wc": g_s @ gate}
+    if Wb is not None:
+        out["Wb"] = g_v.t() @ h
+        out["bb"] = g_v.sum(0)
+    return out

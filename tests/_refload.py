@@ -1,0 +1,50 @@
+"""Import the live reference classes from /root/reference WITHOUT running modules/__init__.py
+(which pulls in `future`/`timm`, absent here).  Test infrastructure only; the GPU box has no
+/root/reference, so every user must guard with `have_reference()`.
+"""
+import importlib
+import importlib.util
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("MHIM_REFERENCE_ROOT", "/root/reference")
+
+
+def have_reference() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "modules", "mhim.py"))
+
+
+def load_reference():
+    """Returns a namespace with the reference classes on the hot path."""
+    if not have_reference():
+        raise RuntimeError("reference tree not present")
+    if "modules" not in sys.modules or getattr(sys.modules["modules"], "__mhim_stub__", False) is False:
+        pkg = types.ModuleType("modules")
+        pkg.__path__ = [os.path.join(REF_ROOT, "modules")]
+        pkg.__mhim_stub__ = True
+        sys.modules["modules"] = pkg
+    ns = types.SimpleNamespace()
+    ns.abmil = importlib.import_module("modules.abmil")
+    ns.mhim = importlib.import_module("modules.mhim")
+    ns.dsmil = importlib.import_module("modules.dsmil")
+    ns.transmil = importlib.import_module("modules.transmil")
+    ns.nystrom = importlib.import_module("modules.nystrom_attention")
+    ns.masking = importlib.import_module("modules.mhim_modules.masking")
+    ns.scoring = importlib.import_module("modules.mhim_modules.scoring")
+    ns.merge = importlib.import_module("modules.mhim_modules.merge")
+    ns.baseline = importlib.import_module("modules.mhim_modules.baseline")
+    spec = importlib.util.spec_from_file_location("ref_common_mil", os.path.join(REF_ROOT, "engines", "common_mil.py"))
+    cm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cm)
+    ns.common_mil = cm
+    return ns
+
+
+def zero_dropout(module):
+    """Neutralise every nn.Dropout inside a reference instance (MCA/Nystrom hard-code p=0.1)."""
+    import torch.nn as nn
+    for m in module.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = 0.0
+    return module
