@@ -1,0 +1,142 @@
+/* mhimk.h -- C ABI of libmhimk.so: B200 (sm_100a) kernels for MHIM-MIL's per-bag aggregation path.
+ *
+ * The reference (DearCaat/MHIM-MIL @ 9d0c91a) is pure PyTorch and has NO FFI for this path; each entry
+ * point below names the reference code it replaces (file:line under /root/reference).  INTEGRATION.md
+ * shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - the caller owns all memory incl. workspaces; kernels never allocate; outputs are fully overwritten;
+ *   - all work is enqueued on `stream` (a cudaStream_t); no call synchronises the device;
+ *   - return 0 on success, <0 for an argument error, >0 = cudaError_t; mil_last_error() describes the
+ *     last failure on the calling thread;
+ *   - batch is always one bag (as everywhere in the reference); fp32 in / fp32 out; indices int64.
+ */
+#ifndef MHIMK_H_
+#define MHIMK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIL_ABI_VERSION 1
+
+/* activation codes used by every entry point */
+enum { MIL_ACT_NONE = 0, MIL_ACT_RELU = 1, MIL_ACT_GELU = 2, MIL_ACT_TANH = 3, MIL_ACT_SIGMOID = 4 };
+
+/* arithmetic of the tensor-core contractions in the fused pass */
+enum {
+  MIL_PREC_BF16X3 = 0, /* x = hi + lo (bf16), 3 tcgen05 products, fp32 accumulate: fp32-class (parity mode) */
+  MIL_PREC_FP16   = 1, /* single fp16 product, fp32 accumulate: TF32-class (the reference's own GPU numerics,
+                          main.py:435 enables TF32) */
+  MIL_PREC_BF16   = 2  /* single bf16 product (fastest, ~2^-9 operand rounding) */
+};
+
+typedef void* mil_stream_t; /* cudaStream_t */
+
+int         mil_abi_version(void);
+const char* mil_last_error(void);
+/* 1 if the current device is compute capability 10.x (tcgen05/TMEM/TMA available), else 0. */
+int         mil_device_supported(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused ABMIL forward pass: ONE streaming pass over the bag.
+ *   h_n = act(W1 x_n + b1);  s_n = wc . (tanh(Wa h_n + ba) [* sigmoid(Wb h_n + bb)]) + bc   (att_act generalises tanh)
+ *   per-CTA online softmax over its rows -> partial (m, l, P[H]) -> merged (m, l, pooled = P/l)
+ * Replaces: modules/abmil.py:213-234 (DAttention.forward), :121-139 (AttentionGated.forward),
+ *           modules/mhim.py:193 + modules/mhim_modules/baseline.py:31-41,97-110 (feature + DAttention),
+ *           and with `keep` the gather of modules/mhim_modules/masking.py:91-110.
+ * X [N,D] row-major, 16-byte aligned, D % 32 == 0, H == 512, Da in {128, 256, 384} (Da*(gated?2:1) <= 768).
+ * keep      nullable uint8[N]: rows with keep[n]==0 are skipped (masked instances).
+ * s_out     nullable float[N]: raw attention logits (-inf for skipped rows).
+ * t_out     nullable float[N,C]: t_{n,c} = h_n . Wp_c (needs Wp [C,H], C <= 4) -- input of mil_cam_score_f32.
+ * h_out     nullable float[N,H]: materialised embedding (training / return_act).
+ * part      float[n_part,(2+H)] scratch for the per-CTA partials, n_part = mil_fused_num_partials().
+ * stats     float[2] = (m, l); pooled float[H].
+ * ws / ws_bytes: scratch of at least mil_fused_workspace_bytes(D, Da, gated) bytes (converted weights).
+ */
+int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H,
+                            const float* W1, const float* b1, int act,
+                            const float* Wa, const float* ba, const float* Wb, const float* bb, int Da, int att_act,
+                            const float* wc, const float* bc,
+                            const uint8_t* keep, const float* Wp, int C,
+                            float* s_out, float* t_out, float* h_out,
+                            float* part, float* stats, float* pooled,
+                            void* ws, size_t ws_bytes, int precision, mil_stream_t stream);
+int    mil_fused_num_partials(void);
+size_t mil_fused_workspace_bytes(int D, int H, int Da, int gated);
+
+/* ---------------------------------------------------------------------------------------------
+ * C[M,N] = act( sum_k A(m,k) B(n,k) + bias[n] ), fp32 FFMA tiles (exact fp32; the parity reference on the GPU
+ * and the workhorse of the backward pass).  A(m,k) = A[rowA(m)*sAm + k*sAk] with rowA(m) = row_ids ? row_ids[m] : m,
+ * B(n,k) = B[n*sBn + k*sBk].  One of (sAm,sAk) and one of (sBn,sBk) must be 1.  pre_out (nullable, ld = ldc)
+ * receives the pre-activation.  splitk > 1 splits K over `splitk` slices reduced deterministically through ws
+ * (ws_bytes >= splitk*M*N*4); use for weight gradients where K = #instances.
+ * Replaces: every nn.Linear on the path (abmil.py:181,194-196; mhim.py:69,97; baseline.py:15,27; dsmil.py:62-70,133)
+ * and its autograd (weight grad = TN form, input grad = NN form).
+ */
+int mil_sgemm_f32(const float* A, int64_t sAm, int64_t sAk, const int64_t* row_ids,
+                  const float* B, int64_t sBn, int64_t sBk, const float* bias,
+                  float* C, int64_t ldc, float* pre_out,
+                  int64_t M, int64_t N, int64_t K, int act, int splitk, void* ws, size_t ws_bytes, mil_stream_t stream);
+
+/* g_pre = g_y * act'(.) elementwise; `y_or_pre` is the activation OUTPUT for relu/tanh/sigmoid and the
+ * PRE-activation for gelu.  n elements.  (autograd of nn.ReLU/GELU/Tanh/Sigmoid on the path) */
+int mil_act_bwd_f32(const float* g_y, const float* y_or_pre, int64_t n, int act, float* g_pre, mil_stream_t stream);
+
+/* out[n] = sum_m A[m,n]  (bias gradients), deterministic. */
+int mil_colsum_f32(const float* A, int64_t M, int64_t N, float* out, void* ws, size_t ws_bytes, mil_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * softmax over instances + weighted sum:  a = softmax_L(s); pooled = a @ h.
+ * Replaces: abmil.py:231-234, baseline.py:33-36, and (per class column) dsmil.py:94-96 / baseline.py:144-147.
+ * s [L] (stride s_stride floats), h [L,H]; keep nullable uint8[L]; part: float[n_part,(2+H)] with
+ * n_part = mil_pool_num_partials(L); stats float[2] = (m, l); pooled float[H]; attn_out nullable float[L].
+ */
+int mil_softmax_pool_fwd_f32(const float* s, int64_t s_stride, const float* h, int64_t L, int H, const uint8_t* keep,
+                             float* part, float* stats, float* pooled, float* attn_out, mil_stream_t stream);
+int mil_pool_num_partials(int64_t L);
+/* backward: g_s[n] = a_n (h_n.g_p - pooled.g_p) (+ g_attn handling is done by the caller);
+ * g_h[n,:] (+)= a_n g_p   (g_h nullable; accumulate_gh != 0 adds into g_h). */
+int mil_softmax_pool_bwd_f32(const float* s, int64_t s_stride, const float* h, int64_t L, int H, const uint8_t* keep,
+                             const float* stats, const float* pooled, const float* g_p,
+                             float* g_s, int64_t gs_stride, float* g_h, int accumulate_gh, mil_stream_t stream);
+
+/* Merge n_part partials (m_i, l_i, P_i[H]) laid out as float[n_part,(2+H)] into stats=(m,l), pooled=P/l.
+ * Used for the per-CTA partials of one GPU and for the per-rank partials of an instance-sharded bag
+ * (SURVEY.md §9.3); entries with l_i == 0 are ignored. */
+int mil_pool_merge_f32(const float* part, int n_part, int H, float* stats, float* pooled, mil_stream_t stream);
+
+/* Teacher attention -> score.  Replaces modules/mhim_modules/scoring.py:37-58 (get_pseudo_score):
+ * score_n = max_c softmax_c( a_n * t_{n,c} + bias0 ), a_n = exp(s_n - m)/l, t = h Wp^T given as float[L,C]. */
+int mil_cam_score_f32(const float* s, const float* t, int64_t L, int C, const float* stats, float bias0,
+                      float* score, mil_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Masked hard-instance selection.  Replaces torch.topk + the python-set complement of
+ * modules/mhim_modules/masking.py:61-63,77-86 (select_mask_fn).
+ * mil_topk_f32: idx_out[k] = indices of the k largest (largest!=0) / smallest scores, ordered by value
+ *   (descending for largest) with ties broken lowest-index-first (a total order: deterministic).
+ * mil_mask_from_indices: mask_ids[N] = [ids NOT in idx, ascending || idx in the given order], keep[N] = 1 for
+ *   kept rows, 0 for masked; *len_keep_out (device int64) = N - #distinct idx.  idx entries must be distinct.
+ * ws: at least mil_topk_workspace_bytes(N) bytes.
+ */
+int    mil_topk_f32(const float* score, int64_t N, int64_t k, int largest, int64_t* idx_out,
+                    void* ws, size_t ws_bytes, mil_stream_t stream);
+int    mil_mask_from_indices(const int64_t* idx, int64_t k, int64_t N, int64_t* mask_ids, uint8_t* keep,
+                             int64_t* len_keep_out, void* ws, size_t ws_bytes, mil_stream_t stream);
+size_t mil_topk_workspace_bytes(int64_t N);
+
+/* Self-test hook for the tcgen05/TMA plumbing: C[M,N] = A[M,K] B[N,K]^T with the fused pass's operand pipeline
+ * (fp32 in HBM -> TMA -> bf16/fp16 split in shared memory -> tcgen05.mma -> TMEM -> registers).  M % 128 == 0,
+ * N in {64,128,256,512}, K % 32 == 0.  Used by tests/ only. */
+int mil_umma_selftest_f32(const float* A, const float* B, float* C, int M, int N, int K, int precision,
+                          void* ws, size_t ws_bytes, mil_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MHIMK_H_ */

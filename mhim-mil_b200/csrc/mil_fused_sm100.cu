@@ -1,0 +1,750 @@
+// Fused ABMIL forward for sm_100a: one persistent, warp-specialised kernel that streams the bag X[N,D] (fp32) from HBM
+// exactly once and produces per-CTA softmax-pool partials.
+//
+//   HBM --TMA(SW128)--> fp32 staging ring --converter warps--> 16-bit hi(/lo) operand ring (UMMA K-major SW64)
+//   L2  --TMA(SW64)---> weight ring (W1 hi/lo chunks, then Wa hi/lo chunks)
+//   tcgen05.mma (one thread) : pre[128 x 512] = X_tile W1^T   -> TMEM columns [0,512)       (GEMM1)
+//   epilogue warps           : h = act(pre + b1) -> 16-bit hi/lo -> operand ring (A2), h kept in TMEM / registers
+//   tcgen05.mma              : u[128 x Da] = h Wa^T            -> TMEM columns [0,Da)        (GEMM2)
+//   epilogue warps           : s = wc . tanh(u + ba) + bc, online softmax over rows, p += e^{s-m} h  (warp shuffles)
+//
+// Precision: MIL_PREC_BF16X3 splits every fp32 operand into bf16 hi + lo and issues 3 products (hi.hi, lo.hi, hi.lo)
+// into the same fp32 TMEM accumulator (fp32-class results); MIL_PREC_FP16 / MIL_PREC_BF16 issue one product.
+//
+// The same pipeline with a "store" epilogue is the tensor-core Linear(+bias+act) used to materialise h and as the
+// self-test of the TMA/UMMA plumbing (mil_umma_selftest_f32).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "mil_common.cuh"
+
+namespace mil {
+
+// ------------------------------------------------------------------------------------------------------------
+// geometry
+// ------------------------------------------------------------------------------------------------------------
+constexpr int BM = 128;                 // rows per tile (UMMA M)
+constexpr int BK = 32;                  // K elements per pipeline stage (two UMMA K=16 steps); 64-byte rows -> SWIZZLE_64B
+constexpr int HMAX = 512;               // accumulator columns = all of TMEM
+constexpr int XS = 3;                   // fp32 staging slots (128 rows x 32 floats, SWIZZLE_128B)
+constexpr int X_SLOT_BYTES = BM * BK * 4;           // 16384
+constexpr int A_OP_BYTES = BM * BK * 2;             // 8192  (one 16-bit operand tile)
+constexpr int B_OP_BYTES = HMAX * BK * 2;           // 32768
+constexpr int NUM_THREADS = 512;
+constexpr int EPI_WARP0 = 8;            // warps 8..15: epilogue; 4..7: converters; 0: X TMA; 1: MMA; 2: TMEM alloc; 3: W TMA
+constexpr uint64_t WAIT_TIMEOUT_CYCLES = 4000000000ull;   // ~2 s: trap instead of hanging the GPU on a pipeline bug
+
+enum { MODE_FUSED = 0, MODE_STORE = 1 };
+
+struct FusedParams {
+  int64_t N;            // rows
+  int D;                // K of GEMM1
+  int nout;             // N of GEMM1 (512 in fused mode)
+  int Da;               // N of GEMM2
+  int act, att_act;
+  const float* b1; const float* ba; const float* wc; const float* bc;
+  const uint8_t* keep; const float* Wp; int C;
+  float* s_out; float* t_out; float* h_out; float* part;
+  float* c_out; int64_t ldc;   // MODE_STORE
+  int* err;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if ((uint64_t)(clock64() - t0) > WAIT_TIMEOUT_CYCLES) {
+      if (err) atomicExch(err, code);
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+#define TMEM_REGS32(v) \
+  "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), \
+  "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),  \
+  "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+#define TMEM_REGS32_IN(v) \
+  "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),   \
+  "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),    \
+  "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+
+// 32 lanes x 32 consecutive columns: lane i of the warp gets row (lane_base + i), v[j] = column (col + j)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : TMEM_REGS32(v) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), TMEM_REGS32_IN(v) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows are 64 B, 8-row groups are 512 B apart.
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address            bits [0,14)
+  d |= (uint64_t)1 << 16;                               // leading byte offset (unused for swizzled K-major) bits [16,30)
+  d |= (uint64_t)(512 >> 4) << 32;                      // stride byte offset = 512  bits [32,46)
+  d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell) bits [46,48)
+  d |= (uint64_t)4 << 61;                               // layout type SWIZZLE_64B  bits [61,64)
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: fp32 accumulate, A/B both K-major.
+__device__ __forceinline__ uint32_t make_idesc(int fp16, int n) {
+  const uint32_t fmt = fp16 ? 0u : 1u;                  // 0 = F16, 1 = BF16
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// fp32 pair -> packed 16-bit hi (and the packed 16-bit rounding residual lo)
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack_hi(float x0, float x1) {
+  uint32_t r;
+  if (FP16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_lo_bf16(float x0, float x1, uint32_t hi) {
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xFFFF0000u);
+  return pack_hi<false>(x0 - h0, x1 - h1);
+}
+
+// Write one row (32 consecutive K elements) of a [128 x 32] 16-bit operand tile in the UMMA K-major SWIZZLE_64B layout.
+template <bool FP16, bool LO>
+__device__ __forceinline__ void write_operand_row(uint32_t a_hi, uint32_t a_lo, int row, const float (&x)[32]) {
+  const uint32_t row_off = (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 64u;
+  const uint32_t sw = (uint32_t)(row >> 1) & 3u;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h[i] = pack_hi<FP16>(x[8 * c + 2 * i], x[8 * c + 2 * i + 1]);
+      if (LO) l[i] = pack_lo_bf16(x[8 * c + 2 * i], x[8 * c + 2 * i + 1], h[i]);
+    }
+    const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+    if (LO) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float x) { return act_apply_t<ACT>(x); }
+
+// column sums over the 32 lanes of a warp of v[0..31] (one value per column per lane): afterwards lane j holds sum_rows v_row[j].
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = up ? v[i + s] : v[i];
+      const float give = up ? v[i] : v[i + s];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, give, s);
+    }
+  }
+  return v[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------
+template <int NPROD, bool FP16, int NST, int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
+                 const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl, const FusedParams p) {
+  constexpr bool LO = NPROD == 3;
+  constexpr int NOP = LO ? 2 : 1;                         // operand tiles per stage (hi, lo)
+  constexpr uint32_t A_STAGE = NOP * A_OP_BYTES, B_STAGE = NOP * B_OP_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sX = smem;                                      // XS x 16 KB
+  uint8_t* sA = sX + XS * X_SLOT_BYTES;                    // NST x A_STAGE
+  uint8_t* sB = sA + NST * A_STAGE;                        // NST x B_STAGE
+  uint8_t* sMisc = sB + NST * B_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMisc);     // barrier block
+  float* s_part = reinterpret_cast<float*>(sMisc + 256);   // [2][128] partial attention logits (+ [2][128][4] t partials)
+  float* t_part = s_part + 256;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sMisc + 256 + 1024 + 4096);
+
+  // barrier indices
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  constexpr int B_XFULL = 0, B_XEMPTY = B_XFULL + XS, B_AFULL = B_XEMPTY + XS, B_BFULL = B_AFULL + NST, B_EMPTY = B_BFULL + NST,
+                B_ACCFULL = B_EMPTY + NST, B_ACCEMPTY = B_ACCFULL + 1, B_TAILFREE = B_ACCEMPTY + 1, B_UFULL = B_TAILFREE + 1, B_COUNT = B_UFULL + 1;
+  static_assert(B_COUNT * 8 <= 256, "barrier block overflow");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KS = p.D / BK;                                 // GEMM1 k-steps per tile
+  const int NCH2 = (MODE == MODE_FUSED) ? HMAX / BK : 0;   // GEMM2 k-steps per tile (16)
+  const int64_t n_tiles = (p.N + BM - 1) / BM;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < XS; ++i) { mbar_init(BAR(B_XFULL + i), 1); mbar_init(BAR(B_XEMPTY + i), 4); }
+    for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_AFULL + i), 4); mbar_init(BAR(B_BFULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+    mbar_init(BAR(B_ACCFULL), 1); mbar_init(BAR(B_ACCEMPTY), 8); mbar_init(BAR(B_TAILFREE), 8); mbar_init(BAR(B_UFULL), 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&mapX);
+  if (warp == 3 && lane == 0) { tma_prefetch_desc(&mapWh); if (LO) tma_prefetch_desc(&mapWl); }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== X producer: HBM -> fp32 staging (TMA, SWIZZLE_128B) =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int ks = 0; ks < KS; ++ks, ++it) {
+          const uint32_t s = it % XS, ph = (it / XS) & 1;
+          mbar_wait(BAR(B_XEMPTY + s), ph ^ 1, p.err, 1);
+          mbar_expect_tx(BAR(B_XFULL + s), X_SLOT_BYTES);
+          tma_load_2d(smem_u32(sX + s * X_SLOT_BYTES), &mapX, BAR(B_XFULL + s), ks * BK, (int)(tile * BM));
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== weight producer: L2 -> weight ring (TMA, SWIZZLE_64B) =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      const int nbox = (p.nout + 255) / 256, box_rows = p.nout < 256 ? p.nout : 256;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int ks = 0; ks < KS; ++ks, ++it) {
+          const uint32_t s = it % NST, ph = (it / NST) & 1;
+          mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 2);
+          mbar_expect_tx(BAR(B_BFULL + s), (uint32_t)(NOP * p.nout * BK * 2));
+          const uint32_t dst = smem_u32(sB + s * B_STAGE);
+          for (int b = 0; b < nbox; ++b) {
+            tma_load_2d(dst + b * box_rows * BK * 2, &mapWh, BAR(B_BFULL + s), ks * BK, b * box_rows);
+            if (LO) tma_load_2d(dst + B_OP_BYTES + b * box_rows * BK * 2, &mapWl, BAR(B_BFULL + s), ks * BK, b * box_rows);
+          }
+        }
+        for (int c = 0; c < NCH2; ++c, ++it) {
+          const uint32_t s = it % NST, ph = (it / NST) & 1;
+          mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 3);
+          mbar_expect_tx(BAR(B_BFULL + s), (uint32_t)(NOP * p.Da * BK * 2));
+          const uint32_t dst = smem_u32(sB + s * B_STAGE);
+          tma_load_2d(dst, &mapAh, BAR(B_BFULL + s), c * BK, 0);
+          if (LO) tma_load_2d(dst + B_OP_BYTES, &mapAl, BAR(B_BFULL + s), c * BK, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      uint32_t it = 0, tl = 0;
+      const int n1 = p.nout < 256 ? p.nout : 256, nhalf = (p.nout + 255) / 256;
+      const uint32_t idesc1 = make_idesc(FP16, n1), idesc2 = make_idesc(FP16, p.Da);
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+        mbar_wait(BAR(B_ACCEMPTY), (tl & 1) ^ 1, p.err, 4);
+        tc_fence_after();
+        for (int ks = 0; ks < KS; ++ks, ++it) {
+          const uint32_t s = it % NST, ph = (it / NST) & 1;
+          mbar_wait(BAR(B_AFULL + s), ph, p.err, 5);
+          mbar_wait(BAR(B_BFULL + s), ph, p.err, 6);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + s * A_STAGE), b0 = smem_u32(sB + s * B_STAGE);
+#pragma unroll
+          for (int k16 = 0; k16 < 2; ++k16) {
+            for (int hf = 0; hf < nhalf; ++hf) {
+              const uint32_t acc = (ks | k16) ? 1u : 0u;
+              const uint32_t d = tmem + (uint32_t)(hf * 256);
+              const uint64_t ah = make_desc_sw64(a0 + k16 * 32), bh = make_desc_sw64(b0 + hf * 256 * BK * 2 + k16 * 32);
+              umma_f16(d, ah, bh, idesc1, acc);
+              if (LO) {
+                const uint64_t al = make_desc_sw64(a0 + A_OP_BYTES + k16 * 32), bl = make_desc_sw64(b0 + B_OP_BYTES + hf * 256 * BK * 2 + k16 * 32);
+                umma_f16(d, al, bh, idesc1, 1u);
+                umma_f16(d, ah, bl, idesc1, 1u);
+              }
+            }
+          }
+          umma_commit(BAR(B_EMPTY + s));
+        }
+        umma_commit(BAR(B_ACCFULL));
+        if (MODE == MODE_FUSED) {
+          mbar_wait(BAR(B_TAILFREE), tl & 1, p.err, 7);
+          tc_fence_after();
+          for (int c = 0; c < NCH2; ++c, ++it) {
+            const uint32_t s = it % NST, ph = (it / NST) & 1;
+            mbar_wait(BAR(B_AFULL + s), ph, p.err, 8);
+            mbar_wait(BAR(B_BFULL + s), ph, p.err, 9);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sA + s * A_STAGE), b0 = smem_u32(sB + s * B_STAGE);
+#pragma unroll
+            for (int k16 = 0; k16 < 2; ++k16) {
+              const uint32_t acc = (c | k16) ? 1u : 0u;
+              const uint64_t ah = make_desc_sw64(a0 + k16 * 32), bh = make_desc_sw64(b0 + k16 * 32);
+              umma_f16(tmem, ah, bh, idesc2, acc);
+              if (LO) {
+                const uint64_t al = make_desc_sw64(a0 + A_OP_BYTES + k16 * 32), bl = make_desc_sw64(b0 + B_OP_BYTES + k16 * 32);
+                umma_f16(tmem, al, bh, idesc2, 1u);
+                umma_f16(tmem, ah, bl, idesc2, 1u);
+              }
+            }
+            umma_commit(BAR(B_EMPTY + s));
+          }
+          umma_commit(BAR(B_UFULL));
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== converters: fp32 staging -> 16-bit hi/lo operand tiles =====================
+    const int row = (warp - 4) * 32 + lane;                 // one row of the 128-row slab per thread
+    uint32_t itx = 0, ita = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int ks = 0; ks < KS; ++ks, ++itx, ++ita) {
+        const uint32_t xs = itx % XS, xph = (itx / XS) & 1;
+        const uint32_t s = ita % NST, ph = (ita / NST) & 1;
+        mbar_wait(BAR(B_XFULL + xs), xph, p.err, 10);
+        float x[32];
+        const uint32_t src = smem_u32(sX + xs * X_SLOT_BYTES) + (uint32_t)row * 128u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t a = src + (((uint32_t)j ^ ((uint32_t)row & 7u)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[4 * j]), "=f"(x[4 * j + 1]), "=f"(x[4 * j + 2]), "=f"(x[4 * j + 3]) : "r"(a));
+        }
+        mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 11);
+        const uint32_t a_hi = smem_u32(sA + s * A_STAGE);
+        write_operand_row<FP16, LO>(a_hi, a_hi + A_OP_BYTES, row, x);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(BAR(B_AFULL + s)); mbar_arrive(BAR(B_XEMPTY + xs)); }
+      }
+      ita += NCH2;                                          // the epilogue warps produce the GEMM2 stages of this tile
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;                                 // TMEM lane quarter this warp may touch
+    const int half = (warp - EPI_WARP0) >> 2;               // two warps per quarter split the columns
+    const int row = q * 32 + lane;                          // row inside the tile
+    const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t tl = 0, ita = 0;
+
+    if (MODE == MODE_STORE) {
+      const int nch = p.nout / 32;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+        mbar_wait(BAR(B_ACCFULL), tl & 1, p.err, 12);
+        tc_fence_after();
+        const int64_t grow = tile * BM + row;
+        for (int c = half; c < nch; c += 2) {
+          uint32_t v[32];
+          tmem_ld32(tq + (uint32_t)(c * 32), v);
+          tmem_wait_ld();
+          if (grow < p.N) {
+            float* dst = p.c_out + grow * p.ldc + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o;
+              o.x = act_apply(__uint_as_float(v[j]) + (p.b1 ? p.b1[c * 32 + j] : 0.f), p.act);
+              o.y = act_apply(__uint_as_float(v[j + 1]) + (p.b1 ? p.b1[c * 32 + j + 1] : 0.f), p.act);
+              o.z = act_apply(__uint_as_float(v[j + 2]) + (p.b1 ? p.b1[c * 32 + j + 2] : 0.f), p.act);
+              o.w = act_apply(__uint_as_float(v[j + 3]) + (p.b1 ? p.b1[c * 32 + j + 3] : 0.f), p.act);
+              *reinterpret_cast<float4*>(dst + j) = o;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_ACCEMPTY));
+      }
+    } else {
+      // running online-softmax state of this warp: rows = its 32 lanes, columns = its 8 chunks (chunk c = 2 j + half)
+      float m_run = -INFINITY, l_run = 0.f;
+      float p_run[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p_run[j] = 0.f;
+      const float bc = p.bc ? p.bc[0] : 0.f;
+
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+        const int64_t grow = tile * BM + row;
+        ita += KS;                                          // GEMM1 stages of this tile belong to the converters
+        mbar_wait(BAR(B_ACCFULL), tl & 1, p.err, 13);
+        tc_fence_after();
+
+        // E1: vacate the first 128 accumulator columns (they become GEMM2's accumulator); keep h for them in registers
+        float keep_h[2][32];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = 2 * j + half;
+          uint32_t v[32];
+          tmem_ld32(tq + (uint32_t)(c * 32), v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) keep_h[j][i] = act_apply(__uint_as_float(v[i]) + p.b1[c * 32 + i], p.act);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_TAILFREE));
+
+        // E2: h chunk -> 16-bit operand tiles for GEMM2 (+ h back into TMEM for the pooling pass, + optional outputs)
+        float tacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = 2 * j + half;
+          float hv[32];
+          if (j < 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) hv[i] = keep_h[j][i];
+          } else {
+            uint32_t v[32];
+            tmem_ld32(tq + (uint32_t)(c * 32), v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              hv[i] = act_apply(__uint_as_float(v[i]) + p.b1[c * 32 + i], p.act);
+              v[i] = __float_as_uint(hv[i]);
+            }
+            tmem_st32(tq + (uint32_t)(c * 32), v);
+          }
+          if (p.h_out && grow < p.N) {
+            float* dst = p.h_out + grow * HMAX + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(hv[i], hv[i + 1], hv[i + 2], hv[i + 3]);
+          }
+          if (p.t_out) {
+            for (int cc = 0; cc < p.C; ++cc) {
+              float a = tacc[cc];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) a = fmaf(hv[i], p.Wp[cc * HMAX + c * 32 + i], a);
+              tacc[cc] = a;
+            }
+          }
+          const uint32_t s = (ita + c) % NST, ph = ((ita + c) / NST) & 1;
+          mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 14);
+          const uint32_t a_hi = smem_u32(sA + s * A_STAGE);
+          write_operand_row<FP16, LO>(a_hi, a_hi + A_OP_BYTES, row, hv);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_AFULL + s));
+        }
+        ita += NCH2;
+        tmem_wait_st();
+
+        // E3: attention logit of every row: s = wc . f(u + ba) + bc   (this warp: 64 of the Da = 128 columns)
+        mbar_wait(BAR(B_UFULL), tl & 1, p.err, 15);
+        tc_fence_after();
+        float sp = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c0 = half * 64 + j * 32;
+          uint32_t v[32];
+          tmem_ld32(tq + (uint32_t)c0, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float u = __uint_as_float(v[i]) + (p.ba ? p.ba[c0 + i] : 0.f);
+            sp = fmaf(act_apply(u, p.att_act), p.wc[c0 + i], sp);
+          }
+        }
+        s_part[half * 128 + row] = sp;
+        if (p.t_out)
+          for (int cc = 0; cc < p.C; ++cc) t_part[(half * 128 + row) * 4 + cc] = tacc[cc];
+        named_bar_sync(1, 256);
+        float sv = s_part[row] + s_part[128 + row] + bc;
+        const bool valid = grow < p.N && (!p.keep || p.keep[grow]);
+        if (!valid) sv = -INFINITY;
+        if (half == 0 && grow < p.N) {
+          if (p.s_out) p.s_out[grow] = sv;
+          if (p.t_out)
+            for (int cc = 0; cc < p.C; ++cc) p.t_out[grow * p.C + cc] = t_part[row * 4 + cc] + t_part[(128 + row) * 4 + cc];
+        }
+        named_bar_sync(1, 256);                             // s_part / t_part may be overwritten by the next tile after this
+
+        // online softmax over the 32 rows of this warp
+        const float m_new = fmaxf(m_run, warp_max(sv));
+        float w = 0.f, scale = 1.f;
+        if (m_new > -INFINITY) {
+          scale = (m_run > -INFINITY) ? expf(m_run - m_new) : 0.f;
+          w = valid ? expf(sv - m_new) : 0.f;
+        }
+        l_run = l_run * scale + warp_sum(w);
+        m_run = m_new;
+
+        // E4: p += sum_rows w * h  (h from registers for the vacated columns, from TMEM otherwise)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = 2 * j + half;
+          float hv[32];
+          if (j < 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) hv[i] = keep_h[j][i] * w;
+          } else {
+            uint32_t v[32];
+            tmem_ld32(tq + (uint32_t)(c * 32), v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) hv[i] = __uint_as_float(v[i]) * w;
+          }
+          p_run[j] = p_run[j] * scale + warp_transpose_sum(hv);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_ACCEMPTY));
+      }
+
+      // CTA partial: merge the 4 row quarters (the two column halves share m, l) -> part[blockIdx] = (m, l, P[512])
+      float* red_m = s_part;                                // [4]
+      float* red_l = s_part + 4;                            // [4]
+      named_bar_sync(1, 256);
+      if (half == 0 && lane == 0) { red_m[q] = m_run; red_l[q] = l_run; }
+      named_bar_sync(1, 256);
+      const float m_cta = fmaxf(fmaxf(red_m[0], red_m[1]), fmaxf(red_m[2], red_m[3]));
+      const float f = (m_run > -INFINITY) ? expf(m_run - m_cta) : 0.f;
+      float* pb = t_part;                                   // [4][512] floats = 8 KB?  no: t_part is 4 KB -> use 2 passes over quarters
+      float* out = p.part + (int64_t)blockIdx.x * (2 + HMAX);
+      // quarter by quarter accumulation through a [512] shared vector (fixed order -> deterministic)
+      for (int qq = 0; qq < 4; ++qq) {
+        if (q == qq) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = (2 * j + half) * 32 + lane;
+            pb[col] = (qq == 0 ? 0.f : pb[col]) + p_run[j] * f;
+          }
+        }
+        named_bar_sync(1, 256);
+      }
+      for (int c = threadIdx.x - EPI_WARP0 * 32; c < HMAX; c += 256) out[2 + c] = pb[c];
+      if (threadIdx.x == EPI_WARP0 * 32) {
+        float l = 0.f;
+        for (int i = 0; i < 4; ++i) l += (red_m[i] > -INFINITY) ? red_l[i] * expf(red_m[i] - m_cta) : 0.f;
+        out[0] = m_cta;
+        out[1] = l;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// fp32 -> 16-bit hi / lo split of the weights (once per call; 2.4 MB of weights vs 205 MB of bag)
+// ------------------------------------------------------------------------------------------------------------
+template <bool FP16, bool LO>
+__global__ void split_weights_kernel(const float* __restrict__ w, int64_t n, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i >= n) return;
+  const float x0 = w[i], x1 = (i + 1 < n) ? w[i + 1] : 0.f;
+  const uint32_t h = pack_hi<FP16>(x0, x1);
+  hi[i] = (uint16_t)(h & 0xFFFFu);
+  if (i + 1 < n) hi[i + 1] = (uint16_t)(h >> 16);
+  if (LO) {
+    const uint32_t l = pack_lo_bf16(x0, x1, h);
+    lo[i] = (uint16_t)(l & 0xFFFFu);
+    if (i + 1 < n) lo[i + 1] = (uint16_t)(l >> 16);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  }
+  return fn;
+}
+
+static int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                       uint32_t box_cols, CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -2; }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {cols * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu box=%ux%u)", (int)r, (unsigned long long)rows, (unsigned long long)cols, box_rows, box_cols); return -3; }
+  return 0;
+}
+
+template <int NPROD, bool FP16, int NST, int MODE>
+static int launch_fused(const CUtensorMap& mx, const CUtensorMap& mwh, const CUtensorMap& mwl, const CUtensorMap& mah, const CUtensorMap& mal,
+                        const FusedParams& p, int grid, cudaStream_t stream) {
+  constexpr int NOP = NPROD == 3 ? 2 : 1;
+  const size_t smem = 1024 + (size_t)XS * X_SLOT_BYTES + (size_t)NST * NOP * (A_OP_BYTES + B_OP_BYTES) + 256 + 1024 + 4096 + 16;
+  auto kern = mil_fused_kernel<NPROD, FP16, NST, MODE>;
+  MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, NUM_THREADS, smem, stream>>>(mx, mwh, mwl, mah, mal, p);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+static int dispatch_fused(int precision, int mode, const CUtensorMap& mx, const CUtensorMap& mwh, const CUtensorMap& mwl, const CUtensorMap& mah,
+                          const CUtensorMap& mal, const FusedParams& p, int grid, cudaStream_t stream) {
+  if (mode == MODE_FUSED) {
+    if (precision == MIL_PREC_BF16X3) return launch_fused<3, false, 2, MODE_FUSED>(mx, mwh, mwl, mah, mal, p, grid, stream);
+    if (precision == MIL_PREC_FP16) return launch_fused<1, true, 4, MODE_FUSED>(mx, mwh, mwl, mah, mal, p, grid, stream);
+    return launch_fused<1, false, 4, MODE_FUSED>(mx, mwh, mwl, mah, mal, p, grid, stream);
+  }
+  if (precision == MIL_PREC_BF16X3) return launch_fused<3, false, 2, MODE_STORE>(mx, mwh, mwl, mah, mal, p, grid, stream);
+  if (precision == MIL_PREC_FP16) return launch_fused<1, true, 4, MODE_STORE>(mx, mwh, mwl, mah, mal, p, grid, stream);
+  return launch_fused<1, false, 4, MODE_STORE>(mx, mwh, mwl, mah, mal, p, grid, stream);
+}
+
+static int split_weights(const float* w, int64_t n, uint16_t* hi, uint16_t* lo, int precision, cudaStream_t stream) {
+  const unsigned blocks = (unsigned)((n / 2 + 255) / 256 + 1);
+  if (precision == MIL_PREC_BF16X3) split_weights_kernel<false, true><<<blocks, 256, 0, stream>>>(w, n, hi, lo);
+  else if (precision == MIL_PREC_FP16) split_weights_kernel<true, false><<<blocks, 256, 0, stream>>>(w, n, hi, lo);
+  else split_weights_kernel<false, false><<<blocks, 256, 0, stream>>>(w, n, hi, lo);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mil
+
+using namespace mil;
+
+extern "C" int mil_fused_num_partials(void) { return num_sms(); }
+
+extern "C" size_t mil_fused_workspace_bytes(int D, int H, int Da, int gated) {
+  (void)gated;
+  return ((size_t)H * D + (size_t)Da * H) * 2 /*hi+lo*/ * sizeof(uint16_t) + 1024 + sizeof(int) * 4;
+}
+
+extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, const float* W1, const float* b1, int act, const float* Wa,
+                                       const float* ba, const float* Wb, const float* bb, int Da, int att_act, const float* wc, const float* bc,
+                                       const uint8_t* keep, const float* Wp, int C, float* s_out, float* t_out, float* h_out, float* part,
+                                       float* stats, float* pooled, void* ws, size_t ws_bytes, int precision, mil_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIL_CHECK_ARG(mil_device_supported(), "mil_abmil_fused_fwd_f32: needs a compute-capability 10.x device (tcgen05/TMEM/TMA)");
+  MIL_CHECK_ARG(X && W1 && b1 && Wa && wc && part && stats && pooled && ws, "mil_abmil_fused_fwd_f32: null argument");
+  MIL_CHECK_ARG(N > 0 && N < (1ll << 31) - 256, "mil_abmil_fused_fwd_f32: N=%lld out of range", (long long)N);
+  MIL_CHECK_ARG(H == HMAX, "mil_abmil_fused_fwd_f32: H=%d (only 512 is supported)", H);
+  MIL_CHECK_ARG(D >= BK && D % BK == 0, "mil_abmil_fused_fwd_f32: D=%d must be a positive multiple of %d", D, BK);
+  MIL_CHECK_ARG(Wb == nullptr && bb == nullptr, "mil_abmil_fused_fwd_f32: the gated branch is not fused yet; use the composed path");
+  MIL_CHECK_ARG(Da == 128, "mil_abmil_fused_fwd_f32: Da=%d (only 128 is fused)", Da);
+  MIL_CHECK_ARG(precision >= 0 && precision <= 2, "mil_abmil_fused_fwd_f32: bad precision %d", precision);
+  MIL_CHECK_ARG(!t_out || (Wp && C >= 1 && C <= 4), "mil_abmil_fused_fwd_f32: t_out needs Wp and 1 <= C <= 4");
+  MIL_CHECK_ARG((uintptr_t)X % 16 == 0 && (!h_out || (uintptr_t)h_out % 16 == 0), "mil_abmil_fused_fwd_f32: X / h_out must be 16-byte aligned");
+  MIL_CHECK_ARG(ws_bytes >= mil_fused_workspace_bytes(D, H, Da, 0), "mil_abmil_fused_fwd_f32: workspace needs %zu bytes", mil_fused_workspace_bytes(D, H, Da, 0));
+
+  char* w = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  uint16_t* w1h = (uint16_t*)w;
+  uint16_t* w1l = w1h + (size_t)H * D;
+  uint16_t* wah = w1l + (size_t)H * D;
+  uint16_t* wal = wah + (size_t)Da * H;
+  int* err = (int*)(wal + (size_t)Da * H);
+  int rc;
+  if ((rc = split_weights(W1, (int64_t)H * D, w1h, w1l, precision, stream))) return rc;
+  if ((rc = split_weights(Wa, (int64_t)Da * H, wah, wal, precision, stream))) return rc;
+  MIL_CUDA(cudaMemsetAsync(err, 0, sizeof(int), stream));
+
+  const CUtensorMapDataType dt16 = precision == MIL_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap mx, mwh, mwl, mah, mal;
+  if ((rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)N, (uint64_t)D, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&mwh, dt16, 2, w1h, (uint64_t)H, (uint64_t)D, 256, BK, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_map_2d(&mwl, dt16, 2, w1l, (uint64_t)H, (uint64_t)D, 256, BK, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_map_2d(&mah, dt16, 2, wah, (uint64_t)Da, (uint64_t)H, (uint32_t)Da, BK, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_map_2d(&mal, dt16, 2, wal, (uint64_t)Da, (uint64_t)H, (uint32_t)Da, BK, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+
+  FusedParams p;
+  p.N = N; p.D = D; p.nout = H; p.Da = Da; p.act = act; p.att_act = att_act;
+  p.b1 = b1; p.ba = ba; p.wc = wc; p.bc = bc; p.keep = keep; p.Wp = Wp; p.C = t_out ? C : 0;
+  p.s_out = s_out; p.t_out = t_out; p.h_out = h_out; p.part = part; p.c_out = nullptr; p.ldc = 0; p.err = err;
+  const int64_t n_tiles = (N + BM - 1) / BM;
+  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+  if ((rc = dispatch_fused(precision, MODE_FUSED, mx, mwh, mwl, mah, mal, p, grid, stream))) return rc;
+  return mil_pool_merge_f32(part, grid, H, stats, pooled, stream_);
+}
+
+extern "C" int mil_umma_selftest_f32(const float* A, const float* B, float* C, int M, int N, int K, int precision, void* ws, size_t ws_bytes,
+                                     mil_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIL_CHECK_ARG(mil_device_supported(), "mil_umma_selftest_f32: needs a compute-capability 10.x device");
+  MIL_CHECK_ARG(A && B && C && ws && M > 0, "mil_umma_selftest_f32: null argument");
+  MIL_CHECK_ARG((N == 64 || N == 128 || N == 256 || N == 512) && K >= BK && K % BK == 0, "mil_umma_selftest_f32: unsupported N=%d K=%d", N, K);
+  MIL_CHECK_ARG(precision >= 0 && precision <= 2, "mil_umma_selftest_f32: bad precision");
+  MIL_CHECK_ARG(ws_bytes >= (size_t)N * K * 4 + 1024, "mil_umma_selftest_f32: workspace needs %zu bytes", (size_t)N * K * 4 + 1024);
+  char* w = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  uint16_t* bh = (uint16_t*)w;
+  uint16_t* bl = bh + (size_t)N * K;
+  int* err = (int*)(bl + (size_t)N * K);
+  int rc;
+  if ((rc = split_weights(B, (int64_t)N * K, bh, bl, precision, stream))) return rc;
+  MIL_CUDA(cudaMemsetAsync(err, 0, sizeof(int), stream));
+  const CUtensorMapDataType dt16 = precision == MIL_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap mx, mwh, mwl;
+  const uint32_t box_rows = N < 256 ? N : 256;
+  if ((rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, (uint64_t)M, (uint64_t)K, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&mwh, dt16, 2, bh, (uint64_t)N, (uint64_t)K, box_rows, BK, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_map_2d(&mwl, dt16, 2, bl, (uint64_t)N, (uint64_t)K, box_rows, BK, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  FusedParams p;
+  p.N = M; p.D = K; p.nout = N; p.Da = 128; p.act = MIL_ACT_NONE; p.att_act = MIL_ACT_NONE;
+  p.b1 = nullptr; p.ba = nullptr; p.wc = nullptr; p.bc = nullptr; p.keep = nullptr; p.Wp = nullptr; p.C = 0;
+  p.s_out = nullptr; p.t_out = nullptr; p.h_out = nullptr; p.part = nullptr; p.c_out = C; p.ldc = N; p.err = err;
+  const int64_t n_tiles = ((int64_t)M + BM - 1) / BM;
+  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+  return dispatch_fused(precision, MODE_STORE, mx, mwh, mwl, mwh, mwl, p, grid, stream);
+}

@@ -1,0 +1,464 @@
+// fp32 CUDA-core kernels: exact-fp32 GEMM (NT / TN / NN through strides), activation backward, column sums,
+// softmax-over-instances pooling (forward, backward, partial merge) and the teacher CAM score.
+// These are the parity reference on the GPU and the backward path; the headline forward is mil_fused_sm100.cu.
+#include "mil_common.cuh"
+
+namespace mil {
+
+// ---------------------------------------------------------------------------------------------------------
+// SGEMM: C[m,n] = act(sum_k A(m,k) B(n,k) + bias[n])
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SG_BM = 128, SG_BN = 128, SG_BK = 8, SG_THREADS = 256;
+
+struct SgemmParams {
+  const float* A; int64_t sAm, sAk; const int64_t* row_ids;
+  const float* B; int64_t sBn, sBk;
+  const float* bias; float* C; int64_t ldc; float* pre_out;
+  int64_t M, N, K; int act; int64_t k_per_split; float* partial; int vecA, vecB;
+};
+
+// Load a [128 x 8] operand tile into registers (4 floats per thread).
+// KC (k contiguous): thread -> (row = t/2, k = (t%2)*4 .. +3).  MC (row contiguous): thread -> (k = t/32, row = (t%32)*4 .. +3).
+template <bool KC>
+__device__ __forceinline__ void load_tile(const float* __restrict__ P, int64_t s_row, int64_t s_k, const int64_t* __restrict__ row_ids,
+                                          int64_t row0, int64_t nrows, int64_t k0, int64_t kend, int vec, float (&v)[4]) {
+  const int t = threadIdx.x;
+  if (KC) {
+    const int64_t r = row0 + (t >> 1);
+    const int64_t k = k0 + (t & 1) * 4;
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    if (r < nrows) {
+      const int64_t rr = row_ids ? row_ids[r] : r;
+      const float* p = P + rr * s_row + k;
+      if (vec && k + 3 < kend) {
+        const float4 q = *reinterpret_cast<const float4*>(p);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (k + j < kend) v[j] = p[j];
+      }
+    }
+  } else {
+    const int64_t k = k0 + (t >> 5);
+    const int64_t r = row0 + (t & 31) * 4;
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    if (k < kend) {
+      const float* p = P + k * s_k + r;
+      if (vec && r + 3 < nrows) {
+        const float4 q = *reinterpret_cast<const float4*>(p);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (r + j < nrows) v[j] = p[j];
+      }
+    }
+  }
+}
+
+template <bool KC>
+__device__ __forceinline__ void store_tile(float (*S)[SG_BM], const float (&v)[4]) {
+  const int t = threadIdx.x;
+  if (KC) {
+    const int r = t >> 1, k = (t & 1) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S[k + j][r] = v[j];
+  } else {
+    const int k = t >> 5, r = (t & 31) * 4;
+    *reinterpret_cast<float4*>(&S[k][r]) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(SG_THREADS, 2) sgemm_kernel(const SgemmParams p) {
+  __shared__ __align__(16) float As[2][SG_BK][SG_BM];
+  __shared__ __align__(16) float Bs[2][SG_BK][SG_BN];
+  const int64_t m0 = (int64_t)blockIdx.y * SG_BM, n0 = (int64_t)blockIdx.x * SG_BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * p.k_per_split;
+  const int64_t kend = min(p.K, kbeg + p.k_per_split);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float ra[4], rb[4];
+  load_tile<A_KC>(p.A, p.sAm, p.sAk, p.row_ids, m0, p.M, kbeg, kend, p.vecA, ra);
+  load_tile<B_KC>(p.B, p.sBn, p.sBk, nullptr, n0, p.N, kbeg, kend, p.vecB, rb);
+  store_tile<A_KC>(As[0], ra);
+  store_tile<B_KC>(Bs[0], rb);
+  __syncthreads();
+
+  int buf = 0;
+  for (int64_t k0 = kbeg; k0 < kend; k0 += SG_BK) {
+    const bool more = k0 + SG_BK < kend;
+    if (more) {
+      load_tile<A_KC>(p.A, p.sAm, p.sAk, p.row_ids, m0, p.M, k0 + SG_BK, kend, p.vecA, ra);
+      load_tile<B_KC>(p.B, p.sBn, p.sBk, nullptr, n0, p.N, k0 + SG_BK, kend, p.vecB, rb);
+    }
+#pragma unroll
+    for (int kk = 0; kk < SG_BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      store_tile<A_KC>(As[buf ^ 1], ra);
+      store_tile<B_KC>(Bs[buf ^ 1], rb);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (p.partial) {
+        p.partial[((int64_t)blockIdx.z * p.M + m) * p.N + n] = v;
+      } else {
+        if (p.bias) v += p.bias[n];
+        if (p.pre_out) p.pre_out[m * p.ldc + n] = v;
+        p.C[m * p.ldc + n] = act_apply(v, p.act);
+      }
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t M, int64_t N, const float* __restrict__ bias,
+                                     float* __restrict__ C, int64_t ldc, float* __restrict__ pre_out, int act) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  float v = 0.f;
+  for (int z = 0; z < splits; ++z) v += partial[(int64_t)z * M * N + i];   // fixed order: deterministic
+  const int64_t m = i / N, n = i % N;
+  if (bias) v += bias[n];
+  if (pre_out) pre_out[m * ldc + n] = v;
+  C[m * ldc + n] = act_apply(v, act);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// elementwise activation backward, column sums
+// ---------------------------------------------------------------------------------------------------------
+__global__ void act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t n, int act, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = y[i];
+  float d;
+  switch (act) {
+    case MIL_ACT_RELU: d = v > 0.f ? 1.f : 0.f; break;
+    case MIL_ACT_TANH: d = 1.f - v * v; break;
+    case MIL_ACT_SIGMOID: d = v * (1.f - v); break;
+    case MIL_ACT_GELU:   // v is the PRE-activation: Phi(v) + v phi(v)
+      d = 0.5f * (1.f + erff(v * 0.70710678118654752440f)) + v * 0.39894228040143267794f * expf(-0.5f * v * v);
+      break;
+    default: d = 1.f;
+  }
+  out[i] = g[i] * d;
+}
+
+__global__ void colsum_partial_kernel(const float* __restrict__ A, int64_t M, int64_t N, int64_t rows_per_slice, float* __restrict__ ws) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice, r1 = min(M, r0 + rows_per_slice);
+  float s = 0.f;
+  for (int64_t r = r0; r < r1; ++r) s += A[r * N + n];
+  ws[(int64_t)blockIdx.y * N + n] = s;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ ws, int slices, int64_t N, float* __restrict__ out) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int z = 0; z < slices; ++z) s += ws[(int64_t)z * N + n];
+  out[n] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// softmax over instances + weighted pooling
+// ---------------------------------------------------------------------------------------------------------
+constexpr int POOL_THREADS = 256;   // 8 warps; warp w takes rows w, w+8, ...; lane takes float4 columns lane + 32 j
+
+template <int NV>   // H = NV * 128
+__global__ void __launch_bounds__(POOL_THREADS) softmax_pool_partial_kernel(const float* __restrict__ s, int64_t s_stride, const float* __restrict__ h,
+                                                                            int64_t L, const uint8_t* __restrict__ keep, int64_t rows_per_block,
+                                                                            float* __restrict__ part) {
+  constexpr int H = NV * 128;
+  __shared__ float red[8];
+  __shared__ __align__(16) float accs[8][H];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(L, r0 + rows_per_block);
+
+  float m = -INFINITY;
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += POOL_THREADS)
+    if (!keep || keep[r]) m = fmaxf(m, s[r * s_stride]);
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+
+  float4 acc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float l = 0.f;
+  if (m > -INFINITY) {
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+      if (keep && !keep[r]) continue;
+      const float e = expf(s[r * s_stride] - m);
+      l += e;
+      const float4* hr = reinterpret_cast<const float4*>(h + r * H);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 v = hr[lane + 32 * j];
+        acc[j].x = fmaf(e, v.x, acc[j].x); acc[j].y = fmaf(e, v.y, acc[j].y);
+        acc[j].z = fmaf(e, v.z, acc[j].z); acc[j].w = fmaf(e, v.w, acc[j].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) *reinterpret_cast<float4*>(&accs[warp][(lane + 32 * j) * 4]) = acc[j];
+  if (lane == 0) red[warp] = l;
+  __syncthreads();
+  float* out = part + (int64_t)blockIdx.x * (2 + H);
+  for (int c = threadIdx.x; c < H; c += POOL_THREADS) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += accs[w][c];
+    out[2 + c] = v;
+  }
+  if (threadIdx.x == 0) {
+    float lt = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) lt += red[w];
+    out[0] = m;
+    out[1] = lt;
+  }
+}
+
+// one block; merges n_part partials (m_i, l_i, P_i[H])
+__global__ void pool_merge_kernel(const float* __restrict__ part, int n_part, int H, float* __restrict__ stats, float* __restrict__ pooled) {
+  __shared__ float sm[32];
+  __shared__ float sl[32];
+  const int stride = 2 + H;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < n_part; i += blockDim.x)
+    if (part[(int64_t)i * stride + 1] > 0.f) m = fmaxf(m, part[(int64_t)i * stride]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = -INFINITY;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) m = fmaxf(m, sm[w]);
+  float l = 0.f;
+  for (int i = threadIdx.x; i < n_part; i += blockDim.x) {
+    const float li = part[(int64_t)i * stride + 1];
+    if (li > 0.f) l += li * expf(part[(int64_t)i * stride] - m);
+  }
+  l = warp_sum(l);
+  if ((threadIdx.x & 31) == 0) sl[threadIdx.x >> 5] = l;
+  __syncthreads();
+  l = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) l += sl[w];
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float v = 0.f;
+    for (int i = 0; i < n_part; ++i) {
+      const float li = part[(int64_t)i * stride + 1];
+      if (li > 0.f) v = fmaf(part[(int64_t)i * stride + 2 + c], expf(part[(int64_t)i * stride] - m), v);
+    }
+    pooled[c] = v / l;
+  }
+  if (threadIdx.x == 0) { stats[0] = m; stats[1] = l; }
+}
+
+__global__ void attn_norm_kernel(const float* __restrict__ s, int64_t s_stride, int64_t L, const uint8_t* __restrict__ keep,
+                                 const float* __restrict__ stats, float* __restrict__ attn) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  attn[i] = (keep && !keep[i]) ? 0.f : expf(s[i * s_stride] - stats[0]) / stats[1];
+}
+
+// one warp per row: g_s[n] = a_n (h_n.g_p - pooled.g_p); g_h[n,:] (+)= a_n g_p
+__global__ void __launch_bounds__(256) softmax_pool_bwd_kernel(const float* __restrict__ s, int64_t s_stride, const float* __restrict__ h, int64_t L, int H,
+                                                               const uint8_t* __restrict__ keep, const float* __restrict__ stats, const float* __restrict__ pooled,
+                                                               const float* __restrict__ g_p, float* __restrict__ g_s, int64_t gs_stride,
+                                                               float* __restrict__ g_h, int accumulate) {
+  __shared__ float kappa_s;
+  __shared__ float red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float kp = 0.f;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) kp = fmaf(pooled[c], g_p[c], kp);
+  kp = warp_sum(kp);
+  if (lane == 0) red[warp] = kp;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    kappa_s = t;
+  }
+  __syncthreads();
+  const float kappa = kappa_s, m = stats[0], inv_l = 1.f / stats[1];
+  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < L; r += (int64_t)gridDim.x * 8) {
+    const bool on = !keep || keep[r];
+    const float a = on ? expf(s[r * s_stride] - m) * inv_l : 0.f;
+    float dot = 0.f;
+    if (on)
+      for (int c = lane; c < H; c += 32) dot = fmaf(h[r * H + c], g_p[c], dot);
+    dot = warp_sum(dot);
+    if (lane == 0) g_s[r * gs_stride] = a * (dot - kappa);
+    if (g_h) {
+      for (int c = lane; c < H; c += 32) {
+        const float v = a * g_p[c];
+        g_h[r * H + c] = accumulate ? g_h[r * H + c] + v : v;
+      }
+    }
+  }
+}
+
+__global__ void cam_score_kernel(const float* __restrict__ s, const float* __restrict__ t, int64_t L, int C, const float* __restrict__ stats,
+                                 float bias0, float* __restrict__ score) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  const float a = expf(s[i] - stats[0]) / stats[1];
+  float mx = -INFINITY;
+  for (int c = 0; c < C; ++c) mx = fmaxf(mx, fmaf(a, t[i * C + c], bias0));
+  float den = 0.f;
+  for (int c = 0; c < C; ++c) den += expf(fmaf(a, t[i * C + c], bias0) - mx);
+  score[i] = 1.f / den;     // max_c softmax_c = exp(0) / den
+}
+
+}  // namespace mil
+
+using namespace mil;
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int mil_sgemm_f32(const float* A, int64_t sAm, int64_t sAk, const int64_t* row_ids, const float* B, int64_t sBn, int64_t sBk,
+                             const float* bias, float* C, int64_t ldc, float* pre_out, int64_t M, int64_t N, int64_t K, int act, int splitk,
+                             void* ws, size_t ws_bytes, mil_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIL_CHECK_ARG(A && B && C, "mil_sgemm_f32: null operand");
+  MIL_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && ldc >= N, "mil_sgemm_f32: bad sizes M=%lld N=%lld K=%lld ldc=%lld", (long long)M, (long long)N, (long long)K, (long long)ldc);
+  MIL_CHECK_ARG(sAk == 1 || sAm == 1, "mil_sgemm_f32: A needs a unit stride");
+  MIL_CHECK_ARG(sBk == 1 || sBn == 1, "mil_sgemm_f32: B needs a unit stride");
+  MIL_CHECK_ARG(!(row_ids && sAk != 1), "mil_sgemm_f32: row_ids needs k-contiguous A");
+  if (M == 0 || N == 0) return 0;
+  if (splitk < 1) splitk = 1;
+  const bool a_kc = (sAk == 1), b_kc = (sBk == 1);
+  SgemmParams p;
+  p.A = A; p.sAm = sAm; p.sAk = sAk; p.row_ids = row_ids; p.B = B; p.sBn = sBn; p.sBk = sBk;
+  p.bias = bias; p.C = C; p.ldc = ldc; p.pre_out = pre_out; p.M = M; p.N = N; p.K = K; p.act = act;
+  int64_t kps = (K + splitk - 1) / splitk;
+  kps = (kps + SG_BK - 1) / SG_BK * SG_BK;
+  if (kps <= 0) kps = SG_BK;
+  const int splits = K > 0 ? (int)((K + kps - 1) / kps) : 1;
+  p.k_per_split = kps;
+  p.partial = nullptr;
+  if (splits > 1) {
+    MIL_CHECK_ARG(ws && ws_bytes >= (size_t)splits * M * N * sizeof(float), "mil_sgemm_f32: workspace too small for splitk");
+    p.partial = (float*)ws;
+  }
+  p.vecA = ((uintptr_t)A % 16 == 0) && ((a_kc ? sAm : sAk) % 4 == 0);
+  p.vecB = ((uintptr_t)B % 16 == 0) && ((b_kc ? sBn : sBk) % 4 == 0);
+  dim3 grid((unsigned)((N + SG_BN - 1) / SG_BN), (unsigned)((M + SG_BM - 1) / SG_BM), (unsigned)splits);
+  if (a_kc && b_kc) sgemm_kernel<true, true><<<grid, SG_THREADS, 0, stream>>>(p);
+  else if (a_kc) sgemm_kernel<true, false><<<grid, SG_THREADS, 0, stream>>>(p);
+  else if (b_kc) sgemm_kernel<false, true><<<grid, SG_THREADS, 0, stream>>>(p);
+  else sgemm_kernel<false, false><<<grid, SG_THREADS, 0, stream>>>(p);
+  MIL_LAUNCH_CHECK();
+  if (splits > 1) {
+    const int64_t tot = M * N;
+    splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(p.partial, splits, M, N, bias, C, ldc, pre_out, act);
+    MIL_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int mil_act_bwd_f32(const float* g_y, const float* y_or_pre, int64_t n, int act, float* g_pre, mil_stream_t stream) {
+  MIL_CHECK_ARG(g_y && y_or_pre && g_pre && n >= 0, "mil_act_bwd_f32: bad arguments");
+  if (n == 0) return 0;
+  act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g_y, y_or_pre, n, act, g_pre);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mil_colsum_f32(const float* A, int64_t M, int64_t N, float* out, void* ws, size_t ws_bytes, mil_stream_t stream) {
+  MIL_CHECK_ARG(A && out && M >= 0 && N > 0, "mil_colsum_f32: bad arguments");
+  int slices = (int)min((int64_t)64, max((int64_t)1, (M + 255) / 256));
+  MIL_CHECK_ARG(ws && ws_bytes >= (size_t)slices * N * sizeof(float), "mil_colsum_f32: workspace needs %zu bytes", (size_t)slices * N * sizeof(float));
+  const int64_t rps = (M + slices - 1) / slices;
+  dim3 grid((unsigned)((N + 127) / 128), (unsigned)slices);
+  colsum_partial_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(A, M, N, rps, (float*)ws);
+  MIL_LAUNCH_CHECK();
+  colsum_final_kernel<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const float*)ws, slices, N, out);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mil_pool_num_partials(int64_t L) {
+  const int64_t want = (L + 63) / 64;
+  const int64_t cap = 2 * (int64_t)num_sms();
+  return (int)max((int64_t)1, min(want, cap));
+}
+
+extern "C" int mil_pool_merge_f32(const float* part, int n_part, int H, float* stats, float* pooled, mil_stream_t stream) {
+  MIL_CHECK_ARG(part && stats && pooled && n_part > 0 && H > 0, "mil_pool_merge_f32: bad arguments");
+  pool_merge_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(part, n_part, H, stats, pooled);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mil_softmax_pool_fwd_f32(const float* s, int64_t s_stride, const float* h, int64_t L, int H, const uint8_t* keep, float* part,
+                                        float* stats, float* pooled, float* attn_out, mil_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIL_CHECK_ARG(s && h && part && stats && pooled && L > 0, "mil_softmax_pool_fwd_f32: bad arguments");
+  MIL_CHECK_ARG(H % 128 == 0 && H >= 128 && H <= 1024, "mil_softmax_pool_fwd_f32: H=%d must be a multiple of 128 in [128,1024]", H);
+  MIL_CHECK_ARG((uintptr_t)h % 16 == 0, "mil_softmax_pool_fwd_f32: h must be 16-byte aligned");
+  const int np = mil_pool_num_partials(L);
+  const int64_t rpb = (L + np - 1) / np;
+  switch (H / 128) {
+#define CASE(NV) case NV: softmax_pool_partial_kernel<NV><<<np, POOL_THREADS, 0, stream>>>(s, s_stride, h, L, keep, rpb, part); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+  }
+  MIL_LAUNCH_CHECK();
+  pool_merge_kernel<<<1, 512, 0, stream>>>(part, np, H, stats, pooled);
+  MIL_LAUNCH_CHECK();
+  if (attn_out) {
+    attn_norm_kernel<<<(unsigned)((L + 255) / 256), 256, 0, stream>>>(s, s_stride, L, keep, stats, attn_out);
+    MIL_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int mil_softmax_pool_bwd_f32(const float* s, int64_t s_stride, const float* h, int64_t L, int H, const uint8_t* keep, const float* stats,
+                                        const float* pooled, const float* g_p, float* g_s, int64_t gs_stride, float* g_h, int accumulate_gh,
+                                        mil_stream_t stream) {
+  MIL_CHECK_ARG(s && h && stats && pooled && g_p && g_s && L > 0 && H > 0, "mil_softmax_pool_bwd_f32: bad arguments");
+  const int64_t blocks = min((int64_t)4 * num_sms(), (L + 7) / 8);
+  softmax_pool_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s, s_stride, h, L, H, keep, stats, pooled, g_p, g_s, gs_stride, g_h,
+                                                                                accumulate_gh);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mil_cam_score_f32(const float* s, const float* t, int64_t L, int C, const float* stats, float bias0, float* score, mil_stream_t stream) {
+  MIL_CHECK_ARG(s && t && stats && score && L > 0 && C > 0, "mil_cam_score_f32: bad arguments");
+  cam_score_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s, t, L, C, stats, bias0, score);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,210 @@
+// Masked hard-instance selection on the device (no host round trip).
+//   mil_topk_f32          : radix-select the k-th key, compact the winners in index order, stable LSD radix sort by value
+//   mil_mask_from_indices : complement + concatenation -> mask_ids = [kept ascending || masked], keep flags, len_keep
+// One 1024-thread CTA each: the score vector (4 B/instance; 200 KB at N=50k) is L2-resident right after the teacher
+// pass, the work is a handful of passes over it, and a single CTA needs no grid-wide synchronisation.
+// Total order used everywhere: value (descending for largest), then index ascending -> deterministic, no ties.
+#include "mil_common.cuh"
+
+namespace mil {
+
+constexpr int TK_THREADS = 1024;
+
+__device__ __forceinline__ uint32_t sortable_key(float f, int largest) {
+  uint32_t u = __float_as_uint(f);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // monotone: bigger float -> bigger key
+  return largest ? u : ~u;                          // "bigger key" always means "selected first"
+}
+
+// Exclusive prefix over the per-warp counts held in sh[0..31]; returns (prefix for this warp, total).
+__device__ __forceinline__ void warp_prefix(const int* sh, int warp, int& prefix, int& total) {
+  int p = 0, t = 0;
+#pragma unroll
+  for (int w = 0; w < TK_THREADS / 32; ++w) {
+    const int c = sh[w];
+    if (w < warp) p += c;
+    t += c;
+  }
+  prefix = p;
+  total = t;
+}
+
+__global__ void __launch_bounds__(TK_THREADS) topk_kernel(const float* __restrict__ score, int64_t N, int64_t k, int largest,
+                                                          uint32_t* __restrict__ keyA, uint32_t* __restrict__ keyB,
+                                                          int64_t* __restrict__ idxA, int64_t* __restrict__ idxB,
+                                                          int64_t* __restrict__ idx_out) {
+  __shared__ int hist[256];
+  __shared__ int64_t base[256];
+  __shared__ int wcnt[32][256];
+  __shared__ int cnt_gt[32], cnt_tie[32];
+  __shared__ uint32_t s_prefix;
+  __shared__ int64_t s_need;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  // ---- 1. radix select: T = key of the k-th element in descending key order; need = how many keys == T to take
+  uint32_t prefix = 0, mask = 0;
+  int64_t need = k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    for (int64_t i = tid; i < N; i += TK_THREADS) {
+      const uint32_t key = sortable_key(score[i], largest);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int64_t cum = 0;
+      int d = 255;
+      for (; d > 0; --d) {
+        if (cum + hist[d] >= need) break;
+        cum += hist[d];
+      }
+      s_need = need - cum;
+      s_prefix = prefix | ((uint32_t)d << shift);
+    }
+    __syncthreads();
+    need = s_need;
+    prefix = s_prefix;
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  const uint32_t T = prefix;
+  const int64_t r_ties = need;   // 1 <= r_ties <= #{key == T}
+
+  // ---- 2. compact winners in ascending index order (ties at T: lowest index first)
+  int64_t run_gt = 0, run_tie = 0;
+  for (int64_t c0 = 0; c0 < N; c0 += TK_THREADS) {
+    const int64_t i = c0 + tid;
+    uint32_t key = 0;
+    bool gt = false, tie = false;
+    if (i < N) {
+      key = sortable_key(score[i], largest);
+      gt = key > T;
+      tie = key == T;
+    }
+    const uint32_t bg = __ballot_sync(0xffffffffu, gt), bt = __ballot_sync(0xffffffffu, tie);
+    if (lane == 0) { cnt_gt[warp] = __popc(bg); cnt_tie[warp] = __popc(bt); }
+    __syncthreads();
+    int pg, tg, pt, tt;
+    warp_prefix(cnt_gt, warp, pg, tg);
+    warp_prefix(cnt_tie, warp, pt, tt);
+    const int64_t gt_before = run_gt + pg + __popc(bg & lt_mask);
+    const int64_t tie_before = run_tie + pt + __popc(bt & lt_mask);
+    if (gt || (tie && tie_before < r_ties)) {
+      const int64_t pos = gt_before + min(tie_before, r_ties);
+      keyA[pos] = key;
+      idxA[pos] = i;
+    }
+    run_gt += tg;
+    run_tie += tt;
+    __syncthreads();
+  }
+
+  // ---- 3. stable LSD radix sort of the k winners by key, descending (stability keeps index-ascending among equals)
+  uint32_t* kin = keyA; uint32_t* kout = keyB;
+  int64_t* iin = idxA; int64_t* iout = idxB;
+  for (int shift = 0; shift < 32; shift += 8) {
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    for (int64_t i = tid; i < k; i += TK_THREADS) atomicAdd(&hist[(kin[i] >> shift) & 255u], 1);
+    __syncthreads();
+    if (tid == 0) {
+      int64_t run = 0;
+      for (int d = 255; d >= 0; --d) { base[d] = run; run += hist[d]; }
+    }
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < k; c0 += TK_THREADS) {
+      for (int j = tid; j < 32 * 256; j += TK_THREADS) (&wcnt[0][0])[j] = 0;
+      __syncthreads();
+      const int64_t i = c0 + tid;
+      const bool on = i < k;
+      uint32_t key = 0;
+      int64_t id = 0;
+      int d = 256 + lane;                 // inactive lanes never match anybody
+      if (on) { key = kin[i]; id = iin[i]; d = (key >> shift) & 255u; }
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const int rank = __popc(peers & lt_mask);
+      if (on && rank == 0) wcnt[warp][d] = __popc(peers);
+      __syncthreads();
+      if (tid < 256) {                    // exclusive prefix over warps for digit tid; hist[] reused as the tile total
+        int run = 0;
+        for (int w = 0; w < 32; ++w) { const int c = wcnt[w][tid]; wcnt[w][tid] = run; run += c; }
+        hist[tid] = run;
+      }
+      __syncthreads();
+      if (on) {
+        const int64_t pos = base[d] + wcnt[warp][d] + rank;
+        kout[pos] = key;
+        iout[pos] = id;
+      }
+      __syncthreads();
+      if (tid < 256) base[tid] += hist[tid];
+      __syncthreads();
+    }
+    uint32_t* tk = kin; kin = kout; kout = tk;
+    int64_t* ti = iin; iin = iout; iout = ti;
+  }
+  for (int64_t i = tid; i < k; i += TK_THREADS) idx_out[i] = iin[i];
+}
+
+__global__ void __launch_bounds__(TK_THREADS) mask_from_indices_kernel(const int64_t* __restrict__ idx, int64_t k, int64_t N,
+                                                                       int64_t* __restrict__ mask_ids, uint8_t* __restrict__ keep,
+                                                                       int64_t* __restrict__ len_keep_out) {
+  __shared__ int cnt[32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (int64_t i = tid; i < N; i += TK_THREADS) keep[i] = 1;
+  __syncthreads();
+  for (int64_t j = tid; j < k; j += TK_THREADS) {
+    const int64_t v = idx[j];
+    if (v >= 0 && v < N) keep[v] = 0;
+  }
+  __syncthreads();
+  int64_t run = 0;
+  for (int64_t c0 = 0; c0 < N; c0 += TK_THREADS) {
+    const int64_t i = c0 + tid;
+    const bool kp = i < N && keep[i];
+    const uint32_t b = __ballot_sync(0xffffffffu, kp);
+    if (lane == 0) cnt[warp] = __popc(b);
+    __syncthreads();
+    int p, t;
+    warp_prefix(cnt, warp, p, t);
+    if (kp) mask_ids[run + p + __popc(b & lt_mask)] = i;
+    run += t;
+    __syncthreads();
+  }
+  for (int64_t j = tid; j < k; j += TK_THREADS)
+    if (run + j < N) mask_ids[run + j] = idx[j];
+  if (tid == 0) *len_keep_out = run;
+}
+
+}  // namespace mil
+
+using namespace mil;
+
+extern "C" size_t mil_topk_workspace_bytes(int64_t N) { return (size_t)N * 24 + 256; }
+
+extern "C" int mil_topk_f32(const float* score, int64_t N, int64_t k, int largest, int64_t* idx_out, void* ws, size_t ws_bytes, mil_stream_t stream) {
+  MIL_CHECK_ARG(score && idx_out && N > 0, "mil_topk_f32: bad arguments");
+  MIL_CHECK_ARG(k >= 0 && k <= N, "mil_topk_f32: k=%lld out of range for N=%lld", (long long)k, (long long)N);
+  MIL_CHECK_ARG(ws && ws_bytes >= mil_topk_workspace_bytes(N), "mil_topk_f32: workspace needs %zu bytes", mil_topk_workspace_bytes(N));
+  if (k == 0) return 0;
+  char* w = (char*)(((uintptr_t)ws + 15) & ~(uintptr_t)15);
+  int64_t* idxA = (int64_t*)w;
+  int64_t* idxB = idxA + N;
+  uint32_t* keyA = (uint32_t*)(idxB + N);
+  uint32_t* keyB = keyA + N;
+  topk_kernel<<<1, TK_THREADS, 0, (cudaStream_t)stream>>>(score, N, k, largest, keyA, keyB, idxA, idxB, idx_out);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mil_mask_from_indices(const int64_t* idx, int64_t k, int64_t N, int64_t* mask_ids, uint8_t* keep, int64_t* len_keep_out, void* ws,
+                                     size_t ws_bytes, mil_stream_t stream) {
+  (void)ws; (void)ws_bytes;
+  MIL_CHECK_ARG(mask_ids && keep && len_keep_out && N > 0 && k >= 0 && k <= N && (idx || k == 0), "mil_mask_from_indices: bad arguments");
+  mask_from_indices_kernel<<<1, TK_THREADS, 0, (cudaStream_t)stream>>>(idx, k, N, mask_ids, keep, len_keep_out);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,241 @@
+"""Tensor-level ops over the C ABI (include/mhimk.h).  Every op runs a hand-written CUDA kernel from libmhimk.so on
+the current CUDA stream; there is no CPU / eager-PyTorch fallback (CPU tensors raise).
+
+Differentiable primitives (torch.autograd.Function with CUDA backward):
+  linear_act      y = act(x W^T + b)                    (every nn.Linear(+activation) on the path)
+  softmax_pool    p = softmax_L(s) @ h                  (abmil.py:231-234, baseline.py:33-36, dsmil.py:94-96)
+No-grad fused paths:
+  abmil_fused_forward   one streaming tcgen05 pass X -> (scores, pooled)  (teacher / inference)
+  topk, mask_from_indices, cam_score                    (masked hard-instance selection, scoring.py:37-58)
+"""
+from ctypes import c_float, c_int, c_int64, c_size_t
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT, PREC, check, ptr, stream_ptr
+
+DEFAULT_PRECISION = "bf16x3"
+
+
+def _need(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"mhimk: `{name}` must be a CUDA tensor -- there is no CPU path (got {getattr(t, 'device', type(t))})")
+    if t.dtype != dtype:
+        raise RuntimeError(f"mhimk: `{name}` must be {dtype} (got {t.dtype})")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# raw GEMM
+# --------------------------------------------------------------------------------------------------------------
+def sgemm(A, sAm, sAk, B, sBn, sBk, M, N, K, bias=None, act="none", pre_out=None, row_ids=None, splitk=1, out=None):
+    """C[M,N] = act(sum_k A(m,k) B(n,k) + bias) on fp32 CUDA cores (mil_sgemm_f32)."""
+    L = _lib.lib()
+    C = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=A.device)
+    ws = _ws(splitk * M * N * 4 if splitk > 1 else 16, A.device)
+    check(L.mil_sgemm_f32(ptr(A), sAm, sAk, ptr(row_ids), ptr(B), sBn, sBk, ptr(bias), ptr(C), N, ptr(pre_out), M, N, K, ACT[act], splitk,
+                          ptr(ws), ws.numel(), stream_ptr()), "mil_sgemm_f32")
+    return C
+
+
+def _splitk_for(M, N, K):
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    want = max(1, (2 * 148 + tiles - 1) // tiles)
+    return int(max(1, min(want, (K + 511) // 512, 64)))
+
+
+class _LinearAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, b, act):
+        x, W = _need(x, "x"), _need(W, "weight")
+        b = _need(b, "bias") if b is not None else None
+        M, K = x.shape
+        N = W.shape[0]
+        need_pre = act == "gelu" and (x.requires_grad or W.requires_grad)
+        pre = torch.empty((M, N), dtype=torch.float32, device=x.device) if need_pre else None
+        y = sgemm(x, K, 1, W, K, 1, M, N, K, bias=b, act=act, pre_out=pre)
+        ctx.act = act
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(x, W, pre if need_pre else y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        x, W, saved = ctx.saved_tensors
+        L = _lib.lib()
+        g_y = _need(g_y, "grad")
+        M, K = x.shape
+        N = W.shape[0]
+        if ctx.act in ("none", None):
+            g_pre = g_y
+        else:
+            g_pre = torch.empty_like(g_y)
+            check(L.mil_act_bwd_f32(ptr(g_y), ptr(saved), g_y.numel(), ACT[ctx.act], ptr(g_pre), stream_ptr()), "mil_act_bwd_f32")
+        gx = gW = gb = None
+        if ctx.needs_input_grad[1]:
+            # gW[n,k] = sum_m g_pre[m,n] x[m,k]:  A(n,m) = g_pre[m*N + n] (row-contiguous), B(k,m) = x[m*K + k]
+            gW = sgemm(g_pre, 1, N, x, 1, K, N, K, M, splitk=_splitk_for(N, K, M))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = torch.empty(N, dtype=torch.float32, device=x.device)
+            ws = _ws(64 * N * 4, x.device)
+            check(L.mil_colsum_f32(ptr(g_pre), M, N, ptr(gb), ptr(ws), ws.numel(), stream_ptr()), "mil_colsum_f32")
+        if ctx.needs_input_grad[0]:
+            # gx[m,k] = sum_n g_pre[m,n] W[n,k]:  A(m,n) = g_pre[m*N + n], B(k,n) = W[n*K + k]
+            gx = sgemm(g_pre, N, 1, W, 1, K, M, K, N)
+        return gx, gW, gb, None
+
+
+def linear_act(x: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor] = None, act: str = "none") -> torch.Tensor:
+    """act(x @ W.T + b) for x [M,K]; differentiable (CUDA backward)."""
+    return _LinearAct.apply(x, W, b, act)
+
+
+def linear_act_rows(x, W, b, act, row_ids):
+    """No-grad variant that reads only the rows `row_ids` (int64) of x: fuses masking.py:108's gather into the GEMM."""
+    x, W = _need(x, "x"), _need(W, "weight")
+    row_ids = _need(row_ids, "row_ids", torch.int64)
+    M, K, N = row_ids.numel(), x.shape[1], W.shape[0]
+    return sgemm(x, K, 1, W, K, 1, M, N, K, bias=b, act=act, row_ids=row_ids)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# softmax over instances + pooling
+# --------------------------------------------------------------------------------------------------------------
+def _pool_fwd(s, h, keep, want_attn):
+    L = _lib.lib()
+    n, H = h.shape
+    npart = L.mil_pool_num_partials(n)
+    part = torch.empty((npart, 2 + H), dtype=torch.float32, device=h.device)
+    stats = torch.empty(2, dtype=torch.float32, device=h.device)
+    pooled = torch.empty(H, dtype=torch.float32, device=h.device)
+    attn = torch.empty(n, dtype=torch.float32, device=h.device) if want_attn else None
+    check(L.mil_softmax_pool_fwd_f32(ptr(s), s.stride(0), ptr(h), n, H, ptr(keep), ptr(part), ptr(stats), ptr(pooled), ptr(attn), stream_ptr()),
+          "mil_softmax_pool_fwd_f32")
+    return pooled, stats, attn
+
+
+class _SoftmaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, h, keep):
+        h = _need(h, "h")
+        if not s.is_cuda or s.dtype != torch.float32 or s.dim() != 1:
+            raise RuntimeError("mhimk: `s` must be a 1-D float32 CUDA tensor")
+        pooled, stats, attn = _pool_fwd(s, h, keep, True)
+        ctx.save_for_backward(s, h, stats, pooled)
+        ctx.keep = keep
+        ctx.mark_non_differentiable(attn)
+        return pooled, attn
+
+    @staticmethod
+    def backward(ctx, g_p, _g_attn):
+        s, h, stats, pooled = ctx.saved_tensors
+        L = _lib.lib()
+        g_p = _need(g_p, "grad")
+        n, H = h.shape
+        g_s = torch.empty(n, dtype=torch.float32, device=h.device)
+        g_h = torch.empty_like(h) if ctx.needs_input_grad[1] else None
+        check(L.mil_softmax_pool_bwd_f32(ptr(s), s.stride(0), ptr(h), n, H, ptr(ctx.keep), ptr(stats), ptr(pooled), ptr(g_p), ptr(g_s), 1,
+                                         ptr(g_h), 0, stream_ptr()), "mil_softmax_pool_bwd_f32")
+        return g_s, g_h, None
+
+
+def softmax_pool(s: torch.Tensor, h: torch.Tensor, keep: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(pooled[H], attn[L]) = (softmax(s) @ h, softmax(s)); s [L] may be a strided column view.  attn is not differentiable."""
+    return _SoftmaxPool.apply(s, h, keep)
+
+
+def pool_merge(part: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge partials [(m, l, P[H])] -> (stats[2], pooled[H]); also the instance-shard merge of SURVEY §9.3."""
+    L = _lib.lib()
+    part = _need(part, "part")
+    n, w = part.shape
+    stats = torch.empty(2, dtype=torch.float32, device=part.device)
+    pooled = torch.empty(w - 2, dtype=torch.float32, device=part.device)
+    check(L.mil_pool_merge_f32(ptr(part), n, w - 2, ptr(stats), ptr(pooled), stream_ptr()), "mil_pool_merge_f32")
+    return stats, pooled
+
+
+def cam_score(s, t, stats, bias0: float):
+    """score_n = max_c softmax_c(a_n t_nc + bias0) with a_n = exp(s_n - m)/l  (scoring.py:49-58)."""
+    L = _lib.lib()
+    s, t = _need(s, "s"), _need(t, "t")
+    n, C = t.shape
+    out = torch.empty(n, dtype=torch.float32, device=s.device)
+    check(L.mil_cam_score_f32(ptr(s), ptr(t), n, C, ptr(stats), c_float(bias0), ptr(out), stream_ptr()), "mil_cam_score_f32")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# masked hard-instance selection
+# --------------------------------------------------------------------------------------------------------------
+def topk(score: torch.Tensor, k: int, largest: bool = True) -> torch.Tensor:
+    """Indices (int64 [k]) of the k largest/smallest scores ordered by value, ties lowest-index-first (masking.py:62)."""
+    L = _lib.lib()
+    score = _need(score.reshape(-1), "score")
+    n = score.numel()
+    idx = torch.empty(k, dtype=torch.int64, device=score.device)
+    if k == 0:
+        return idx
+    ws = _ws(L.mil_topk_workspace_bytes(n), score.device)
+    check(L.mil_topk_f32(ptr(score), n, k, 1 if largest else 0, ptr(idx), ptr(ws), ws.numel(), stream_ptr()), "mil_topk_f32")
+    return idx
+
+
+def mask_from_indices(idx: torch.Tensor, n: int):
+    """(mask_ids int64 [1,n] = [kept ascending || idx], keep uint8 [n], len_keep int64 device scalar)  (masking.py:77-86)."""
+    L = _lib.lib()
+    idx = _need(idx.reshape(-1), "idx", torch.int64)
+    mask_ids = torch.empty((1, n), dtype=torch.int64, device=idx.device)
+    keep = torch.empty(n, dtype=torch.uint8, device=idx.device)
+    len_keep = torch.empty(1, dtype=torch.int64, device=idx.device)
+    check(L.mil_mask_from_indices(ptr(idx), idx.numel(), n, ptr(mask_ids), ptr(keep), ptr(len_keep), None, 0, stream_ptr()), "mil_mask_from_indices")
+    return mask_ids, keep, len_keep
+
+
+# --------------------------------------------------------------------------------------------------------------
+# fused tcgen05 forward
+# --------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def abmil_fused_forward(x, W1, b1, act, Wa, ba, wc, bc, att_act="tanh", keep=None, Wp=None, want_scores=False, want_h=False,
+                        precision: str = DEFAULT_PRECISION):
+    """One streaming pass over x [N,D]: returns dict(pooled[H], stats[2] = (m, l), s[N]?, t[N,C]?, h[N,H]?, part).
+
+    h = act(x W1^T + b1); s = wc . att_act(Wa h + ba) + bc; pooled = softmax_N(s) @ h.  (mil_abmil_fused_fwd_f32)
+    """
+    L = _lib.lib()
+    x, W1, b1, Wa, wc = _need(x, "x"), _need(W1, "W1"), _need(b1, "b1"), _need(Wa, "Wa"), _need(wc.reshape(-1), "wc")
+    N, D = x.shape
+    H, Da = W1.shape[0], Wa.shape[0]
+    dev = x.device
+    npart = L.mil_fused_num_partials()
+    part = torch.zeros((npart, 2 + H), dtype=torch.float32, device=dev)
+    stats = torch.empty(2, dtype=torch.float32, device=dev)
+    pooled = torch.empty(H, dtype=torch.float32, device=dev)
+    s = torch.empty(N, dtype=torch.float32, device=dev) if want_scores else None
+    C = Wp.shape[0] if Wp is not None else 0
+    t = torch.empty((N, C), dtype=torch.float32, device=dev) if Wp is not None else None
+    h = torch.empty((N, H), dtype=torch.float32, device=dev) if want_h else None
+    ws = _ws(L.mil_fused_workspace_bytes(D, H, Da, 0), dev)
+    check(L.mil_abmil_fused_fwd_f32(ptr(x), N, D, H, ptr(W1), ptr(b1), ACT[act], ptr(Wa), ptr(ba), None, None, Da, ACT[att_act], ptr(wc),
+                                    ptr(bc), ptr(keep), ptr(Wp), C, ptr(s), ptr(t), ptr(h), ptr(part), ptr(stats), ptr(pooled), ptr(ws),
+                                    ws.numel(), PREC[precision], stream_ptr()), "mil_abmil_fused_fwd_f32")
+    return {"pooled": pooled, "stats": stats, "s": s, "t": t, "h": h, "part": part}
+
+
+@torch.no_grad()
+def umma_selftest(A, B, precision: str = DEFAULT_PRECISION):
+    """C = A @ B.T through the fused pass's TMA -> split -> tcgen05 -> TMEM pipeline (tests only)."""
+    L = _lib.lib()
+    A, B = _need(A, "A"), _need(B, "B")
+    M, K = A.shape
+    N = B.shape[0]
+    C = torch.zeros((M, N), dtype=torch.float32, device=A.device)
+    ws = _ws(N * K * 4 + 2048, A.device)
+    check(L.mil_umma_selftest_f32(ptr(A), ptr(B), ptr(C), M, N, K, PREC[precision], ptr(ws), ws.numel(), stream_ptr()), "mil_umma_selftest_f32")
+    return C

@@ -1,0 +1,80 @@
+"""GPU parity of the fused tcgen05 ABMIL forward against the CPU oracle (fp64 and fp32)."""
+import pytest
+import torch
+
+import cases
+from oracle import mil_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# relative tolerance (max|d| / max|ref|) per arithmetic; the north-star gate is 1e-4 for the parity mode
+TOL = {"bf16x3": 1e-4, "fp16": 2e-3, "bf16": 2e-2}
+
+
+@pytest.fixture(scope="module")
+def K():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import mhimk
+    return mhimk.ops
+
+
+def run_oracle(sd, x, act, keep=None):
+    sd64 = {k: v.double() for k, v in sd.items()}
+    h = O.apply_act(O.affine(x[0].double(), sd64["feature.0.weight"], sd64["feature.0.bias"]), act)
+    u = torch.tanh(O.affine(h, sd64["attention.0.weight"], sd64["attention.0.bias"]))
+    s = O.affine(u, sd64["attention.2.weight"], sd64["attention.2.bias"])[:, 0]
+    if keep is not None:
+        s = s.masked_fill(keep == 0, float("-inf"))
+    a = torch.softmax(s, 0)
+    return h, s, a @ h
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16", "bf16"])
+@pytest.mark.parametrize("N,act,kind", [(1, "relu", "randn"), (100, "gelu", "randn"), (128, "relu", "randn"), (129, "relu", "relu"),
+                                        (1024, "gelu", "randn"), (4099, "relu", "randn"), (50000, "relu", "randn")])
+def test_fused_forward(K, prec, N, act, kind):
+    sd = cases.abmil_state(100 + N)
+    x = cases.make_bag(200 + N, N, 1024, kind)
+    h_ref, s_ref, p_ref = run_oracle(sd, x, act)
+    c = {k: v.cuda() for k, v in sd.items()}
+    Wp = torch.randn(2, 512, generator=torch.Generator().manual_seed(1)) * 0.05
+    out = K.abmil_fused_forward(x[0].cuda(), c["feature.0.weight"], c["feature.0.bias"], act, c["attention.0.weight"], c["attention.0.bias"],
+                                c["attention.2.weight"], c["attention.2.bias"], "tanh", Wp=Wp.cuda(), want_scores=True, want_h=(N <= 4099),
+                                precision=prec)
+    torch.cuda.synchronize()
+    assert cases.rel_err(out["pooled"], p_ref) < TOL[prec]
+    assert cases.rel_err(out["s"], s_ref) < TOL[prec] * 3
+    assert cases.rel_err(out["t"], h_ref @ Wp.double().t()) < TOL[prec] * 3
+    if out["h"] is not None:
+        assert cases.rel_err(out["h"], h_ref) < TOL[prec]
+    logits = out["pooled"].cpu().double() @ sd["classifier.weight"].double().t() + sd["classifier.bias"].double()
+    ref_logits = p_ref @ sd["classifier.weight"].double().t() + sd["classifier.bias"].double()
+    assert cases.rel_err(logits, ref_logits) < TOL[prec]
+
+
+def test_fused_forward_with_keep_mask(K):
+    N = 3000
+    sd = cases.abmil_state(7)
+    x = cases.make_bag(8, N, 1024)
+    keep = (torch.rand(N, generator=torch.Generator().manual_seed(3)) > 0.2).to(torch.uint8)
+    _, s_ref, p_ref = run_oracle(sd, x, "gelu", keep)
+    c = {k: v.cuda() for k, v in sd.items()}
+    out = K.abmil_fused_forward(x[0].cuda(), c["feature.0.weight"], c["feature.0.bias"], "gelu", c["attention.0.weight"], c["attention.0.bias"],
+                                c["attention.2.weight"], c["attention.2.bias"], "tanh", keep=keep.cuda(), want_scores=True)
+    assert cases.rel_err(out["pooled"], p_ref) < 1e-4
+    sk = out["s"].cpu()
+    assert torch.isinf(sk[keep == 0]).all() and cases.rel_err(sk[keep == 1], s_ref[keep == 1]) < 3e-4
+
+
+def test_fused_matches_golden_logits(K):
+    """Committed golden vector made from the live reference: abmil relu N=1024 (BASELINE config 0 shape)."""
+    import os
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.pt"), weights_only=False)["abmil"]["relu_1024_randn"]
+    sd, x = cases.abmil_state(11), cases.make_bag(1011, 1024, 1024)
+    c = {k: v.cuda() for k, v in sd.items()}
+    out = K.abmil_fused_forward(x[0].cuda(), c["feature.0.weight"], c["feature.0.bias"], "relu", c["attention.0.weight"], c["attention.0.bias"],
+                                c["attention.2.weight"], c["attention.2.bias"], "tanh")
+    assert cases.rel_err(out["pooled"], G["pooled"][0]) < 1e-4
+    logits = out["pooled"].cpu() @ sd["classifier.weight"].t() + sd["classifier.bias"]
+    assert cases.rel_err(logits, G["logits"][0]) < 1e-4
