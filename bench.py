@@ -1,0 +1,233 @@
+#!/usr/bin/env python
+"""bench.py -- patch-instances/s through the MIL aggregator at N=50 000 x D=1024 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16x3|fp16|bf16]
+
+One "step" = one pass of the hot path (abmil.DAttention eval forward: projection -> gated tanh attention logit ->
+softmax over N -> weighted pool -> classifier) over one synthetic bag of N=50 000 x D=1024 fp32 (204.8 MB).
+N>1 (torchrun): bag-parallel -- every rank streams its own bags, no data-path collective; value = all ranks' instances
+divided by the max-over-ranks device time ("scaling": "weak").
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for the definition of every key.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_INST, D_IN, N_CLASSES = 50000, 1024, 2
+WORKLOAD = "abmil.DAttention eval forward, N=50000 x D=1024 fp32, act=relu, C=2"
+METRIC = "patch-instances/sec through MIL aggregator at N=50k x D=1024"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:  # NVML missing: report it, do not fail the bench
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(sm)}
+
+
+def cpu_forward_fn():
+    """The CPU arm: the oracle restatement of abmil.DAttention.forward (the reference tree does not travel to the GPU box)."""
+    import torch
+    import cases
+    from oracle import mil_oracle as O
+    sd = cases.abmil_state(2021)
+    return (lambda x: O.abmil_dattention(sd, x, "relu")), torch
+
+
+def time_cpu(n_rep, n_inst):
+    fn, torch = cpu_forward_fn()
+    import cases
+    torch.set_num_threads(os.cpu_count())
+    x = cases.make_bag(2021, n_inst, D_IN)
+    with torch.no_grad():
+        fn(x)
+        ts = []
+        for _ in range(n_rep):
+            t0 = time.perf_counter()
+            fn(x)
+            ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; torch CPU, all host threads)."""
+    if rank != 0:
+        return
+    med = time_cpu(max(args.steps, 3), N_INST)
+    val = N_INST / med
+    cb = {"value": val, "unit": "instances/s", "cores": os.cpu_count(), "kind": "port",
+          "sample": f"{max(args.steps, 3)} full bags of N={N_INST} (median), torch CPU fp32, {os.cpu_count()} threads"}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "instances/s", "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD}, "cpu_baseline": cb,
+                      "e2e": {"value": val, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp16", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import cases
+    import mhimk
+    from mhimk.modules import DAttention
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    model = DAttention(D_IN, N_CLASSES, dropout=0.0, act="relu").to(dev).eval()
+    model.load_state_dict({k: v.to(dev) for k, v in cases.abmil_state(2021).items()}, strict=True)
+    model.precision = args.precision
+    # 4 distinct bags (820 MB) visited round-robin: every step streams 205 MB that cannot be in the 126 MB L2
+    n_bags = 4
+    bags = [torch.randn(1, N_INST, D_IN, device=dev, generator=torch.Generator(device=dev).manual_seed(2021 + 17 * rank + i)) for i in range(n_bags)]
+    f0, a0, a2 = model.feature[0], model.attention[0], model.attention[2]
+
+    def step(i):                       # the fused pass + classifier, inputs resident in HBM
+        with torch.no_grad():
+            return model(bags[i % n_bags])
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    sync_all()
+    total_ms = e0.elapsed_time(e1)
+
+    # the dominant kernel alone (CUDA events on the launching stream, same rotation of bags)
+    k_ms = []
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    L = mhimk._lib.lib()
+    prof = hasattr(L, "mil_profile_begin")
+    for i in range(args.steps):
+        ev[i][0].record()
+        mhimk.ops.abmil_fused_forward(bags[i % n_bags][0], f0.weight, f0.bias, "relu", a0.weight, a0.bias, a2.weight, a2.bias, "tanh",
+                                      precision=args.precision)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    k_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    kernel_ms = sum(k_ms) / len(k_ms)
+
+    # end to end through the public module call: pinned host bag -> H2D -> forward -> logits D2H, every step
+    host = [torch.randn(1, N_INST, D_IN).pin_memory() for _ in range(2)]
+    dbuf = torch.empty(1, N_INST, D_IN, device=dev)
+    hout = torch.empty(1, N_CLASSES).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2):
+        dbuf.copy_(host[i % 2], non_blocking=True)
+        with torch.no_grad():
+            hout.copy_(model(dbuf), non_blocking=True)
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(e2e_steps):
+        dbuf.copy_(host[i % 2], non_blocking=True)
+        with torch.no_grad():
+            hout.copy_(model(dbuf), non_blocking=True)
+    e3.record()
+    sync_all()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    e2e_ms = e2.elapsed_time(e3)
+
+    t = torch.tensor([total_ms, e2e_ms, kernel_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, kernel_ms = (float(v) for v in t.tolist())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        ms_step = total_ms / args.steps
+        value = world * N_INST / (ms_step * 1e-3)
+        alg_bytes = N_INST * D_IN * 4                     # X read exactly once; weights (2.4 MB) excluded
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_fused.json")
+        if os.path.isfile(tp):
+            traffic = json.load(open(tp)).get(args.precision)
+        out = {"metric": METRIC, "value": value, "unit": "instances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "precision": args.precision,
+               "config": {"workload": WORKLOAD, "parallelism": f"bag-parallel x{world}", "l2": "4 distinct 205 MB bags round-robin (> 126 MB L2)",
+                          "operand_arithmetic": {"bf16x3": "bf16 hi+lo split, 3 tcgen05 products, fp32 accumulate", "fp16": "single fp16 product",
+                                                 "bf16": "single bf16 product"}[args.precision]},
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                            "peak_source": peak_src, "kernel_ms": kernel_ms, "alg_bytes": alg_bytes,
+                            "note": "event-timed mil_abmil_fused_fwd_f32 call (weight split + fused kernel + merge)"},
+               "e2e": {"value": world * N_INST / (e2e_ms / e2e_steps * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": alg_bytes,
+                       "d2h_bytes_per_step": N_CLASSES * 4, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
+               "gpu_launches": args.steps * 5,            # per step: 2 weight splits, fused kernel, partial merge, classifier GEMM
+               "clocks": sampler.summary()}
+        if not args.no_cpu_baseline:
+            med = time_cpu(5, N_INST)
+            out["cpu_baseline"] = {"value": N_INST / med, "unit": "instances/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"5 full bags of N={N_INST} (median {med * 1e3:.1f} ms), oracle port of abmil.DAttention, torch CPU fp32"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -352,8 +352,11 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
   } else if (warp >= 4 && warp < 8) {
     // ===================== converters: fp32 staging -> 16-bit hi/lo operand tiles =====================
     const int row = (warp - 4) * 32 + lane;                 // one row of the 128-row slab per thread
-    uint32_t itx = 0, ita = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    uint32_t itx = 0, ita = 0, tl = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      // The operand ring is shared with the epilogue warps (GEMM2 stages of the previous tile).  mbarrier waits only carry
+      // one parity bit, so a waiter must never be two phases away from the barrier: do not run ahead of GEMM2(t-1).
+      if (MODE == MODE_FUSED && tl > 0) mbar_wait(BAR(B_UFULL), (tl - 1) & 1, p.err, 16);
       for (int ks = 0; ks < KS; ++ks, ++itx, ++ita) {
         const uint32_t xs = itx % XS, xph = (itx / XS) & 1;
         const uint32_t s = ita % NST, ph = (ita / NST) & 1;

@@ -1,0 +1,42 @@
+"""Helpers shared by the drop-in modules."""
+import torch
+from torch import nn
+
+from .. import ops
+
+
+def init_linear_layers(module: nn.Module) -> None:
+    """Reference init policy (abmil.py:8-21, mhim_modules/utils.py:8-22): Xavier-normal Linear weights, zero biases,
+    LayerNorm weight 1 / bias 0."""
+    for m in module.modules():
+        if isinstance(m, nn.Linear):
+            nn.init.xavier_normal_(m.weight)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.LayerNorm):
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+            nn.init.ones_(m.weight)
+
+
+def act_module(name: str) -> nn.Module:
+    name = name.lower()
+    return {"relu": nn.ReLU, "gelu": nn.GELU, "tanh": nn.Tanh}[name]()
+
+
+def grad_needed(module: nn.Module, *tensors) -> bool:
+    if not torch.is_grad_enabled():
+        return False
+    if any(t is not None and t.requires_grad for t in tensors):
+        return True
+    return any(p.requires_grad for p in module.parameters())
+
+
+def lin(layer: nn.Linear, x: torch.Tensor, act: str = "none") -> torch.Tensor:
+    """act(layer(x)) through the CUDA GEMM of libmhimk (x is [M, in])."""
+    return ops.linear_act(x, layer.weight, layer.bias, act)
+
+
+def require_cuda(x: torch.Tensor, who: str) -> None:
+    if not x.is_cuda:
+        raise RuntimeError(f"{who}: input is on {x.device}; mhimk modules run only on a CUDA (sm_100) device -- no CPU fallback")
