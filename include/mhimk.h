@@ -56,7 +56,9 @@ int         mil_device_supported(void);
  * h_out     nullable float[N,H]: materialised embedding (training / return_act).
  * part      float[n_part,(2+H)] scratch for the per-CTA partials, n_part = mil_fused_num_partials().
  * stats     float[2] = (m, l); pooled float[H].
- * ws / ws_bytes: scratch of at least mil_fused_workspace_bytes(D, Da, gated) bytes (converted weights).
+ * ws / ws_bytes: scratch of at least mil_fused_workspace_bytes(D, H, Da, gated) bytes; it holds the 16-bit hi/lo images of
+ *           W1 and Wa.  ws_ready = 0: the images are (re)built by this call; ws_ready = 1: the caller guarantees `ws` was
+ *           filled by an earlier call with the same weights and precision (skips two small kernels per bag).
  */
 int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H,
                             const float* W1, const float* b1, int act,
@@ -65,8 +67,13 @@ int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H,
                             const uint8_t* keep, const float* Wp, int C,
                             float* s_out, float* t_out, float* h_out,
                             float* part, float* stats, float* pooled,
-                            void* ws, size_t ws_bytes, int precision, mil_stream_t stream);
+                            void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream);
 int    mil_fused_num_partials(void);
+/* Kernel-only timing of the fused pass for the roofline line of bench.py: while enabled, every fused launch is bracketed
+ * by CUDA events on its stream; mil_profile_collect() synchronises them, returns how many launches were timed and writes
+ * their summed duration in ms. */
+void   mil_profile_enable(int on);
+int    mil_profile_collect(double* total_ms);
 size_t mil_fused_workspace_bytes(int D, int H, int Da, int gated);
 
 /* ---------------------------------------------------------------------------------------------

@@ -22,7 +22,9 @@ _SIGS = {
     "mil_device_supported": (c_int, []),
     "mil_abmil_fused_fwd_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                        c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+                                        c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "mil_profile_enable": (None, [c_int]),
+    "mil_profile_collect": (c_int, [ctypes.POINTER(ctypes.c_double)]),
     "mil_fused_num_partials": (c_int, []),
     "mil_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mil_sgemm_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p,

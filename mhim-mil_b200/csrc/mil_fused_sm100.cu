@@ -14,6 +14,9 @@
 // The same pipeline with a "store" epilogue is the tensor-core Linear(+bias+act) used to materialise h and as the
 // self-test of the TMA/UMMA plumbing (mil_umma_selftest_f32).
 #include <cuda.h>
+#include <stdlib.h>
+#include <utility>
+#include <vector>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -48,6 +51,7 @@ struct FusedParams {
   float* s_out; float* t_out; float* h_out; float* part;
   float* c_out; int64_t ldc;   // MODE_STORE
   int* err;
+  int dbg;              // MHIMK_DEBUG bitmask (timing attribution only): 1 skip W TMA, 2 skip X TMA, 4 skip MMA, 8 skip convert
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -131,6 +135,20 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
       ::"r"(taddr), TMEM_REGS32_IN(v) : "memory");
 }
+__device__ __forceinline__ void tmem_wait_ld();
+__device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float (&f)[32]) {
+  uint32_t v[32];
+  tmem_ld32(taddr, v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+}
+__device__ __forceinline__ void tmem_st32f(uint32_t taddr, const float (&f)[32]) {
+  uint32_t v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(f[i]);
+  tmem_st32(taddr, v);
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -184,8 +202,29 @@ __device__ __forceinline__ void write_operand_row(uint32_t a_hi, uint32_t a_lo, 
   }
 }
 
-template <int ACT>
-__device__ __forceinline__ float act_t(float x) { return act_apply_t<ACT>(x); }
+// Transcendental activations are real function calls: inlining erff/tanhf/expf at every element of the unrolled
+// epilogue made the kernel 600 KB of SASS and the profile was dominated by instruction-cache misses.
+__device__ __noinline__ float act_slow(float x, int act) {
+  if (act == MIL_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+  if (act == MIL_ACT_TANH) return tanhf(x);
+  if (act == MIL_ACT_SIGMOID) return 1.f / (1.f + expf(-x));
+  return x;
+}
+// v[i] = act(v[i] + bias[i]); bias points into shared memory (broadcast reads)
+__device__ __forceinline__ void bias_act32(float (&v)[32], const float* bias, int act) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + i);
+    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+  }
+  if (act == MIL_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (act != MIL_ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = act_slow(v[i], act);
+  }
+}
 
 // column sums over the 32 lanes of a warp of v[0..31] (one value per column per lane): afterwards lane j holds sum_rows v_row[j].
 __device__ __forceinline__ float warp_transpose_sum(float (&v)[32]) {
@@ -224,6 +263,10 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
   float* s_part = reinterpret_cast<float*>(sMisc + 256);   // [2][128] partial attention logits (+ [2][128][4] t partials)
   float* t_part = s_part + 256;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sMisc + 256 + 1024 + 4096);
+  float* c_b1 = reinterpret_cast<float*>(sMisc + 256 + 1024 + 4096 + 16);   // [512] feature bias
+  float* c_ba = c_b1 + HMAX;                                                 // [128] attention bias
+  float* c_wc = c_ba + 128;                                                  // [128] attention output weights
+  float* p_acc = c_wc + 128;                                                 // [8 warps][8 chunks][32 lanes] pooled partial sums
 
   // barrier indices
   const uint32_t bar0 = smem_u32(bars);
@@ -260,6 +303,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         for (int ks = 0; ks < KS; ++ks, ++it) {
           const uint32_t s = it % XS, ph = (it / XS) & 1;
           mbar_wait(BAR(B_XEMPTY + s), ph ^ 1, p.err, 1);
+          if (p.dbg & 2) { mbar_arrive(BAR(B_XFULL + s)); continue; }
           mbar_expect_tx(BAR(B_XFULL + s), X_SLOT_BYTES);
           tma_load_2d(smem_u32(sX + s * X_SLOT_BYTES), &mapX, BAR(B_XFULL + s), ks * BK, (int)(tile * BM));
         }
@@ -274,6 +318,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         for (int ks = 0; ks < KS; ++ks, ++it) {
           const uint32_t s = it % NST, ph = (it / NST) & 1;
           mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 2);
+          if (p.dbg & 1) { mbar_arrive(BAR(B_BFULL + s)); continue; }
           mbar_expect_tx(BAR(B_BFULL + s), (uint32_t)(NOP * p.nout * BK * 2));
           const uint32_t dst = smem_u32(sB + s * B_STAGE);
           for (int b = 0; b < nbox; ++b) {
@@ -284,6 +329,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         for (int c = 0; c < NCH2; ++c, ++it) {
           const uint32_t s = it % NST, ph = (it / NST) & 1;
           mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 3);
+          if (p.dbg & 1) { mbar_arrive(BAR(B_BFULL + s)); continue; }
           mbar_expect_tx(BAR(B_BFULL + s), (uint32_t)(NOP * p.Da * BK * 2));
           const uint32_t dst = smem_u32(sB + s * B_STAGE);
           tma_load_2d(dst, &mapAh, BAR(B_BFULL + s), c * BK, 0);
@@ -308,6 +354,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
           const uint32_t a0 = smem_u32(sA + s * A_STAGE), b0 = smem_u32(sB + s * B_STAGE);
 #pragma unroll
           for (int k16 = 0; k16 < 2; ++k16) {
+            if (p.dbg & 4) break;
             for (int hf = 0; hf < nhalf; ++hf) {
               const uint32_t acc = (ks | k16) ? 1u : 0u;
               const uint32_t d = tmem + (uint32_t)(hf * 256);
@@ -370,7 +417,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         }
         mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 11);
         const uint32_t a_hi = smem_u32(sA + s * A_STAGE);
-        write_operand_row<FP16, LO>(a_hi, a_hi + A_OP_BYTES, row, x);
+        if (!(p.dbg & 8)) write_operand_row<FP16, LO>(a_hi, a_hi + A_OP_BYTES, row, x);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) { mbar_arrive(BAR(B_AFULL + s)); mbar_arrive(BAR(B_XEMPTY + xs)); }
@@ -383,7 +430,14 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const int half = (warp - EPI_WARP0) >> 2;               // two warps per quarter split the columns
     const int row = q * 32 + lane;                          // row inside the tile
     const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+    const int et = threadIdx.x - EPI_WARP0 * 32;            // 0..255
     uint32_t tl = 0, ita = 0;
+
+    // per-column constants -> shared memory (broadcast reads in the hot loops)
+    for (int i = et; i < HMAX; i += 256) c_b1[i] = p.b1 ? p.b1[i] : 0.f;
+    if (MODE == MODE_FUSED)
+      for (int i = et; i < 128; i += 256) { c_ba[i] = p.ba ? p.ba[i] : 0.f; c_wc[i] = p.wc[i]; }
+    named_bar_sync(1, 256);
 
     if (MODE == MODE_STORE) {
       const int nch = p.nout / 32;
@@ -391,21 +445,15 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         mbar_wait(BAR(B_ACCFULL), tl & 1, p.err, 12);
         tc_fence_after();
         const int64_t grow = tile * BM + row;
+#pragma unroll 1
         for (int c = half; c < nch; c += 2) {
-          uint32_t v[32];
-          tmem_ld32(tq + (uint32_t)(c * 32), v);
-          tmem_wait_ld();
+          float hv[32];
+          tmem_ld32f(tq + (uint32_t)(c * 32), hv);
+          bias_act32(hv, c_b1 + c * 32, p.act);
           if (grow < p.N) {
             float* dst = p.c_out + grow * p.ldc + c * 32;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o;
-              o.x = act_apply(__uint_as_float(v[j]) + (p.b1 ? p.b1[c * 32 + j] : 0.f), p.act);
-              o.y = act_apply(__uint_as_float(v[j + 1]) + (p.b1 ? p.b1[c * 32 + j + 1] : 0.f), p.act);
-              o.z = act_apply(__uint_as_float(v[j + 2]) + (p.b1 ? p.b1[c * 32 + j + 2] : 0.f), p.act);
-              o.w = act_apply(__uint_as_float(v[j + 3]) + (p.b1 ? p.b1[c * 32 + j + 3] : 0.f), p.act);
-              *reinterpret_cast<float4*>(dst + j) = o;
-            }
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(hv[j], hv[j + 1], hv[j + 2], hv[j + 3]);
           }
         }
         tc_fence_before();
@@ -413,11 +461,12 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         if (lane == 0) mbar_arrive(BAR(B_ACCEMPTY));
       }
     } else {
-      // running online-softmax state of this warp: rows = its 32 lanes, columns = its 8 chunks (chunk c = 2 j + half)
+      // running online-softmax state of this warp: rows = its 32 lanes, columns = its 8 chunks (chunk c = 2 j + half);
+      // the pooled partial sums live in shared memory: prun[j * 32 + lane] = column (2 j + half) * 32 + lane
       float m_run = -INFINITY, l_run = 0.f;
-      float p_run[8];
+      float* prun = p_acc + (warp - EPI_WARP0) * 256;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) p_run[j] = 0.f;
+      for (int j = 0; j < 8; ++j) prun[j * 32 + lane] = 0.f;
       const float bc = p.bc ? p.bc[0] : 0.f;
 
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
@@ -431,11 +480,8 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int c = 2 * j + half;
-          uint32_t v[32];
-          tmem_ld32(tq + (uint32_t)(c * 32), v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) keep_h[j][i] = act_apply(__uint_as_float(v[i]) + p.b1[c * 32 + i], p.act);
+          tmem_ld32f(tq + (uint32_t)(c * 32), keep_h[j]);
+          bias_act32(keep_h[j], c_b1 + c * 32, p.act);
         }
         tc_fence_before();
         __syncwarp();
@@ -443,35 +489,23 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 
         // E2: h chunk -> 16-bit operand tiles for GEMM2 (+ h back into TMEM for the pooling pass, + optional outputs)
         float tacc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = 2 * j + half;
-          float hv[32];
-          if (j < 2) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) hv[i] = keep_h[j][i];
-          } else {
-            uint32_t v[32];
-            tmem_ld32(tq + (uint32_t)(c * 32), v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              hv[i] = act_apply(__uint_as_float(v[i]) + p.b1[c * 32 + i], p.act);
-              v[i] = __float_as_uint(hv[i]);
-            }
-            tmem_st32(tq + (uint32_t)(c * 32), v);
-          }
+        auto emit_chunk = [&](int c, const float (&hv)[32]) {
           if (p.h_out && grow < p.N) {
             float* dst = p.h_out + grow * HMAX + c * 32;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(hv[i], hv[i + 1], hv[i + 2], hv[i + 3]);
           }
           if (p.t_out) {
+#pragma unroll 1
             for (int cc = 0; cc < p.C; ++cc) {
-              float a = tacc[cc];
+              const float4* wp = reinterpret_cast<const float4*>(p.Wp + cc * HMAX + c * 32);
+              float a = 0.f;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) a = fmaf(hv[i], p.Wp[cc * HMAX + c * 32 + i], a);
-              tacc[cc] = a;
+              for (int i = 0; i < 8; ++i) {
+                const float4 w4 = __ldg(wp + i);
+                a = fmaf(hv[4 * i], w4.x, a); a = fmaf(hv[4 * i + 1], w4.y, a); a = fmaf(hv[4 * i + 2], w4.z, a); a = fmaf(hv[4 * i + 3], w4.w, a);
+              }
+              tacc[cc] += a;
             }
           }
           const uint32_t s = (ita + c) % NST, ph = ((ita + c) / NST) & 1;
@@ -481,6 +515,17 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_AFULL + s));
+        };
+        emit_chunk(half, keep_h[0]);
+        emit_chunk(2 + half, keep_h[1]);
+#pragma unroll 1
+        for (int j = 2; j < 8; ++j) {
+          const int c = 2 * j + half;
+          float hv[32];
+          tmem_ld32f(tq + (uint32_t)(c * 32), hv);
+          bias_act32(hv, c_b1 + c * 32, p.act);
+          tmem_st32f(tq + (uint32_t)(c * 32), hv);
+          emit_chunk(c, hv);
         }
         ita += NCH2;
         tmem_wait_st();
@@ -489,17 +534,14 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         mbar_wait(BAR(B_UFULL), tl & 1, p.err, 15);
         tc_fence_after();
         float sp = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < 2; ++j) {
           const int c0 = half * 64 + j * 32;
-          uint32_t v[32];
-          tmem_ld32(tq + (uint32_t)c0, v);
-          tmem_wait_ld();
+          float uv[32];
+          tmem_ld32f(tq + (uint32_t)c0, uv);
+          bias_act32(uv, c_ba + c0, p.att_act);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float u = __uint_as_float(v[i]) + (p.ba ? p.ba[c0 + i] : 0.f);
-            sp = fmaf(act_apply(u, p.att_act), p.wc[c0 + i], sp);
-          }
+          for (int i = 0; i < 32; ++i) sp = fmaf(uv[i], c_wc[c0 + i], sp);
         }
         s_part[half * 128 + row] = sp;
         if (p.t_out)
@@ -527,20 +569,19 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 
         // E4: p += sum_rows w * h  (h from registers for the vacated columns, from TMEM otherwise)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) keep_h[j][i] *= w;
+          prun[j * 32 + lane] = prun[j * 32 + lane] * scale + warp_transpose_sum(keep_h[j]);
+        }
+#pragma unroll 1
+        for (int j = 2; j < 8; ++j) {
           const int c = 2 * j + half;
           float hv[32];
-          if (j < 2) {
+          tmem_ld32f(tq + (uint32_t)(c * 32), hv);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) hv[i] = keep_h[j][i] * w;
-          } else {
-            uint32_t v[32];
-            tmem_ld32(tq + (uint32_t)(c * 32), v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) hv[i] = __uint_as_float(v[i]) * w;
-          }
-          p_run[j] = p_run[j] * scale + warp_transpose_sum(hv);
+          for (int i = 0; i < 32; ++i) hv[i] *= w;
+          prun[j * 32 + lane] = prun[j * 32 + lane] * scale + warp_transpose_sum(hv);
         }
         tc_fence_before();
         __syncwarp();
@@ -554,22 +595,19 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       if (half == 0 && lane == 0) { red_m[q] = m_run; red_l[q] = l_run; }
       named_bar_sync(1, 256);
       const float m_cta = fmaxf(fmaxf(red_m[0], red_m[1]), fmaxf(red_m[2], red_m[3]));
-      const float f = (m_run > -INFINITY) ? expf(m_run - m_cta) : 0.f;
-      float* pb = t_part;                                   // [4][512] floats = 8 KB?  no: t_part is 4 KB -> use 2 passes over quarters
       float* out = p.part + (int64_t)blockIdx.x * (2 + HMAX);
-      // quarter by quarter accumulation through a [512] shared vector (fixed order -> deterministic)
-      for (int qq = 0; qq < 4; ++qq) {
-        if (q == qq) {
+      // column c = (2 j + half) * 32 + lane lives in prun of warp (half * 4 + q'), q' = 0..3: sum the quarters in fixed order
+      for (int c = et; c < HMAX; c += 256) {
+        const int ch = c >> 5, ln = c & 31, hf = ch & 1, j = ch >> 1;
+        float v = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = (2 * j + half) * 32 + lane;
-            pb[col] = (qq == 0 ? 0.f : pb[col]) + p_run[j] * f;
-          }
+        for (int qq = 0; qq < 4; ++qq) {
+          const float f = (red_m[qq] > -INFINITY) ? expf(red_m[qq] - m_cta) : 0.f;
+          v = fmaf(p_acc[(hf * 4 + qq) * 256 + j * 32 + ln], f, v);
         }
-        named_bar_sync(1, 256);
+        out[2 + c] = v;
       }
-      for (int c = threadIdx.x - EPI_WARP0 * 32; c < HMAX; c += 256) out[2 + c] = pb[c];
-      if (threadIdx.x == EPI_WARP0 * 32) {
+      if (et == 0) {
         float l = 0.f;
         for (int i = 0; i < 4; ++i) l += (red_m[i] > -INFINITY) ? red_l[i] * expf(red_m[i] - m_cta) : 0.f;
         out[0] = m_cta;
@@ -632,16 +670,37 @@ static int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, c
   return 0;
 }
 
+// optional kernel-only timing (bench.py roofline): CUDA events recorded on the launching stream around the fused kernel
+static bool g_profile = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+
 template <int NPROD, bool FP16, int NST, int MODE>
 static int launch_fused(const CUtensorMap& mx, const CUtensorMap& mwh, const CUtensorMap& mwl, const CUtensorMap& mah, const CUtensorMap& mal,
                         const FusedParams& p, int grid, cudaStream_t stream) {
   constexpr int NOP = NPROD == 3 ? 2 : 1;
-  const size_t smem = 1024 + (size_t)XS * X_SLOT_BYTES + (size_t)NST * NOP * (A_OP_BYTES + B_OP_BYTES) + 256 + 1024 + 4096 + 16;
+  const size_t smem = 1024 + (size_t)XS * X_SLOT_BYTES + (size_t)NST * NOP * (A_OP_BYTES + B_OP_BYTES) + 256 + 1024 + 4096 + 16 + (HMAX + 256) * 4 + 8 * 256 * 4;
   auto kern = mil_fused_kernel<NPROD, FP16, NST, MODE>;
-  MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_set = false;
+  if (!attr_set) {
+    MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
   kern<<<grid, NUM_THREADS, smem, stream>>>(mx, mwh, mwl, mah, mal, p);
+  if (g_profile) { cudaEventRecord(e1, stream); g_prof_events.push_back({e0, e1}); }
   MIL_LAUNCH_CHECK();
   return 0;
+}
+
+static int debug_mask() {
+  const char* e = getenv("MHIMK_DEBUG");
+  return e ? atoi(e) : 0;
+}
+static int grid_override(int grid) {
+  const char* e = getenv("MHIMK_GRID");
+  const int g = e ? atoi(e) : 0;
+  return (g > 0 && g < grid) ? g : grid;
 }
 
 static int dispatch_fused(int precision, int mode, const CUtensorMap& mx, const CUtensorMap& mwh, const CUtensorMap& mwl, const CUtensorMap& mah,
@@ -671,6 +730,22 @@ using namespace mil;
 
 extern "C" int mil_fused_num_partials(void) { return num_sms(); }
 
+extern "C" void mil_profile_enable(int on) { g_profile = on != 0; }
+// Synchronises the recorded event pairs; returns their count and writes the summed kernel time in ms.
+extern "C" int mil_profile_collect(double* total_ms) {
+  double tot = 0.0;
+  int n = 0;
+  for (auto& ev : g_prof_events) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) { tot += ms; ++n; }
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  g_prof_events.clear();
+  if (total_ms) *total_ms = tot;
+  return n;
+}
+
 extern "C" size_t mil_fused_workspace_bytes(int D, int H, int Da, int gated) {
   (void)gated;
   return ((size_t)H * D + (size_t)Da * H) * 2 /*hi+lo*/ * sizeof(uint16_t) + 1024 + sizeof(int) * 4;
@@ -679,7 +754,7 @@ extern "C" size_t mil_fused_workspace_bytes(int D, int H, int Da, int gated) {
 extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, const float* W1, const float* b1, int act, const float* Wa,
                                        const float* ba, const float* Wb, const float* bb, int Da, int att_act, const float* wc, const float* bc,
                                        const uint8_t* keep, const float* Wp, int C, float* s_out, float* t_out, float* h_out, float* part,
-                                       float* stats, float* pooled, void* ws, size_t ws_bytes, int precision, mil_stream_t stream_) {
+                                       float* stats, float* pooled, void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MIL_CHECK_ARG(mil_device_supported(), "mil_abmil_fused_fwd_f32: needs a compute-capability 10.x device (tcgen05/TMEM/TMA)");
   MIL_CHECK_ARG(X && W1 && b1 && Wa && wc && part && stats && pooled && ws, "mil_abmil_fused_fwd_f32: null argument");
@@ -700,9 +775,11 @@ extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, 
   uint16_t* wal = wah + (size_t)Da * H;
   int* err = (int*)(wal + (size_t)Da * H);
   int rc;
-  if ((rc = split_weights(W1, (int64_t)H * D, w1h, w1l, precision, stream))) return rc;
-  if ((rc = split_weights(Wa, (int64_t)Da * H, wah, wal, precision, stream))) return rc;
-  MIL_CUDA(cudaMemsetAsync(err, 0, sizeof(int), stream));
+  if (!ws_ready) {   // 16-bit hi/lo images of the weights: reusable across calls until the weights change (ws_ready = 1)
+    if ((rc = split_weights(W1, (int64_t)H * D, w1h, w1l, precision, stream))) return rc;
+    if ((rc = split_weights(Wa, (int64_t)Da * H, wah, wal, precision, stream))) return rc;
+    MIL_CUDA(cudaMemsetAsync(err, 0, sizeof(int), stream));
+  }
 
   const CUtensorMapDataType dt16 = precision == MIL_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap mx, mwh, mwl, mah, mal;
@@ -715,9 +792,9 @@ extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, 
   FusedParams p;
   p.N = N; p.D = D; p.nout = H; p.Da = Da; p.act = act; p.att_act = att_act;
   p.b1 = b1; p.ba = ba; p.wc = wc; p.bc = bc; p.keep = keep; p.Wp = Wp; p.C = t_out ? C : 0;
-  p.s_out = s_out; p.t_out = t_out; p.h_out = h_out; p.part = part; p.c_out = nullptr; p.ldc = 0; p.err = err;
+  p.s_out = s_out; p.t_out = t_out; p.h_out = h_out; p.part = part; p.c_out = nullptr; p.ldc = 0; p.err = err; p.dbg = debug_mask();
   const int64_t n_tiles = (N + BM - 1) / BM;
-  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+  const int grid = grid_override((int)(n_tiles < num_sms() ? n_tiles : num_sms()));
   if ((rc = dispatch_fused(precision, MODE_FUSED, mx, mwh, mwl, mah, mal, p, grid, stream))) return rc;
   return mil_pool_merge_f32(part, grid, H, stats, pooled, stream_);
 }
@@ -746,8 +823,8 @@ extern "C" int mil_umma_selftest_f32(const float* A, const float* B, float* C, i
   FusedParams p;
   p.N = M; p.D = K; p.nout = N; p.Da = 128; p.act = MIL_ACT_NONE; p.att_act = MIL_ACT_NONE;
   p.b1 = nullptr; p.ba = nullptr; p.wc = nullptr; p.bc = nullptr; p.keep = nullptr; p.Wp = nullptr; p.C = 0;
-  p.s_out = nullptr; p.t_out = nullptr; p.h_out = nullptr; p.part = nullptr; p.c_out = C; p.ldc = N; p.err = err;
+  p.s_out = nullptr; p.t_out = nullptr; p.h_out = nullptr; p.part = nullptr; p.c_out = C; p.ldc = N; p.err = err; p.dbg = debug_mask();
   const int64_t n_tiles = ((int64_t)M + BM - 1) / BM;
-  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+  const int grid = grid_override((int)(n_tiles < num_sms() ? n_tiles : num_sms()));
   return dispatch_fused(precision, MODE_STORE, mx, mwh, mwl, mwh, mwl, p, grid, stream);
 }

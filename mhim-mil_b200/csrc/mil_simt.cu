@@ -250,38 +250,48 @@ __global__ void __launch_bounds__(POOL_THREADS) softmax_pool_partial_kernel(cons
   }
 }
 
-// one block; merges n_part partials (m_i, l_i, P_i[H])
-__global__ void pool_merge_kernel(const float* __restrict__ part, int n_part, int H, float* __restrict__ stats, float* __restrict__ pooled) {
-  __shared__ float sm[32];
-  __shared__ float sl[32];
-  const int stride = 2 + H;
+// Merge n_part partials (m_i, l_i, P_i[H]).  Grid: one block per 64 columns; block = 64 columns x 4 row groups.
+// Every block recomputes the (tiny) global max / denominator so no second launch or grid sync is needed.
+constexpr int MERGE_COLS = 64, MERGE_GROUPS = 4, MERGE_MAXP = 1024;
+__global__ void __launch_bounds__(MERGE_COLS * MERGE_GROUPS) pool_merge_kernel(const float* __restrict__ part, int n_part, int H,
+                                                                                float* __restrict__ stats, float* __restrict__ pooled) {
+  __shared__ float wgt[MERGE_MAXP];              // exp(m_i - m) (0 for idle partials)
+  __shared__ float red[8];
+  __shared__ float acc[MERGE_GROUPS][MERGE_COLS];
+  const int stride = 2 + H, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float m = -INFINITY;
-  for (int i = threadIdx.x; i < n_part; i += blockDim.x)
+  for (int i = tid; i < n_part; i += blockDim.x)
     if (part[(int64_t)i * stride + 1] > 0.f) m = fmaxf(m, part[(int64_t)i * stride]);
   m = warp_max(m);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  if (lane == 0) red[warp] = m;
   __syncthreads();
-  m = -INFINITY;
-  for (int w = 0; w < (blockDim.x >> 5); ++w) m = fmaxf(m, sm[w]);
+  m = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
   float l = 0.f;
-  for (int i = threadIdx.x; i < n_part; i += blockDim.x) {
+  for (int i = tid; i < n_part; i += blockDim.x) {
     const float li = part[(int64_t)i * stride + 1];
-    if (li > 0.f) l += li * expf(part[(int64_t)i * stride] - m);
+    const float w = li > 0.f ? expf(part[(int64_t)i * stride] - m) : 0.f;
+    wgt[i] = w;
+    l += li * w;
   }
   l = warp_sum(l);
-  if ((threadIdx.x & 31) == 0) sl[threadIdx.x >> 5] = l;
+  if (lane == 0) red[warp] = l;
   __syncthreads();
   l = 0.f;
-  for (int w = 0; w < (blockDim.x >> 5); ++w) l += sl[w];
-  for (int c = threadIdx.x; c < H; c += blockDim.x) {
-    float v = 0.f;
-    for (int i = 0; i < n_part; ++i) {
-      const float li = part[(int64_t)i * stride + 1];
-      if (li > 0.f) v = fmaf(part[(int64_t)i * stride + 2 + c], expf(part[(int64_t)i * stride] - m), v);
-    }
-    pooled[c] = v / l;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) l += red[w];   // fixed order: identical in every block
+  const int col = blockIdx.x * MERGE_COLS + (tid & (MERGE_COLS - 1)), grp = tid / MERGE_COLS;
+  float v = 0.f;
+  if (col < H) {
+    const int per = (n_part + MERGE_GROUPS - 1) / MERGE_GROUPS;
+    const int i0 = grp * per, i1 = min(n_part, i0 + per);
+#pragma unroll 4
+    for (int i = i0; i < i1; ++i) v = fmaf(part[(int64_t)i * stride + 2 + col], wgt[i], v);
   }
-  if (threadIdx.x == 0) { stats[0] = m; stats[1] = l; }
+  acc[grp][tid & (MERGE_COLS - 1)] = v;
+  __syncthreads();
+  if (grp == 0 && col < H) pooled[col] = (acc[0][tid] + acc[1][tid] + acc[2][tid] + acc[3][tid]) / l;
+  if (blockIdx.x == 0 && tid == 0) { stats[0] = m; stats[1] = l; }
 }
 
 __global__ void attn_norm_kernel(const float* __restrict__ s, int64_t s_stride, int64_t L, const uint8_t* __restrict__ keep,
@@ -416,8 +426,8 @@ extern "C" int mil_pool_num_partials(int64_t L) {
 }
 
 extern "C" int mil_pool_merge_f32(const float* part, int n_part, int H, float* stats, float* pooled, mil_stream_t stream) {
-  MIL_CHECK_ARG(part && stats && pooled && n_part > 0 && H > 0, "mil_pool_merge_f32: bad arguments");
-  pool_merge_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(part, n_part, H, stats, pooled);
+  MIL_CHECK_ARG(part && stats && pooled && n_part > 0 && n_part <= MERGE_MAXP && H > 0, "mil_pool_merge_f32: bad arguments (n_part <= %d)", MERGE_MAXP);
+  pool_merge_kernel<<<(H + MERGE_COLS - 1) / MERGE_COLS, MERGE_COLS * MERGE_GROUPS, 0, (cudaStream_t)stream>>>(part, n_part, H, stats, pooled);
   MIL_LAUNCH_CHECK();
   return 0;
 }
@@ -436,7 +446,7 @@ extern "C" int mil_softmax_pool_fwd_f32(const float* s, int64_t s_stride, const 
 #undef CASE
   }
   MIL_LAUNCH_CHECK();
-  pool_merge_kernel<<<1, 512, 0, stream>>>(part, np, H, stats, pooled);
+  pool_merge_kernel<<<(H + MERGE_COLS - 1) / MERGE_COLS, MERGE_COLS * MERGE_GROUPS, 0, stream>>>(part, np, H, stats, pooled);
   MIL_LAUNCH_CHECK();
   if (attn_out) {
     attn_norm_kernel<<<(unsigned)((L + 255) / 256), 256, 0, stream>>>(s, s_stride, L, keep, stats, attn_out);

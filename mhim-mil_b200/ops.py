@@ -201,6 +201,27 @@ def mask_from_indices(idx: torch.Tensor, n: int):
 # --------------------------------------------------------------------------------------------------------------
 # fused tcgen05 forward
 # --------------------------------------------------------------------------------------------------------------
+# 16-bit hi/lo weight images for the fused pass, cached per (weight tensor OBJECTS, precision).  An entry is valid only
+# while both tensors are the very same live objects (weakrefs; a recycled address is not enough) and their autograd
+# version counters are unchanged (an optimizer step / load_state_dict / copy_ bumps `_version`).
+_WS_CACHE = {}
+
+
+def _fused_workspace(W1, Wa, precision):
+    import weakref
+    L = _lib.lib()
+    key = (id(W1), id(Wa), precision)
+    ver = (W1._version, Wa._version, W1.data_ptr(), Wa.data_ptr(), tuple(W1.shape), tuple(Wa.shape))
+    hit = _WS_CACHE.get(key)
+    if hit is not None and hit[0]() is W1 and hit[1]() is Wa and hit[2] == ver:
+        return hit[3], 1
+    ws = _ws(L.mil_fused_workspace_bytes(W1.shape[1], W1.shape[0], Wa.shape[0], 0), W1.device)
+    if len(_WS_CACHE) > 64:
+        _WS_CACHE.clear()
+    _WS_CACHE[key] = (weakref.ref(W1), weakref.ref(Wa), ver, ws)
+    return ws, 0
+
+
 @torch.no_grad()
 def abmil_fused_forward(x, W1, b1, act, Wa, ba, wc, bc, att_act="tanh", keep=None, Wp=None, want_scores=False, want_h=False,
                         precision: str = DEFAULT_PRECISION):
@@ -214,18 +235,31 @@ def abmil_fused_forward(x, W1, b1, act, Wa, ba, wc, bc, att_act="tanh", keep=Non
     H, Da = W1.shape[0], Wa.shape[0]
     dev = x.device
     npart = L.mil_fused_num_partials()
-    part = torch.zeros((npart, 2 + H), dtype=torch.float32, device=dev)
+    part = torch.empty((npart, 2 + H), dtype=torch.float32, device=dev)
     stats = torch.empty(2, dtype=torch.float32, device=dev)
     pooled = torch.empty(H, dtype=torch.float32, device=dev)
     s = torch.empty(N, dtype=torch.float32, device=dev) if want_scores else None
     C = Wp.shape[0] if Wp is not None else 0
     t = torch.empty((N, C), dtype=torch.float32, device=dev) if Wp is not None else None
     h = torch.empty((N, H), dtype=torch.float32, device=dev) if want_h else None
-    ws = _ws(L.mil_fused_workspace_bytes(D, H, Da, 0), dev)
+    ws, ready = _fused_workspace(W1, Wa, precision)
     check(L.mil_abmil_fused_fwd_f32(ptr(x), N, D, H, ptr(W1), ptr(b1), ACT[act], ptr(Wa), ptr(ba), None, None, Da, ACT[att_act], ptr(wc),
                                     ptr(bc), ptr(keep), ptr(Wp), C, ptr(s), ptr(t), ptr(h), ptr(part), ptr(stats), ptr(pooled), ptr(ws),
-                                    ws.numel(), PREC[precision], stream_ptr()), "mil_abmil_fused_fwd_f32")
+                                    ws.numel(), ready, PREC[precision], stream_ptr()), "mil_abmil_fused_fwd_f32")
     return {"pooled": pooled, "stats": stats, "s": s, "t": t, "h": h, "part": part}
+
+
+def profile_fused(enable: bool):
+    """Bracket every fused-kernel launch with CUDA events (kernel-only time for bench.py's roofline)."""
+    _lib.lib().mil_profile_enable(1 if enable else 0)
+
+
+def profile_collect():
+    """-> (number of timed fused launches, their summed duration in ms); synchronises the recorded events."""
+    import ctypes
+    tot = ctypes.c_double(0.0)
+    n = _lib.lib().mil_profile_collect(ctypes.byref(tot))
+    return n, tot.value
 
 
 @torch.no_grad()
