@@ -1,0 +1,28 @@
+"""PPEG positional encoding used by MHIM's SAttention (reference: modules/emb_position.py:85-120)."""
+import math
+
+import torch
+from torch import nn
+
+
+class PPEG(nn.Module):
+    def __init__(self, dim=512, k=7, conv_1d=False, bias=True):
+        super().__init__()
+        mk = lambda ks: nn.Conv2d(dim, dim, (ks, 1) if conv_1d else ks, 1, (ks // 2, 0) if conv_1d else ks // 2, groups=dim, bias=bias)
+        self.proj, self.proj1, self.proj2 = mk(k), mk(5), mk(3)
+
+    def forward(self, x):
+        if x.dim() == 2:
+            x = x.unsqueeze(0)
+        B, N, Cc = x.shape
+        H = W = int(math.ceil(math.sqrt(N)))
+        add = H * W - N
+        x = torch.cat([x, x[:, :add]], dim=1)                   # wrap-pad to a square
+        if H < 7:                                                # minimum 7x7 grid, zero filled
+            H = W = 7
+            zp = H * W - (N + add)
+            x = torch.cat([x, x.new_zeros(B, zp, Cc)], dim=1)
+            add += zp
+        g = x.transpose(1, 2).reshape(B, Cc, H, W)
+        y = (self.proj(g) + g + self.proj1(g) + self.proj2(g)).flatten(2).transpose(1, 2)
+        return y[:, :-add] if add > 0 else y

@@ -1,0 +1,210 @@
+"""GPU parity of the drop-in modules (same constructors / forward signatures / state_dict keys as the reference) against the
+committed golden vectors made from the live reference and against the CPU oracle."""
+import os
+import types
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cases
+from oracle import mil_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.pt"), weights_only=False)
+TOL = 1e-4            # north-star gate: logits and gradients within 1e-4 relative (max|d| / max|ref| per tensor)
+
+
+@pytest.fixture(scope="module")
+def M():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import mhimk
+    from mhimk import modules
+    return modules
+
+
+def cuda_sd(sd):
+    return {k: v.cuda() for k, v in sd.items()}
+
+
+def check_grads(model, golden, tol=TOL):
+    for k, p in model.named_parameters():
+        if k not in golden:
+            continue
+        g = golden[k]
+        assert p.grad is not None, k
+        if g["norm"] < 1e-6:
+            assert p.grad.norm().item() < 1e-4, k
+            continue
+        assert abs(p.grad.double().norm().item() - g["norm"]) <= tol * g["norm"], (k, p.grad.double().norm().item(), g["norm"])
+        scale = max(g["head"].abs().max().item(), g["norm"] / (p.numel() ** 0.5))
+        assert float((p.grad.flatten()[:8].cpu() - g["head"]).abs().max()) <= 10 * tol * scale, k
+
+
+@pytest.mark.parametrize("name", list(G["abmil"]))
+def test_dattention_eval_fused_and_train(M, name):
+    act, n, kind = name.split("_")
+    i = list(G["abmil"]).index(name)
+    g = G["abmil"][name]
+    sd, x = cases.abmil_state(11 + i), cases.make_bag(11 + i + 1000, int(n), 1024, kind)
+    m = M.DAttention(1024, 2, dropout=0.0, act=act).cuda()
+    m.load_state_dict(cuda_sd(sd), strict=True)
+    m.eval()
+    with torch.no_grad():                                             # fused tcgen05 path
+        logits, attn, actv = m(x.cuda(), return_attn=True, return_act=True)
+        lg2, feat = m(x.cuda(), return_img_feat=True)
+    assert cases.rel_err(logits, g["logits"]) < TOL and cases.rel_err(lg2, g["logits"]) < TOL
+    assert cases.rel_err(feat, g["pooled"]) < TOL
+    assert cases.rel_err(attn[0, :16], g["attn_head"]) < 3 * TOL
+    assert tuple(actv.shape) == (1, int(n), 512)
+    m.train()                                                          # composed path with CUDA backward
+    logits = m(x.cuda())
+    assert cases.rel_err(logits, g["logits"]) < TOL
+    F.cross_entropy(logits, torch.tensor([1]).cuda()).backward()
+    check_grads(m, g["grads"])
+
+
+@pytest.mark.parametrize("name", list(G["gated"]))
+def test_attention_gated_fwd_bwd(M, name):
+    """BASELINE config 0: ABMIL gated-attention fwd/bwd on a synthetic bag (N=1024, D=1024)."""
+    act, n, kind = name.split("_")
+    i = list(G["gated"]).index(name)
+    g = G["gated"][name]
+    sd, x = cases.gated_state(31 + i), cases.make_bag(31 + i + 1000, int(n), 1024, kind)
+    m = M.AttentionGated(1024, 2, act=act, dropout=0.0).cuda()
+    m.load_state_dict(cuda_sd(sd), strict=True)
+    m.train()
+    x2 = x[0].cuda()                                                   # 2-D input is unsqueezed in place like the reference
+    logits = m(x2)
+    assert x2.dim() == 3
+    assert cases.rel_err(logits, g["logits"]) < TOL
+    F.cross_entropy(logits, torch.tensor([1]).cuda()).backward()
+    check_grads(m, g["grads"])
+
+
+MHIM_CASES = {"attn_2000": ("attn", 2000, 1024, 51), "attn_33": ("attn", 33, 1024, 52), "dsmil_1000": ("dsmil", 1000, 1536, 61),
+              "selfattn_600": ("selfattn", 600, 1024, 71)}
+
+
+def build_mhim(M, base, d, seed):
+    m = M.MHIM(**dict(cases.MHIM_KW, baseline=base, input_dim=d, dropout=0.0)).cuda()
+    m.load_state_dict(cuda_sd(cases.mhim_state(seed, base, D=d)), strict=True)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0                                                # golden was made with every dropout neutralised
+    return m
+
+
+@pytest.mark.parametrize("name", list(MHIM_CASES))
+def test_mhim_teacher_student_test_pure(M, name):
+    base, n, d, seed = MHIM_CASES[name]
+    g = G["mhim"][name]
+    tol = 3e-4 if base == "selfattn" else TOL
+    stu, tea = build_mhim(M, base, d, seed), build_mhim(M, base, d, seed + 1)
+    stu.train(), tea.train()
+    x = cases.make_bag(seed + 1000, n, d).cuda()
+    cls_tea, score = tea.forward_teacher(x)
+    assert cases.rel_err(cls_tea, g["cls_tea"]) < tol
+    assert cases.rel_err(score, g["score"]) < tol
+    # index parity is defined on equal inputs: feed the reference's own fp32 scores
+    score_ref = g["score"].cuda()
+    lk, ids = stu.get_mask(n, 0, score_ref)
+    assert lk == g["mask_len_keep"] and cases.tensor_digest(ids) == g["mask_ids_digest"]      # bit-exact mask indices
+    torch.manual_seed(seed + 7)
+    stu.merge._noise = lambda L, dev: torch.rand(L).to(dev)            # the CPU random stream the reference consumed
+    tcf = g["cls_tea"].cuda()
+    tcf = tcf[0] if base == "dsmil" else tcf
+    logits, loss, ps, len_keep = stu(x, score_ref, tcf, i=0)
+    assert (ps, len_keep) == (g["ps"], g["len_keep"])
+    if base == "dsmil":
+        for a, b in zip(logits, g["logits"]):
+            assert cases.rel_err(a, b) < tol
+        lt = 0.5 * logits[0].view(1, -1) + 0.5 * logits[1].view(1, -1)
+    else:
+        assert cases.rel_err(logits, g["logits"]) < tol
+        lt = logits
+    assert cases.rel_err(loss, g["loss"]) < tol
+    assert cases.rel_err(stu.merge.global_q_mm.data[0, :, :8], g["new_global_q_head"]) < tol
+    (F.cross_entropy(lt, torch.tensor([1]).cuda()) + 0.5 * loss).backward()
+    check_grads(stu, g["grads"], tol=1e-3 if base == "selfattn" else 2e-4)
+    stu.eval()
+    stu.merge.global_q_mm.data.copy_(cases.mhim_state(seed, base, D=d)["merge.global_q_mm"].cuda())
+    ft, pu = stu.forward_test(x), stu.pure(x)
+    if base == "dsmil":
+        for a, b in zip(ft[0], g["forward_test"]):
+            assert cases.rel_err(a, b) < tol
+        for a, b in zip(pu, g["pure_eval"]):
+            assert cases.rel_err(a, b) < tol
+    else:
+        assert cases.rel_err(ft, g["forward_test"]) < tol and cases.rel_err(pu, g["pure_eval"]) < tol
+
+
+def test_mhim_teacher_scores_topk_tie_aware(M):
+    """End to end the CAM scores sit on a few hundred fp32 values around 0.5: the kept set computed from OUR
+    scores must agree with the one from the reference scores wherever values are strictly separated."""
+    base, n, d, seed = MHIM_CASES["attn_2000"]
+    g = G["mhim"]["attn_2000"]
+    tea = build_mhim(M, base, d, seed + 1).eval()
+    _, score = tea.forward_teacher(cases.make_bag(seed + 1000, n, d).cuda())
+    ref = g["score"][0]
+    k = O.topk_count(n, 0.03)
+    mine = set(torch.topk(score[0].cpu(), k).indices.tolist())
+    thr = torch.topk(ref, k).values.min()
+    margin = 4 * 5.96e-8
+    must_have = set(torch.nonzero(ref > thr + margin).flatten().tolist())
+    may_have = set(torch.nonzero(ref >= thr - margin).flatten().tolist())
+    assert must_have <= mine <= may_have
+
+
+def test_transmil_and_milnet_eval(M):
+    g = G["transmil"]["700"]
+    t = M.TransMIL(1024, 2, dropout=0.0, act="relu").cuda().eval()
+    t.load_state_dict(cuda_sd(cases.transmil_state(81)), strict=True)
+    for mod in t.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    with torch.no_grad():
+        logits, attn, v = t(cases.make_bag(1081, 700, 1024).cuda(), return_attn=True, return_act=True)
+    assert cases.rel_err(logits, g["logits"]) < 5e-4
+    assert cases.rel_err(attn[0][0, :, :8], g["attn0_head"]) < 5e-4 and cases.rel_err(v[0, :, :2, :4], g["v_head"]) < 5e-4
+    g = G["milnet"]["500"]
+    d = M.MILNet(2, 0.0, "relu", input_dim=1536).cuda().eval()
+    d.load_state_dict(cuda_sd(cases.milnet_state(85)), strict=True)
+    with torch.no_grad():
+        pred, classes = d(cases.make_bag(1085, 500, 1536).cuda())
+    assert cases.rel_err(pred, g["pred"]) < TOL and cases.rel_err(classes, g["classes"]) < TOL
+
+
+def test_common_mil_adapter_tuple(M):
+    import mhimk
+    from mhimk.engines import CommonMIL
+    base, n, d, seed = "attn", 500, 1024, 5
+    stu, tea = build_mhim(M, base, d, seed), build_mhim(M, base, d, seed + 1)
+    stu.train(), tea.train()
+    args = types.SimpleNamespace(model="mhim", baseline="attn", aux_alpha=0.5)
+    bag, label = cases.make_bag(9, n, d).cuda(), torch.tensor([1]).cuda()
+    out = CommonMIL(args).forward_func(args, stu, tea, bag, label, torch.nn.CrossEntropyLoss(), 1, 0, 0, 0, None)
+    logits, lab, aux, patch_num, keep_num, pad_ratio, kn_std = out
+    assert tuple(logits.shape) == (1, 2) and patch_num == n and keep_num == int((n - O.topk_count(n, 0.03)) * 0.8) + 5
+    assert float(aux) > 0 and pad_ratio == 0.0 and kn_std == 0.0
+    stu.eval()
+    lg, _ = CommonMIL(args).validate_func(args, stu, bag, label, None, 1, 0, None)
+    assert tuple(lg.shape) == (1, 2)
+    args2 = types.SimpleNamespace(model="abmil", baseline="attn", aux_alpha=0.0)
+    ab = M.DAttention(1024, 2, dropout=0.0, act="relu").cuda().eval()
+    out2 = CommonMIL(args2).forward_func(args2, ab, None, bag, label, None, 1, 0, 0, 0, None)
+    assert tuple(out2[0].shape) == (1, 2) and out2[3] == n
+
+
+def test_fused_refuses_stale_weight_images(M):
+    """The cached 16-bit weight images must follow in-place weight updates (optimizer steps)."""
+    m = M.DAttention(1024, 2, dropout=0.0, act="relu").cuda().eval()
+    x = cases.make_bag(3, 300, 1024).cuda()
+    with torch.no_grad():
+        a = m(x).clone()
+        m.feature[0].weight.mul_(0.5)
+        b = m(x)
+        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    assert cases.rel_err(b, O.abmil_dattention(sd, x.cpu(), "relu")) < TOL
+    assert cases.rel_err(a, b) > 1e-3
