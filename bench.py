@@ -212,7 +212,7 @@ def main():
                             "note": "mil_fused_kernel alone, CUDA events on its stream inside the C ABI, mean over the timed steps"},
                "e2e": {"value": world * N_INST / (e2e_ms / e2e_steps * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": alg_bytes,
                        "d2h_bytes_per_step": N_CLASSES * 4, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
-               "gpu_launches": args.steps * 3,            # per step: fused kernel, partial merge, classifier GEMM (weight images cached)
+               "gpu_launches": args.steps,                # per step: ONE fused kernel (merge + classifier in its tail; weight images cached)
                "clocks": sampler.summary()}
         if not args.no_cpu_baseline:
             med = time_cpu(5, N_INST)

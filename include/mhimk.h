@@ -55,7 +55,9 @@ int         mil_device_supported(void);
  * t_out     nullable float[N,C]: t_{n,c} = h_n . Wp_c (needs Wp [C,H], C <= 4) -- input of mil_cam_score_f32.
  * h_out     nullable float[N,H]: materialised embedding (training / return_act).
  * part      float[n_part,(2+H)] scratch for the per-CTA partials, n_part = mil_fused_num_partials().
- * stats     float[2] = (m, l); pooled float[H].
+ * stats     float[2] = (m, l); pooled float[H]: written by the last CTA to finish (in-kernel log-sum-exp merge of the partials).
+ * logits    nullable float[n_cls] = Wcls pooled + bcls (classifier fused into the same tail; replaces abmil.py:238 /
+ *           mhim.py:267); Wcls [n_cls, H], bcls nullable.
  * ws / ws_bytes: scratch of at least mil_fused_workspace_bytes(D, H, Da, gated) bytes; it holds the 16-bit hi/lo images of
  *           W1 and Wa.  ws_ready = 0: the images are (re)built by this call; ws_ready = 1: the caller guarantees `ws` was
  *           filled by an earlier call with the same weights and precision (skips two small kernels per bag).
@@ -67,6 +69,7 @@ int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H,
                             const uint8_t* keep, const float* Wp, int C,
                             float* s_out, float* t_out, float* h_out,
                             float* part, float* stats, float* pooled,
+                            const float* Wcls, const float* bcls, int n_cls, float* logits,
                             void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream);
 int    mil_fused_num_partials(void);
 /* Kernel-only timing of the fused pass for the roofline line of bench.py: while enabled, every fused launch is bracketed

@@ -22,7 +22,7 @@ _SIGS = {
     "mil_device_supported": (c_int, []),
     "mil_abmil_fused_fwd_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                        c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "mil_profile_enable": (None, [c_int]),
     "mil_profile_collect": (c_int, [ctypes.POINTER(ctypes.c_double)]),
     "mil_fused_num_partials": (c_int, []),
@@ -77,4 +77,4 @@ def ptr(t):
 
 def stream_ptr():
     import torch
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    return c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))

@@ -50,8 +50,12 @@ struct FusedParams {
   const uint8_t* keep; const float* Wp; int C;
   float* s_out; float* t_out; float* h_out; float* part;
   float* c_out; int64_t ldc;   // MODE_STORE
+  const uint8_t* w1_img; const uint8_t* wa_img;   // pre-swizzled 16-bit weight images (see split_weights_kernel)
+  float* stats; float* pooled; unsigned int* counter;      // in-kernel finalisation by the last CTA to finish
+  const float* Wcls; const float* bcls; int n_cls; float* logits;
   int* err;
-  int dbg;              // MHIMK_DEBUG bitmask (timing attribution only): 1 skip W TMA, 2 skip X TMA, 4 skip MMA, 8 skip convert
+  long long* trace;     // optional [16 tiles][16 slots] clock64 stamps of CTA 0 (MHIMK_TRACE=1), see tools/trace_fused.py
+  int dbg;              // MHIMK_DEBUG bitmask (timing attribution only): 1 skip W1 TMA, 2 skip X TMA, 4 skip GEMM1 MMA, 8 skip convert, 16 skip Wa TMA, 32 skip pooling, 64 skip GEMM2 MMA
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -93,6 +97,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine, no tensor map): one request moves a whole pre-swizzled operand tile
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -154,6 +163,10 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+__device__ __forceinline__ void trace_stamp(const FusedParams& p, uint32_t tl, int slot) {
+  if (p.trace && blockIdx.x == 0 && tl < 16) p.trace[tl * 16 + slot] = clock64();
+}
+
 // K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows are 64 B, 8-row groups are 512 B apart.
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -202,27 +215,45 @@ __device__ __forceinline__ void write_operand_row(uint32_t a_hi, uint32_t a_lo, 
   }
 }
 
-// Transcendental activations are real function calls: inlining erff/tanhf/expf at every element of the unrolled
-// epilogue made the kernel 600 KB of SASS and the profile was dominated by instruction-cache misses.
-__device__ __noinline__ float act_slow(float x, int act) {
-  if (act == MIL_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
-  if (act == MIL_ACT_TANH) return tanhf(x);
-  if (act == MIL_ACT_SIGMOID) return 1.f / (1.f + expf(-x));
-  return x;
+// Short inline transcendental activations (MUFU ex2/rcp based).  Inlining libm's erff/tanhf/expf at every element made the
+// kernel 600 KB of SASS (instruction-cache bound) and calling them out of line cost ~250 cycles per element.
+//   tanh(x)    = 1 - 2 / (1 + e^{2x})                                   |abs err| <~ 5e-7
+//   sigmoid(x) = 1 / (1 + e^{-x})                                       |abs err| <~ 2e-7
+//   erf(z)     = 1 - (a1 t + ... + a5 t^5) e^{-z^2}, t = 1/(1 + p z)    |abs err| <= 1.5e-7 (Abramowitz-Stegun 7.1.26)
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.f - poly * t * __expf(-z * z);
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
 }
-// v[i] = act(v[i] + bias[i]); bias points into shared memory (broadcast reads)
-__device__ __forceinline__ void bias_act32(float (&v)[32], const float* bias, int act) {
+// v[i] = act(v[i] + bias[i]); bias points into shared memory (broadcast reads).  ACT is a compile-time constant in the fused
+// kernel (one variant per instantiation keeps the epilogue small); ACT = -1 selects at run time (store mode only).
+template <int ACT>
+__device__ __forceinline__ void bias_act32(float (&v)[32], const float* bias, int act_rt) {
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
     const float4 b = *reinterpret_cast<const float4*>(bias + i);
     v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
   }
+  const int act = ACT >= 0 ? ACT : act_rt;
   if (act == MIL_ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-  } else if (act != MIL_ACT_NONE) {
+  } else if (act == MIL_ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = act_slow(v[i], act);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+  } else if (act == MIL_ACT_TANH) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = tanh_fast(v[i]);
+  } else if (act == MIL_ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = sigmoid_fast(v[i]);
   }
 }
 
@@ -245,10 +276,9 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32]) {
 // ------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------
-template <int NPROD, bool FP16, int NST, int MODE>
+template <int NPROD, bool FP16, int NST, int MODE, int ACT, int ATT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
-                 const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl, const FusedParams p) {
+mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) {
   constexpr bool LO = NPROD == 3;
   constexpr int NOP = LO ? 2 : 1;                         // operand tiles per stage (hi, lo)
   constexpr uint32_t A_STAGE = NOP * A_OP_BYTES, B_STAGE = NOP * B_OP_BYTES;
@@ -276,6 +306,11 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
   static_assert(B_COUNT * 8 <= 256, "barrier block overflow");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.trace && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.trace[256 + 2 * blockIdx.x] = (long long)gt;
+  }
   const int KS = p.D / BK;                                 // GEMM1 k-steps per tile
   const int NCH2 = (MODE == MODE_FUSED) ? HMAX / BK : 0;   // GEMM2 k-steps per tile (16)
   const int64_t n_tiles = (p.N + BM - 1) / BM;
@@ -288,7 +323,6 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     fence_proxy_async();
   }
   if (warp == 0 && lane == 0) tma_prefetch_desc(&mapX);
-  if (warp == 3 && lane == 0) { tma_prefetch_desc(&mapWh); if (LO) tma_prefetch_desc(&mapWl); }
   if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
@@ -310,30 +344,32 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       }
     }
   } else if (warp == 3) {
-    // ===================== weight producer: L2 -> weight ring (TMA, SWIZZLE_64B) =====================
+    // ===================== weight producer: L2 -> weight ring =====================
+    // The weights were pre-arranged (split_weights_kernel) as the exact shared-memory image of every stage's operand tile
+    // (UMMA K-major SWIZZLE_64B), so each stage is ONE contiguous bulk copy per operand instead of 256-512 64-byte TMA rows.
     if (lane == 0) {
       uint32_t it = 0;
-      const int nbox = (p.nout + 255) / 256, box_rows = p.nout < 256 ? p.nout : 256;
+      const uint32_t w1_tile = (uint32_t)p.nout * BK * 2, wa_tile = (uint32_t)p.Da * BK * 2;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int ks = 0; ks < KS; ++ks, ++it) {
           const uint32_t s = it % NST, ph = (it / NST) & 1;
           mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 2);
           if (p.dbg & 1) { mbar_arrive(BAR(B_BFULL + s)); continue; }
-          mbar_expect_tx(BAR(B_BFULL + s), (uint32_t)(NOP * p.nout * BK * 2));
+          mbar_expect_tx(BAR(B_BFULL + s), NOP * w1_tile);
           const uint32_t dst = smem_u32(sB + s * B_STAGE);
-          for (int b = 0; b < nbox; ++b) {
-            tma_load_2d(dst + b * box_rows * BK * 2, &mapWh, BAR(B_BFULL + s), ks * BK, b * box_rows);
-            if (LO) tma_load_2d(dst + B_OP_BYTES + b * box_rows * BK * 2, &mapWl, BAR(B_BFULL + s), ks * BK, b * box_rows);
-          }
+          const uint8_t* src = p.w1_img + (size_t)ks * NOP * w1_tile;
+          bulk_load(dst, src, w1_tile, BAR(B_BFULL + s));
+          if (LO) bulk_load(dst + B_OP_BYTES, src + w1_tile, w1_tile, BAR(B_BFULL + s));
         }
         for (int c = 0; c < NCH2; ++c, ++it) {
           const uint32_t s = it % NST, ph = (it / NST) & 1;
           mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 3);
-          if (p.dbg & 1) { mbar_arrive(BAR(B_BFULL + s)); continue; }
-          mbar_expect_tx(BAR(B_BFULL + s), (uint32_t)(NOP * p.Da * BK * 2));
+          if (p.dbg & 16) { mbar_arrive(BAR(B_BFULL + s)); continue; }
+          mbar_expect_tx(BAR(B_BFULL + s), NOP * wa_tile);
           const uint32_t dst = smem_u32(sB + s * B_STAGE);
-          tma_load_2d(dst, &mapAh, BAR(B_BFULL + s), c * BK, 0);
-          if (LO) tma_load_2d(dst + B_OP_BYTES, &mapAl, BAR(B_BFULL + s), c * BK, 0);
+          const uint8_t* src = p.wa_img + (size_t)c * NOP * wa_tile;
+          bulk_load(dst, src, wa_tile, BAR(B_BFULL + s));
+          if (LO) bulk_load(dst + B_OP_BYTES, src + wa_tile, wa_tile, BAR(B_BFULL + s));
         }
       }
     }
@@ -346,6 +382,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
         mbar_wait(BAR(B_ACCEMPTY), (tl & 1) ^ 1, p.err, 4);
         tc_fence_after();
+        trace_stamp(p, tl, 0);                               // GEMM1 may start
         for (int ks = 0; ks < KS; ++ks, ++it) {
           const uint32_t s = it % NST, ph = (it / NST) & 1;
           mbar_wait(BAR(B_AFULL + s), ph, p.err, 5);
@@ -370,9 +407,11 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
           umma_commit(BAR(B_EMPTY + s));
         }
         umma_commit(BAR(B_ACCFULL));
+        trace_stamp(p, tl, 1);                               // GEMM1 fully issued
         if (MODE == MODE_FUSED) {
           mbar_wait(BAR(B_TAILFREE), tl & 1, p.err, 7);
           tc_fence_after();
+          trace_stamp(p, tl, 2);                             // GEMM2 may start
           for (int c = 0; c < NCH2; ++c, ++it) {
             const uint32_t s = it % NST, ph = (it / NST) & 1;
             mbar_wait(BAR(B_AFULL + s), ph, p.err, 8);
@@ -381,6 +420,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             const uint32_t a0 = smem_u32(sA + s * A_STAGE), b0 = smem_u32(sB + s * B_STAGE);
 #pragma unroll
             for (int k16 = 0; k16 < 2; ++k16) {
+              if (p.dbg & 64) break;
               const uint32_t acc = (c | k16) ? 1u : 0u;
               const uint64_t ah = make_desc_sw64(a0 + k16 * 32), bh = make_desc_sw64(b0 + k16 * 32);
               umma_f16(tmem, ah, bh, idesc2, acc);
@@ -393,6 +433,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             umma_commit(BAR(B_EMPTY + s));
           }
           umma_commit(BAR(B_UFULL));
+          trace_stamp(p, tl, 3);                             // GEMM2 fully issued
         }
       }
     }
@@ -449,7 +490,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         for (int c = half; c < nch; c += 2) {
           float hv[32];
           tmem_ld32f(tq + (uint32_t)(c * 32), hv);
-          bias_act32(hv, c_b1 + c * 32, p.act);
+          bias_act32<-1>(hv, c_b1 + c * 32, p.act);
           if (grow < p.N) {
             float* dst = p.c_out + grow * p.ldc + c * 32;
 #pragma unroll
@@ -474,6 +515,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         ita += KS;                                          // GEMM1 stages of this tile belong to the converters
         mbar_wait(BAR(B_ACCFULL), tl & 1, p.err, 13);
         tc_fence_after();
+        if (et == 0) trace_stamp(p, tl, 4);                  // accumulator complete
 
         // E1: vacate the first 128 accumulator columns (they become GEMM2's accumulator); keep h for them in registers
         float keep_h[2][32];
@@ -481,11 +523,12 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         for (int j = 0; j < 2; ++j) {
           const int c = 2 * j + half;
           tmem_ld32f(tq + (uint32_t)(c * 32), keep_h[j]);
-          bias_act32(keep_h[j], c_b1 + c * 32, p.act);
+          bias_act32<ACT>(keep_h[j], c_b1 + c * 32, p.act);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_TAILFREE));
+        if (et == 0) trace_stamp(p, tl, 5);                  // E1 done
 
         // E2: h chunk -> 16-bit operand tiles for GEMM2 (+ h back into TMEM for the pooling pass, + optional outputs)
         float tacc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -523,23 +566,25 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
           const int c = 2 * j + half;
           float hv[32];
           tmem_ld32f(tq + (uint32_t)(c * 32), hv);
-          bias_act32(hv, c_b1 + c * 32, p.act);
+          bias_act32<ACT>(hv, c_b1 + c * 32, p.act);
           tmem_st32f(tq + (uint32_t)(c * 32), hv);
           emit_chunk(c, hv);
         }
         ita += NCH2;
         tmem_wait_st();
+        if (et == 0) trace_stamp(p, tl, 6);                  // E2 done (all my A2 chunks produced)
 
         // E3: attention logit of every row: s = wc . f(u + ba) + bc   (this warp: 64 of the Da = 128 columns)
         mbar_wait(BAR(B_UFULL), tl & 1, p.err, 15);
         tc_fence_after();
+        if (et == 0) trace_stamp(p, tl, 7);                  // u complete
         float sp = 0.f;
 #pragma unroll 1
         for (int j = 0; j < 2; ++j) {
           const int c0 = half * 64 + j * 32;
           float uv[32];
           tmem_ld32f(tq + (uint32_t)c0, uv);
-          bias_act32(uv, c_ba + c0, p.att_act);
+          bias_act32<ATT>(uv, c_ba + c0, p.att_act);
 #pragma unroll
           for (int i = 0; i < 32; ++i) sp = fmaf(uv[i], c_wc[c0 + i], sp);
         }
@@ -557,6 +602,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         }
         named_bar_sync(1, 256);                             // s_part / t_part may be overwritten by the next tile after this
 
+        if (et == 0) trace_stamp(p, tl, 8);                  // E3 done (scores exchanged)
         // online softmax over the 32 rows of this warp
         const float m_new = fmaxf(m_run, warp_max(sv));
         float w = 0.f, scale = 1.f;
@@ -576,6 +622,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         }
 #pragma unroll 1
         for (int j = 2; j < 8; ++j) {
+          if (p.dbg & 32) break;
           const int c = 2 * j + half;
           float hv[32];
           tmem_ld32f(tq + (uint32_t)(c * 32), hv);
@@ -586,6 +633,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_ACCEMPTY));
+        if (et == 0) trace_stamp(p, tl, 9);                  // E4 done
       }
 
       // CTA partial: merge the 4 row quarters (the two column halves share m, l) -> part[blockIdx] = (m, l, P[512])
@@ -613,29 +661,91 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         out[0] = m_cta;
         out[1] = l;
       }
+
+      // ---- grid-level finalisation: the last CTA to publish its partial merges all of them (log-sum-exp, fixed order ->
+      // deterministic), normalises the pooled vector and applies the classifier.  No extra launches on the critical path.
+      __threadfence();
+      named_bar_sync(1, 256);
+      int* flag = reinterpret_cast<int*>(s_part + 16);
+      if (et == 0) *flag = (atomicAdd(p.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+      named_bar_sync(1, 256);
+      if (*flag) {
+        __threadfence();
+        const int np = (int)gridDim.x;                        // <= 148 partials
+        float* wgt = t_part;                                  // [np] exp(m_i - m)          (t_part holds 1024 floats)
+        float* sm_m = t_part + 256;                           // [np] m_i (-inf for idle partials)
+        float* sm_l = t_part + 512;                           // [np] l_i
+        for (int i = et; i < np; i += 256) {                  // independent, coalesced-ish loads: one L2 round trip
+          const float mi = __ldcg(p.part + (int64_t)i * (2 + HMAX)), li = __ldcg(p.part + (int64_t)i * (2 + HMAX) + 1);
+          sm_m[i] = li > 0.f ? mi : -INFINITY;
+          sm_l[i] = li;
+        }
+        named_bar_sync(1, 256);
+        float mg = -INFINITY;
+        for (int i = 0; i < np; ++i) mg = fmaxf(mg, sm_m[i]);
+        for (int i = et; i < np; i += 256) wgt[i] = sm_l[i] > 0.f ? expf(sm_m[i] - mg) : 0.f;
+        named_bar_sync(1, 256);
+        float lg = 0.f;
+        for (int i = 0; i < np; ++i) lg = fmaf(sm_l[i], wgt[i], lg);      // fixed order: identical in every thread
+        float* pooled_s = p_acc;                              // reuse [512] floats of the pooled-accumulator scratch
+        for (int c = et; c < HMAX; c += 256) {
+          float v = 0.f;
+#pragma unroll 8
+          for (int i = 0; i < np; ++i) v = fmaf(__ldcg(p.part + (int64_t)i * (2 + HMAX) + 2 + c), wgt[i], v);
+          v /= lg;
+          pooled_s[c] = v;
+          p.pooled[c] = v;
+        }
+        if (et == 0) { p.stats[0] = mg; p.stats[1] = lg; *p.counter = 0u; }
+        named_bar_sync(1, 256);
+        if (p.logits) {
+          const int wid = et >> 5;
+          for (int k = wid; k < p.n_cls; k += 8) {
+            float a = 0.f;
+            for (int c = lane; c < HMAX; c += 32) a = fmaf(pooled_s[c], p.Wcls[k * HMAX + c], a);
+            a = warp_sum(a);
+            if (lane == 0) p.logits[k] = a + (p.bcls ? p.bcls[k] : 0.f);
+          }
+        }
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.trace && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.trace[256 + 2 * blockIdx.x + 1] = (long long)gt;
+  }
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// fp32 -> 16-bit hi / lo split of the weights (once per call; 2.4 MB of weights vs 205 MB of bag)
+// fp32 weights W[R, K] -> pre-swizzled 16-bit operand image (once per weight version; 2.4 MB of weights vs 205 MB of bag)
+//   image = for every k-step ks (32 elements): [hi tile | lo tile], each tile = R rows x 64 B laid out exactly as the
+//   UMMA K-major SWIZZLE_64B shared-memory tile: byte(r, c, e) = (r/8)*512 + (r%8)*64 + ((c ^ ((r>>1)&3))*16) + 2e,
+//   c = 16-byte chunk (8 elements) inside the 64-byte row.  One thread converts one (row, chunk).
 // ------------------------------------------------------------------------------------------------------------
 template <bool FP16, bool LO>
-__global__ void split_weights_kernel(const float* __restrict__ w, int64_t n, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
-  if (i >= n) return;
-  const float x0 = w[i], x1 = (i + 1 < n) ? w[i + 1] : 0.f;
-  const uint32_t h = pack_hi<FP16>(x0, x1);
-  hi[i] = (uint16_t)(h & 0xFFFFu);
-  if (i + 1 < n) hi[i + 1] = (uint16_t)(h >> 16);
+__global__ void split_weights_kernel(const float* __restrict__ w, int R, int K, uint8_t* __restrict__ img) {
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (r, kc): kc = k / 8
+  const int kchunks = K / 8;
+  if (item >= (int64_t)R * kchunks) return;
+  const int r = (int)(item / kchunks), kc = (int)(item % kchunks);
+  const int ks = kc >> 2, c = kc & 3;
+  const float4 a = *reinterpret_cast<const float4*>(w + (int64_t)r * K + kc * 8);
+  const float4 b = *reinterpret_cast<const float4*>(w + (int64_t)r * K + kc * 8 + 4);
+  uint32_t h[4], l[4];
+  h[0] = pack_hi<FP16>(a.x, a.y); h[1] = pack_hi<FP16>(a.z, a.w); h[2] = pack_hi<FP16>(b.x, b.y); h[3] = pack_hi<FP16>(b.z, b.w);
+  constexpr int NOPK = LO ? 2 : 1;
+  const size_t tile = (size_t)R * 64;
+  const size_t off = (size_t)(r >> 3) * 512 + (size_t)(r & 7) * 64 + (size_t)((c ^ ((r >> 1) & 3)) << 4);
+  uint8_t* dst = img + (size_t)ks * NOPK * tile + off;
+  *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
   if (LO) {
-    const uint32_t l = pack_lo_bf16(x0, x1, h);
-    lo[i] = (uint16_t)(l & 0xFFFFu);
-    if (i + 1 < n) lo[i + 1] = (uint16_t)(l >> 16);
+    l[0] = pack_lo_bf16(a.x, a.y, h[0]); l[1] = pack_lo_bf16(a.z, a.w, h[1]); l[2] = pack_lo_bf16(b.x, b.y, h[2]); l[3] = pack_lo_bf16(b.z, b.w, h[3]);
+    *reinterpret_cast<uint4*>(dst + tile) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
@@ -674,12 +784,11 @@ static int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, c
 static bool g_profile = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 
-template <int NPROD, bool FP16, int NST, int MODE>
-static int launch_fused(const CUtensorMap& mx, const CUtensorMap& mwh, const CUtensorMap& mwl, const CUtensorMap& mah, const CUtensorMap& mal,
-                        const FusedParams& p, int grid, cudaStream_t stream) {
+template <int NPROD, bool FP16, int NST, int MODE, int ACT, int ATT>
+static int launch_fused(const CUtensorMap& mx, const FusedParams& p, int grid, cudaStream_t stream) {
   constexpr int NOP = NPROD == 3 ? 2 : 1;
   const size_t smem = 1024 + (size_t)XS * X_SLOT_BYTES + (size_t)NST * NOP * (A_OP_BYTES + B_OP_BYTES) + 256 + 1024 + 4096 + 16 + (HMAX + 256) * 4 + 8 * 256 * 4;
-  auto kern = mil_fused_kernel<NPROD, FP16, NST, MODE>;
+  auto kern = mil_fused_kernel<NPROD, FP16, NST, MODE, ACT, ATT>;
   static bool attr_set = false;
   if (!attr_set) {
     MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -687,7 +796,7 @@ static int launch_fused(const CUtensorMap& mx, const CUtensorMap& mwh, const CUt
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
-  kern<<<grid, NUM_THREADS, smem, stream>>>(mx, mwh, mwl, mah, mal, p);
+  kern<<<grid, NUM_THREADS, smem, stream>>>(mx, p);
   if (g_profile) { cudaEventRecord(e1, stream); g_prof_events.push_back({e0, e1}); }
   MIL_LAUNCH_CHECK();
   return 0;
@@ -703,23 +812,32 @@ static int grid_override(int grid) {
   return (g > 0 && g < grid) ? g : grid;
 }
 
-static int dispatch_fused(int precision, int mode, const CUtensorMap& mx, const CUtensorMap& mwh, const CUtensorMap& mwl, const CUtensorMap& mah,
-                          const CUtensorMap& mal, const FusedParams& p, int grid, cudaStream_t stream) {
-  if (mode == MODE_FUSED) {
-    if (precision == MIL_PREC_BF16X3) return launch_fused<3, false, 2, MODE_FUSED>(mx, mwh, mwl, mah, mal, p, grid, stream);
-    if (precision == MIL_PREC_FP16) return launch_fused<1, true, 4, MODE_FUSED>(mx, mwh, mwl, mah, mal, p, grid, stream);
-    return launch_fused<1, false, 4, MODE_FUSED>(mx, mwh, mwl, mah, mal, p, grid, stream);
-  }
-  if (precision == MIL_PREC_BF16X3) return launch_fused<3, false, 2, MODE_STORE>(mx, mwh, mwl, mah, mal, p, grid, stream);
-  if (precision == MIL_PREC_FP16) return launch_fused<1, true, 4, MODE_STORE>(mx, mwh, mwl, mah, mal, p, grid, stream);
-  return launch_fused<1, false, 4, MODE_STORE>(mx, mwh, mwl, mah, mal, p, grid, stream);
+template <int MODE, int ACT, int ATT>
+static int dispatch_prec(int precision, const CUtensorMap& mx, const FusedParams& p, int grid, cudaStream_t stream) {
+  if (precision == MIL_PREC_BF16X3) return launch_fused<3, false, 2, MODE, ACT, ATT>(mx, p, grid, stream);
+  if (precision == MIL_PREC_FP16) return launch_fused<1, true, 4, MODE, ACT, ATT>(mx, p, grid, stream);
+  return launch_fused<1, false, 4, MODE, ACT, ATT>(mx, p, grid, stream);
 }
 
-static int split_weights(const float* w, int64_t n, uint16_t* hi, uint16_t* lo, int precision, cudaStream_t stream) {
-  const unsigned blocks = (unsigned)((n / 2 + 255) / 256 + 1);
-  if (precision == MIL_PREC_BF16X3) split_weights_kernel<false, true><<<blocks, 256, 0, stream>>>(w, n, hi, lo);
-  else if (precision == MIL_PREC_FP16) split_weights_kernel<true, false><<<blocks, 256, 0, stream>>>(w, n, hi, lo);
-  else split_weights_kernel<false, false><<<blocks, 256, 0, stream>>>(w, n, hi, lo);
+// Fused mode is instantiated for the activation pairs the reference can produce: feature act relu / gelu (abmil.py:183-186,
+// mhim.py:71-74) x attention act tanh (abmil.py:195) or relu / gelu / tanh (MHIM da_act, baseline.py:17-22).
+static int dispatch_fused(int precision, int mode, const CUtensorMap& mx, const FusedParams& p, int grid, cudaStream_t stream) {
+  if (mode == MODE_STORE) return dispatch_prec<MODE_STORE, -1, -1>(precision, mx, p, grid, stream);
+#define MIL_CASE(A, T) if (p.act == A && p.att_act == T) return dispatch_prec<MODE_FUSED, A, T>(precision, mx, p, grid, stream);
+  MIL_CASE(MIL_ACT_RELU, MIL_ACT_TANH) MIL_CASE(MIL_ACT_GELU, MIL_ACT_TANH)
+  MIL_CASE(MIL_ACT_RELU, MIL_ACT_RELU) MIL_CASE(MIL_ACT_GELU, MIL_ACT_RELU)
+  MIL_CASE(MIL_ACT_RELU, MIL_ACT_GELU) MIL_CASE(MIL_ACT_GELU, MIL_ACT_GELU)
+#undef MIL_CASE
+  set_error("fused pass: unsupported activation pair act=%d att_act=%d (use the composed path)", p.act, p.att_act);
+  return -1;
+}
+
+static int split_weights(const float* w, int R, int K, uint8_t* img, int precision, cudaStream_t stream) {
+  const int64_t items = (int64_t)R * (K / 8);
+  const unsigned blocks = (unsigned)((items + 255) / 256);
+  if (precision == MIL_PREC_BF16X3) split_weights_kernel<false, true><<<blocks, 256, 0, stream>>>(w, R, K, img);
+  else if (precision == MIL_PREC_FP16) split_weights_kernel<true, false><<<blocks, 256, 0, stream>>>(w, R, K, img);
+  else split_weights_kernel<false, false><<<blocks, 256, 0, stream>>>(w, R, K, img);
   MIL_LAUNCH_CHECK();
   return 0;
 }
@@ -748,13 +866,14 @@ extern "C" int mil_profile_collect(double* total_ms) {
 
 extern "C" size_t mil_fused_workspace_bytes(int D, int H, int Da, int gated) {
   (void)gated;
-  return ((size_t)H * D + (size_t)Da * H) * 2 /*hi+lo*/ * sizeof(uint16_t) + 1024 + sizeof(int) * 4;
+  return ((size_t)H * D + (size_t)Da * H) * 2 /*hi+lo*/ * sizeof(uint16_t) + 1024 + sizeof(int) * 4 + 64 + (16 * 16 + 2 * 1024) * sizeof(long long);
 }
 
 extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, const float* W1, const float* b1, int act, const float* Wa,
                                        const float* ba, const float* Wb, const float* bb, int Da, int att_act, const float* wc, const float* bc,
                                        const uint8_t* keep, const float* Wp, int C, float* s_out, float* t_out, float* h_out, float* part,
-                                       float* stats, float* pooled, void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream_) {
+                                       float* stats, float* pooled, const float* Wcls, const float* bcls, int n_cls, float* logits,
+                                       void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MIL_CHECK_ARG(mil_device_supported(), "mil_abmil_fused_fwd_f32: needs a compute-capability 10.x device (tcgen05/TMEM/TMA)");
   MIL_CHECK_ARG(X && W1 && b1 && Wa && wc && part && stats && pooled && ws, "mil_abmil_fused_fwd_f32: null argument");
@@ -768,35 +887,30 @@ extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, 
   MIL_CHECK_ARG((uintptr_t)X % 16 == 0 && (!h_out || (uintptr_t)h_out % 16 == 0), "mil_abmil_fused_fwd_f32: X / h_out must be 16-byte aligned");
   MIL_CHECK_ARG(ws_bytes >= mil_fused_workspace_bytes(D, H, Da, 0), "mil_abmil_fused_fwd_f32: workspace needs %zu bytes", mil_fused_workspace_bytes(D, H, Da, 0));
 
-  char* w = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-  uint16_t* w1h = (uint16_t*)w;
-  uint16_t* w1l = w1h + (size_t)H * D;
-  uint16_t* wah = w1l + (size_t)H * D;
-  uint16_t* wal = wah + (size_t)Da * H;
-  int* err = (int*)(wal + (size_t)Da * H);
+  uint8_t* w = (uint8_t*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  uint8_t* w1_img = w;                                        // [D/32][hi|lo][H x 64 B]
+  uint8_t* wa_img = w1_img + (size_t)H * D * 4;               // [H/32][hi|lo][Da x 64 B]
+  int* err = (int*)(wa_img + (size_t)Da * H * 4);     // err[0] = pipeline error code, err[1] = finished-CTA counter
   int rc;
-  if (!ws_ready) {   // 16-bit hi/lo images of the weights: reusable across calls until the weights change (ws_ready = 1)
-    if ((rc = split_weights(W1, (int64_t)H * D, w1h, w1l, precision, stream))) return rc;
-    if ((rc = split_weights(Wa, (int64_t)Da * H, wah, wal, precision, stream))) return rc;
-    MIL_CUDA(cudaMemsetAsync(err, 0, sizeof(int), stream));
+  MIL_CHECK_ARG(!logits || (Wcls && n_cls >= 1 && n_cls <= 64), "mil_abmil_fused_fwd_f32: logits needs Wcls and 1 <= n_cls <= 64");
+  if (!ws_ready) {   // 16-bit operand images of the weights: reusable across calls until the weights change (ws_ready = 1)
+    MIL_CHECK_ARG((uintptr_t)W1 % 16 == 0 && (uintptr_t)Wa % 16 == 0, "mil_abmil_fused_fwd_f32: weights must be 16-byte aligned");
+    if ((rc = split_weights(W1, H, D, w1_img, precision, stream))) return rc;
+    if ((rc = split_weights(Wa, Da, H, wa_img, precision, stream))) return rc;
+    MIL_CUDA(cudaMemsetAsync(err, 0, 4 * sizeof(int), stream));
   }
-
-  const CUtensorMapDataType dt16 = precision == MIL_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  CUtensorMap mx, mwh, mwl, mah, mal;
+  CUtensorMap mx;
   if ((rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)N, (uint64_t)D, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map_2d(&mwh, dt16, 2, w1h, (uint64_t)H, (uint64_t)D, 256, BK, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  if ((rc = make_map_2d(&mwl, dt16, 2, w1l, (uint64_t)H, (uint64_t)D, 256, BK, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  if ((rc = make_map_2d(&mah, dt16, 2, wah, (uint64_t)Da, (uint64_t)H, (uint32_t)Da, BK, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  if ((rc = make_map_2d(&mal, dt16, 2, wal, (uint64_t)Da, (uint64_t)H, (uint32_t)Da, BK, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
 
   FusedParams p;
   p.N = N; p.D = D; p.nout = H; p.Da = Da; p.act = act; p.att_act = att_act;
   p.b1 = b1; p.ba = ba; p.wc = wc; p.bc = bc; p.keep = keep; p.Wp = Wp; p.C = t_out ? C : 0;
-  p.s_out = s_out; p.t_out = t_out; p.h_out = h_out; p.part = part; p.c_out = nullptr; p.ldc = 0; p.err = err; p.dbg = debug_mask();
+  p.s_out = s_out; p.t_out = t_out; p.h_out = h_out; p.part = part; p.c_out = nullptr; p.ldc = 0; p.err = err; p.dbg = debug_mask(); p.w1_img = w1_img; p.wa_img = wa_img;
+  p.stats = stats; p.pooled = pooled; p.counter = (unsigned int*)(err + 1); p.Wcls = Wcls; p.bcls = bcls; p.n_cls = n_cls; p.logits = logits;
+  p.trace = getenv("MHIMK_TRACE") ? (long long*)(((uintptr_t)(err + 4) + 63) & ~(uintptr_t)63) : nullptr;
   const int64_t n_tiles = (N + BM - 1) / BM;
   const int grid = grid_override((int)(n_tiles < num_sms() ? n_tiles : num_sms()));
-  if ((rc = dispatch_fused(precision, MODE_FUSED, mx, mwh, mwl, mah, mal, p, grid, stream))) return rc;
-  return mil_pool_merge_f32(part, grid, H, stats, pooled, stream_);
+  return dispatch_fused(precision, MODE_FUSED, mx, p, grid, stream);
 }
 
 extern "C" int mil_umma_selftest_f32(const float* A, const float* B, float* C, int M, int N, int K, int precision, void* ws, size_t ws_bytes,
@@ -807,24 +921,21 @@ extern "C" int mil_umma_selftest_f32(const float* A, const float* B, float* C, i
   MIL_CHECK_ARG((N == 64 || N == 128 || N == 256 || N == 512) && K >= BK && K % BK == 0, "mil_umma_selftest_f32: unsupported N=%d K=%d", N, K);
   MIL_CHECK_ARG(precision >= 0 && precision <= 2, "mil_umma_selftest_f32: bad precision");
   MIL_CHECK_ARG(ws_bytes >= (size_t)N * K * 4 + 1024, "mil_umma_selftest_f32: workspace needs %zu bytes", (size_t)N * K * 4 + 1024);
-  char* w = (char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-  uint16_t* bh = (uint16_t*)w;
-  uint16_t* bl = bh + (size_t)N * K;
-  int* err = (int*)(bl + (size_t)N * K);
+  MIL_CHECK_ARG(K % 32 == 0, "mil_umma_selftest_f32: K must be a multiple of 32");
+  uint8_t* b_img = (uint8_t*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  int* err = (int*)(b_img + (size_t)N * K * 4);
   int rc;
-  if ((rc = split_weights(B, (int64_t)N * K, bh, bl, precision, stream))) return rc;
+  MIL_CHECK_ARG((uintptr_t)B % 16 == 0, "mil_umma_selftest_f32: B must be 16-byte aligned");
+  if ((rc = split_weights(B, N, K, b_img, precision, stream))) return rc;
   MIL_CUDA(cudaMemsetAsync(err, 0, sizeof(int), stream));
-  const CUtensorMapDataType dt16 = precision == MIL_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  CUtensorMap mx, mwh, mwl;
-  const uint32_t box_rows = N < 256 ? N : 256;
+  CUtensorMap mx;
   if ((rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, (uint64_t)M, (uint64_t)K, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map_2d(&mwh, dt16, 2, bh, (uint64_t)N, (uint64_t)K, box_rows, BK, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  if ((rc = make_map_2d(&mwl, dt16, 2, bl, (uint64_t)N, (uint64_t)K, box_rows, BK, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   FusedParams p;
   p.N = M; p.D = K; p.nout = N; p.Da = 128; p.act = MIL_ACT_NONE; p.att_act = MIL_ACT_NONE;
   p.b1 = nullptr; p.ba = nullptr; p.wc = nullptr; p.bc = nullptr; p.keep = nullptr; p.Wp = nullptr; p.C = 0;
-  p.s_out = nullptr; p.t_out = nullptr; p.h_out = nullptr; p.part = nullptr; p.c_out = C; p.ldc = N; p.err = err; p.dbg = debug_mask();
+  p.s_out = nullptr; p.t_out = nullptr; p.h_out = nullptr; p.part = nullptr; p.c_out = C; p.ldc = N; p.err = err; p.dbg = debug_mask(); p.w1_img = b_img; p.wa_img = b_img; p.trace = nullptr;
+  p.stats = nullptr; p.pooled = nullptr; p.counter = nullptr; p.Wcls = nullptr; p.bcls = nullptr; p.n_cls = 0; p.logits = nullptr;
   const int64_t n_tiles = ((int64_t)M + BM - 1) / BM;
   const int grid = grid_override((int)(n_tiles < num_sms() ? n_tiles : num_sms()));
-  return dispatch_fused(precision, MODE_STORE, mx, mwh, mwl, mwh, mwl, p, grid, stream);
+  return dispatch_fused(precision, MODE_STORE, mx, p, grid, stream);
 }

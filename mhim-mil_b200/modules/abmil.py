@@ -57,8 +57,9 @@ class DAttention(nn.Module):
         if not grad_needed(self, x) and self._fused_ok(x):
             f0 = self.feature[0]
             out = ops.abmil_fused_forward(x2, f0.weight, f0.bias, self.act, att0.weight, att0.bias, att2.weight, att2.bias, "tanh",
-                                          want_scores=return_attn, want_h=return_attn and return_act, precision=self.precision)
-            pooled = out["pooled"]
+                                          want_scores=return_attn, want_h=return_attn and return_act, precision=self.precision,
+                                          Wcls=self.classifier.weight, bcls=self.classifier.bias)
+            pooled, fused_logits = out["pooled"], out["logits"]
             attn = torch.exp(out["s"] - out["stats"][0]) / out["stats"][1] if return_attn else None
             h = out["h"]
         else:
@@ -68,8 +69,9 @@ class DAttention(nn.Module):
             u = lin(att0, h, "tanh")
             s = lin(att2, u)[:, 0]
             pooled, attn = ops.softmax_pool(s, h)
+            fused_logits = None
         img_feat = pooled[None]
-        logits = lin(self.classifier, img_feat)
+        logits = fused_logits if fused_logits is not None else lin(self.classifier, img_feat)
         if return_img_feat:
             logits = [logits, img_feat]
         if return_attn:

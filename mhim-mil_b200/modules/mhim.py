@@ -67,11 +67,12 @@ class MHIM(nn.Module):
                 and x.dim() == 3 and x.shape[0] == 1 and x.shape[-1] % 32 == 0 and self.feature[0].out_features == 512
                 and not (self.training and enc.attention.p_drop > 0))
 
-    def _fused(self, x, want_scores=False, want_h=False, with_pred=False):
+    def _fused(self, x, want_scores=False, want_h=False, with_pred=False, with_logits=False):
         f0, att = self.feature[0], self.online_encoder.attention
         return ops.abmil_fused_forward(x[0], f0.weight, f0.bias, self.act, att.attention[0].weight, None, att.attention[-1].weight, None,
                                        att.act, Wp=self.predictor.weight if with_pred else None, want_scores=want_scores, want_h=want_h,
-                                       precision=self.precision)
+                                       precision=self.precision, Wcls=self.predictor.weight if with_logits else None,
+                                       bcls=self.predictor.bias if with_logits else None)
 
     # ------------------------------------------------------------------ masking
     def get_mask(self, ps, i, attn, mrh=None):
@@ -136,8 +137,8 @@ class MHIM(nn.Module):
     def forward_test(self, x, return_attn=False, no_norm=False, return_act=False, **kwargs):
         """inference (mhim.py:229-272)"""
         if self._fusable(x) and not self.merge_test and not return_act:
-            out = self._fused(x, want_scores=return_attn)
-            logits = C.lin(self.predictor, out["pooled"][None])
+            out = self._fused(x, want_scores=return_attn, with_logits=True)
+            logits = out["logits"]
             if not return_attn:
                 return logits
             a = out["s"] if no_norm else torch.exp(out["s"] - out["stats"][0]) / out["stats"][1]
@@ -164,7 +165,7 @@ class MHIM(nn.Module):
         """no masking, no merging (mhim.py:274-298)"""
         ps = x.size(1)
         if self._fusable(x):
-            y = C.lin(self.predictor, self._fused(x)["pooled"][None])
+            y = self._fused(x, with_logits=True)["logits"]
         else:
             h = self._embed(x)
             if self.baseline == "dsmil":

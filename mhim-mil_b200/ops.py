@@ -224,10 +224,11 @@ def _fused_workspace(W1, Wa, precision):
 
 @torch.no_grad()
 def abmil_fused_forward(x, W1, b1, act, Wa, ba, wc, bc, att_act="tanh", keep=None, Wp=None, want_scores=False, want_h=False,
-                        precision: str = DEFAULT_PRECISION):
+                        precision: str = DEFAULT_PRECISION, Wcls=None, bcls=None):
     """One streaming pass over x [N,D]: returns dict(pooled[H], stats[2] = (m, l), s[N]?, t[N,C]?, h[N,H]?, part).
 
-    h = act(x W1^T + b1); s = wc . att_act(Wa h + ba) + bc; pooled = softmax_N(s) @ h.  (mil_abmil_fused_fwd_f32)
+    h = act(x W1^T + b1); s = wc . att_act(Wa h + ba) + bc; pooled = softmax_N(s) @ h; logits = Wcls pooled + bcls when a
+    classifier is given (same kernel).  (mil_abmil_fused_fwd_f32)
     """
     L = _lib.lib()
     x, W1, b1, Wa, wc = _need(x, "x"), _need(W1, "W1"), _need(b1, "b1"), _need(Wa, "Wa"), _need(wc.reshape(-1), "wc")
@@ -242,11 +243,14 @@ def abmil_fused_forward(x, W1, b1, act, Wa, ba, wc, bc, att_act="tanh", keep=Non
     C = Wp.shape[0] if Wp is not None else 0
     t = torch.empty((N, C), dtype=torch.float32, device=dev) if Wp is not None else None
     h = torch.empty((N, H), dtype=torch.float32, device=dev) if want_h else None
+    ncls = Wcls.shape[0] if Wcls is not None else 0
+    logits = torch.empty((1, ncls), dtype=torch.float32, device=dev) if Wcls is not None else None
     ws, ready = _fused_workspace(W1, Wa, precision)
     check(L.mil_abmil_fused_fwd_f32(ptr(x), N, D, H, ptr(W1), ptr(b1), ACT[act], ptr(Wa), ptr(ba), None, None, Da, ACT[att_act], ptr(wc),
-                                    ptr(bc), ptr(keep), ptr(Wp), C, ptr(s), ptr(t), ptr(h), ptr(part), ptr(stats), ptr(pooled), ptr(ws),
-                                    ws.numel(), ready, PREC[precision], stream_ptr()), "mil_abmil_fused_fwd_f32")
-    return {"pooled": pooled, "stats": stats, "s": s, "t": t, "h": h, "part": part}
+                                    ptr(bc), ptr(keep), ptr(Wp), C, ptr(s), ptr(t), ptr(h), ptr(part), ptr(stats), ptr(pooled),
+                                    ptr(Wcls), ptr(bcls), ncls, ptr(logits), ptr(ws), ws.numel(), ready, PREC[precision], stream_ptr()),
+          "mil_abmil_fused_fwd_f32")
+    return {"pooled": pooled, "stats": stats, "s": s, "t": t, "h": h, "part": part, "logits": logits}
 
 
 def profile_fused(enable: bool):

@@ -41,7 +41,7 @@ def test_fused_forward(K, prec, N, act, kind):
     Wp = torch.randn(2, 512, generator=torch.Generator().manual_seed(1)) * 0.05
     out = K.abmil_fused_forward(x[0].cuda(), c["feature.0.weight"], c["feature.0.bias"], act, c["attention.0.weight"], c["attention.0.bias"],
                                 c["attention.2.weight"], c["attention.2.bias"], "tanh", Wp=Wp.cuda(), want_scores=True, want_h=(N <= 4099),
-                                precision=prec)
+                                precision=prec, Wcls=c["classifier.weight"], bcls=c["classifier.bias"])
     torch.cuda.synchronize()
     assert cases.rel_err(out["pooled"], p_ref) < TOL[prec]
     assert cases.rel_err(out["s"], s_ref) < TOL[prec] * 3
@@ -51,6 +51,10 @@ def test_fused_forward(K, prec, N, act, kind):
     logits = out["pooled"].cpu().double() @ sd["classifier.weight"].double().t() + sd["classifier.bias"].double()
     ref_logits = p_ref @ sd["classifier.weight"].double().t() + sd["classifier.bias"].double()
     assert cases.rel_err(logits, ref_logits) < TOL[prec]
+    assert cases.rel_err(out["logits"][0], ref_logits) < TOL[prec]          # classifier fused into the kernel tail
+    stats = out["stats"].cpu().double()
+    assert abs(float(stats[0]) - float(s_ref.max())) < 3 * TOL[prec] * max(1.0, float(s_ref.abs().max()))
+    assert cases.rel_err(stats[1], torch.exp(s_ref - s_ref.max()).sum()) < 30 * TOL[prec]
 
 
 def test_fused_forward_with_keep_mask(K):

@@ -21,6 +21,13 @@ act = os.environ.get("PROF_ACT", "relu")
 def timeit(fn):
     fn(0)
     torch.cuda.synchronize()
+    mhimk.ops.profile_fused(True)
+    for i in range(reps):
+        fn(i)
+    torch.cuda.synchronize()
+    n, tot = mhimk.ops.profile_collect()
+    mhimk.ops.profile_fused(False)
+    print(f"   kernel-only mean {tot / max(n, 1) * 1e3:8.1f} us over {n} launches", end="  |  ")
     ts = []
     for i in range(reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
