@@ -308,10 +308,10 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
   uint8_t* sB = sA + NST * A_STAGE;                        // NST x B_STAGE
   uint8_t* sMisc = sB + NST * B_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sMisc);     // barrier block
-  float* s_part = reinterpret_cast<float*>(sMisc + 256);   // [2][128] partial attention logits (+ [2][128][4] t partials)
+  float* s_part = reinterpret_cast<float*>(sMisc + 512);   // [2][128] partial attention logits (+ [2][128][4] t partials)
   float* t_part = s_part + 256;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sMisc + 256 + 1024 + 4096);
-  float* c_b1 = reinterpret_cast<float*>(sMisc + 256 + 1024 + 4096 + 16);   // [512] feature bias
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sMisc + 512 + 1024 + 4096);
+  float* c_b1 = reinterpret_cast<float*>(sMisc + 512 + 1024 + 4096 + 16);   // [512] feature bias
   float* c_ba = c_b1 + HMAX;                                                 // [128] attention bias
   float* c_wc = c_ba + 128;                                                  // [128] attention output weights
   float* p_acc = c_wc + 128;                                                 // [8 warps][8 chunks][32 lanes] pooled partial sums
@@ -320,8 +320,24 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   constexpr int B_XFULL = 0, B_XEMPTY = B_XFULL + XS, B_AFULL = B_XEMPTY + XS, B_BFULL = B_AFULL + NST, B_EMPTY = B_BFULL + NST,
-                B_ACCFULL = B_EMPTY + NST, B_ACCEMPTY = B_ACCFULL + 1, B_TAILFREE = B_ACCEMPTY + 1, B_UFULL = B_TAILFREE + 1, B_COUNT = B_UFULL + 1;
-  static_assert(B_COUNT * 8 <= 256, "barrier block overflow");
+                B_ACCFULL = B_EMPTY + NST, B_ACCEMPTY = B_ACCFULL + 1, B_TAILFREE = B_ACCEMPTY + 1, B_UFULL = B_TAILFREE + 1,
+                B_G2AFULL = B_UFULL + 1, B_G2BFULL = B_G2AFULL + 4, B_G2EMPTY = B_G2BFULL + 4, B_COUNT = B_G2EMPTY + 4;
+  static_assert(B_COUNT * 8 <= 512, "barrier block overflow");
+
+  // GEMM2 has its own 4-deep operand ring (barriers G2*).  Its buffers are carved out of the GEMM1 stage slots, which are idle
+  // between ACC_FULL (all GEMM1 MMAs of the tile done) and U_FULL (all GEMM2 MMAs done):
+  //   1-product modes: ring entry r = GEMM1 slot r (NST = 4).
+  //   3-product mode (NST = 2, slot = A 16 KB + B 64 KB): r = (slot = r & 1, sub = r >> 1);
+  //     sub 0: A2 hi/lo in the A slot, Wa hi @ B+0, Wa lo @ B+32K;  sub 1: A2 hi @ B+8K, A2 lo @ B+40K, Wa hi @ B+16K, Wa lo @ B+48K.
+  auto g2_a_hi = [&](uint32_t r) -> uint32_t {
+    if (LO) return (r >> 1) ? smem_u32(sB + (r & 1) * B_STAGE + 8192) : smem_u32(sA + (r & 1) * A_STAGE);
+    return smem_u32(sA + r * A_STAGE);
+  };
+  auto g2_a_lo = [&](uint32_t r) -> uint32_t { return g2_a_hi(r) + ((r >> 1) ? (uint32_t)B_OP_BYTES : (uint32_t)A_OP_BYTES); };
+  auto g2_b_hi = [&](uint32_t r) -> uint32_t {
+    if (LO) return smem_u32(sB + (r & 1) * B_STAGE + ((r >> 1) ? 16384 : 0));
+    return smem_u32(sB + r * B_STAGE);
+  };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.trace && threadIdx.x == 0) {
@@ -337,6 +353,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
     for (int i = 0; i < XS; ++i) { mbar_init(BAR(B_XFULL + i), 1); mbar_init(BAR(B_XEMPTY + i), 4); }
     for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_AFULL + i), 4); mbar_init(BAR(B_BFULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
     mbar_init(BAR(B_ACCFULL), 1); mbar_init(BAR(B_ACCEMPTY), 8); mbar_init(BAR(B_TAILFREE), 8); mbar_init(BAR(B_UFULL), 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(BAR(B_G2AFULL + i), 4); mbar_init(BAR(B_G2BFULL + i), 1); mbar_init(BAR(B_G2EMPTY + i), 1); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -370,9 +387,11 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
     // The weights were pre-arranged (split_weights_kernel) as the exact shared-memory image of every stage's operand tile
     // (UMMA K-major SWIZZLE_64B), so each stage is ONE contiguous bulk copy per operand instead of 256-512 64-byte TMA rows.
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t it = 0, tl = 0;
       const uint32_t w1_tile = (uint32_t)p.nout * BK * 2, wa_tile = (uint32_t)p.Da * BK * 2;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+        // the GEMM1 stage slots host GEMM2's ring between ACC_FULL and U_FULL of the previous tile
+        if (MODE == MODE_FUSED && tl > 0) mbar_wait(BAR(B_UFULL), (tl - 1) & 1, p.err, 17);
         for (int ks = 0; ks < KS; ++ks, ++it) {
           const uint32_t s = it % NST, ph = (it / NST) & 1;
           mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 2);
@@ -383,15 +402,16 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
           bulk_load(dst, src, w1_tile, BAR(B_BFULL + s));
           if (LO) bulk_load(dst + B_OP_BYTES, src + w1_tile, w1_tile, BAR(B_BFULL + s));
         }
-        for (int c = 0; c < NCH2; ++c, ++it) {
-          const uint32_t s = it % NST, ph = (it / NST) & 1;
-          mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 3);
-          if (p.dbg & 16) { mbar_arrive(BAR(B_BFULL + s)); continue; }
-          mbar_expect_tx(BAR(B_BFULL + s), NOP * wa_tile);
-          const uint32_t dst = smem_u32(sB + s * B_STAGE);
+        if (NCH2 > 0) mbar_wait(BAR(B_ACCFULL), tl & 1, p.err, 18);
+        for (int c = 0; c < NCH2; ++c) {
+          const uint32_t r = c & 3, ph = (tl * 4 + (c >> 2)) & 1;
+          mbar_wait(BAR(B_G2EMPTY + r), ph ^ 1, p.err, 3);
+          if (p.dbg & 16) { mbar_arrive(BAR(B_G2BFULL + r)); continue; }
+          mbar_expect_tx(BAR(B_G2BFULL + r), NOP * wa_tile);
+          const uint32_t dst = g2_b_hi(r);
           const uint8_t* src = p.wa_img + (size_t)c * NOP * wa_tile;
-          bulk_load(dst, src, wa_tile, BAR(B_BFULL + s));
-          if (LO) bulk_load(dst + B_OP_BYTES, src + wa_tile, wa_tile, BAR(B_BFULL + s));
+          bulk_load(dst, src, wa_tile, BAR(B_G2BFULL + r));
+          if (LO) bulk_load(dst + B_OP_BYTES, src + wa_tile, wa_tile, BAR(B_G2BFULL + r));
         }
       }
     }
@@ -434,12 +454,12 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
           mbar_wait(BAR(B_TAILFREE), tl & 1, p.err, 7);
           tc_fence_after();
           trace_stamp(p, tl, 2);                             // GEMM2 may start
-          for (int c = 0; c < NCH2; ++c, ++it) {
-            const uint32_t s = it % NST, ph = (it / NST) & 1;
-            mbar_wait(BAR(B_AFULL + s), ph, p.err, 8);
-            mbar_wait(BAR(B_BFULL + s), ph, p.err, 9);
+          for (int c = 0; c < NCH2; ++c) {
+            const uint32_t r = c & 3, ph = (tl * 4 + (c >> 2)) & 1;
+            mbar_wait(BAR(B_G2AFULL + r), ph, p.err, 8);
+            mbar_wait(BAR(B_G2BFULL + r), ph, p.err, 9);
             tc_fence_after();
-            const uint32_t a0 = smem_u32(sA + s * A_STAGE), b0 = smem_u32(sB + s * B_STAGE);
+            const uint32_t a0 = g2_a_hi(r), a0l = g2_a_lo(r), b0 = g2_b_hi(r);
 #pragma unroll
             for (int k16 = 0; k16 < 2; ++k16) {
               if (p.dbg & 64) break;
@@ -447,12 +467,12 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
               const uint64_t ah = make_desc_sw64(a0 + k16 * 32), bh = make_desc_sw64(b0 + k16 * 32);
               umma_f16(tmem, ah, bh, idesc2, acc);
               if (LO) {
-                const uint64_t al = make_desc_sw64(a0 + A_OP_BYTES + k16 * 32), bl = make_desc_sw64(b0 + B_OP_BYTES + k16 * 32);
+                const uint64_t al = make_desc_sw64(a0l + k16 * 32), bl = make_desc_sw64(b0 + B_OP_BYTES + k16 * 32);
                 umma_f16(tmem, al, bh, idesc2, 1u);
                 umma_f16(tmem, ah, bl, idesc2, 1u);
               }
             }
-            umma_commit(BAR(B_EMPTY + s));
+            umma_commit(BAR(B_G2EMPTY + r));
           }
           umma_commit(BAR(B_UFULL));
           trace_stamp(p, tl, 3);                             // GEMM2 fully issued
@@ -466,8 +486,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
     const int row = (warp - 4) * 32 + lane;                 // one row of the 128-row slab per thread
     uint32_t itx = 0, ita = 0, tl = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
-      // The operand ring is shared with the epilogue warps (GEMM2 stages of the previous tile).  mbarrier waits only carry
-      // one parity bit, so a waiter must never be two phases away from the barrier: do not run ahead of GEMM2(t-1).
+      // The stage slots host GEMM2's operand ring until U_FULL of the previous tile: do not overwrite them earlier.
       if (MODE == MODE_FUSED && tl > 0) mbar_wait(BAR(B_UFULL), (tl - 1) & 1, p.err, 16);
       for (int ks = 0; ks < KS; ++ks, ++itx, ++ita) {
         const uint32_t xs = itx % XS, xph = (itx / XS) & 1;
@@ -487,7 +506,6 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
         __syncwarp();
         if (lane == 0) { mbar_arrive(BAR(B_AFULL + s)); mbar_arrive(BAR(B_XEMPTY + xs)); }
       }
-      ita += NCH2;                                          // the epilogue warps produce the GEMM2 stages of this tile
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
@@ -497,7 +515,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
     const int row = q * 32 + lane;                          // row inside the tile
     const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
     const int et = threadIdx.x - EPI_WARP0 * 32;            // 0..255
-    uint32_t tl = 0, ita = 0;
+    uint32_t tl = 0;
 
     // per-column constants -> shared memory (broadcast reads in the hot loops)
     for (int i = et; i < HMAX; i += 256) c_b1[i] = p.b1 ? p.b1[i] : 0.f;
@@ -537,7 +555,6 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
 
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
         const int64_t grow = tile * BM + row;
-        ita += KS;                                          // GEMM1 stages of this tile belong to the converters
         mbar_wait(BAR(B_ACCFULL), tl & 1, p.err, 13);
         tc_fence_after();
         if (et == 0) trace_stamp(p, tl, 4);                  // accumulator complete
@@ -576,13 +593,12 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
               tacc[cc] += a;
             }
           }
-          const uint32_t s = (ita + c) % NST, ph = ((ita + c) / NST) & 1;
-          mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 14);
-          const uint32_t a_hi = smem_u32(sA + s * A_STAGE);
-          write_operand_row<FP16, LO>(a_hi, a_hi + A_OP_BYTES, row, hv);
+          const uint32_t r = (uint32_t)c & 3u, ph = (tl * 4 + ((uint32_t)c >> 2)) & 1u;
+          mbar_wait(BAR(B_G2EMPTY + r), ph ^ 1, p.err, 14);
+          write_operand_row<FP16, LO>(g2_a_hi(r), g2_a_lo(r), row, hv);
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(B_AFULL + s));
+          if (lane == 0) mbar_arrive(BAR(B_G2AFULL + r));
         };
         emit_chunk(half, keep_h[0]);
         emit_chunk(2 + half, keep_h[1]);
@@ -595,7 +611,6 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
           tmem_st32f(tq + (uint32_t)(c * 32), hv);
           emit_chunk(c, hv);
         }
-        ita += NCH2;
         tmem_wait_st();
         if (et == 0) trace_stamp(p, tl, 6);                  // E2 done (all my A2 chunks produced)
 
@@ -831,7 +846,7 @@ static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 template <int NPROD, bool FP16, int NST, int MODE, int ACT, int ATT>
 static int launch_fused(const CUtensorMap& mx, const FusedParams& p, int grid, cudaStream_t stream) {
   constexpr int NOP = NPROD == 3 ? 2 : 1;
-  const size_t smem = 1024 + (size_t)XS * X_SLOT_BYTES + (size_t)NST * NOP * (A_OP_BYTES + B_OP_BYTES) + 256 + 1024 + 4096 + 16 + (HMAX + 256) * 4 + 8 * 256 * 4;
+  const size_t smem = 1024 + (size_t)XS * X_SLOT_BYTES + (size_t)NST * NOP * (A_OP_BYTES + B_OP_BYTES) + 512 + 1024 + 4096 + 16 + (HMAX + 256) * 4 + 8 * 256 * 4;
   auto kern = mil_fused_kernel<NPROD, FP16, NST, MODE, ACT, ATT>;
   static bool attr_set = false;
   if (!attr_set) {
