@@ -93,6 +93,14 @@ int mil_sgemm_f32(const float* A, int64_t sAm, int64_t sAk, const int64_t* row_i
                   float* C, int64_t ldc, float* pre_out,
                   int64_t M, int64_t N, int64_t K, int act, int splitk, void* ws, size_t ws_bytes, mil_stream_t stream);
 
+/* Tensor-core variant of the NT form: Y[M,N] = act(X[M,K] W[N,K]^T + bias) through the fused pass's TMA -> 16-bit split ->
+ * tcgen05 pipeline (fp32-class results in MIL_PREC_BF16X3).  K % 32 == 0; N in {64,128,192,256,512}; pre_out nullable
+ * (pre-activation, ld = N).  ws >= mil_linear_tc_workspace_bytes(N, K) holds the weight image; ws_ready as above.
+ * Replaces the forward of the N-row projections (mhim.py:69, dsmil.py:62-70, nystrom_attention.py:52-57, merge.py:35-41). */
+int    mil_linear_act_tc_f32(const float* X, int64_t M, int K, const float* W, const float* bias, int N, int act, float* pre_out,
+                             float* Y, void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream);
+size_t mil_linear_tc_workspace_bytes(int N, int K);
+
 /* g_pre = g_y * act'(.) elementwise; `y_or_pre` is the activation OUTPUT for relu/tanh/sigmoid and the
  * PRE-activation for gelu.  n elements.  (autograd of nn.ReLU/GELU/Tanh/Sigmoid on the path) */
 int mil_act_bwd_f32(const float* g_y, const float* y_or_pre, int64_t n, int act, float* g_pre, mil_stream_t stream);

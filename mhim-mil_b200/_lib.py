@@ -29,6 +29,9 @@ _SIGS = {
     "mil_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mil_sgemm_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                               c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "mil_linear_act_tc_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
+                                      c_int, c_void_p]),
+    "mil_linear_tc_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mil_act_bwd_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "mil_colsum_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mil_softmax_pool_fwd_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

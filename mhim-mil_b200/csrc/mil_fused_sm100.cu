@@ -519,8 +519,12 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
 
     // per-column constants -> shared memory (broadcast reads in the hot loops)
     for (int i = et; i < HMAX; i += 256) c_b1[i] = p.b1 ? p.b1[i] : 0.f;
-    if (MODE == MODE_FUSED)
+    if (MODE == MODE_FUSED) {
       for (int i = et; i < 128; i += 256) { c_ba[i] = p.ba ? p.ba[i] : 0.f; c_wc[i] = p.wc[i]; }
+    } else {
+      for (int i = et; i < 128; i += 256) c_ba[i] = 0.f;
+    }
+    const float* c_zero = c_ba;                             // 32+ zeros (store mode only)
     named_bar_sync(1, 256);
 
     if (MODE == MODE_STORE) {
@@ -533,7 +537,17 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
         for (int c = half; c < nch; c += 2) {
           float hv[32];
           tmem_ld32f(tq + (uint32_t)(c * 32), hv);
-          bias_act32<-1>(hv, c_b1 + c * 32, p.act);
+          if (p.h_out) {                                      // pre-activation (needed by the GELU backward)
+            bias_act32<MIL_ACT_NONE>(hv, c_b1 + c * 32, 0);
+            if (grow < p.N) {
+              float* dst = p.h_out + grow * p.ldc + c * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(hv[j], hv[j + 1], hv[j + 2], hv[j + 3]);
+            }
+            bias_act32<-1>(hv, c_zero, p.act);
+          } else {
+            bias_act32<-1>(hv, c_b1 + c * 32, p.act);
+          }
           if (grow < p.N) {
             float* dst = p.c_out + grow * p.ldc + c * 32;
 #pragma unroll
@@ -996,5 +1010,38 @@ extern "C" int mil_umma_selftest_f32(const float* A, const float* B, float* C, i
   p.stats = nullptr; p.pooled = nullptr; p.counter = nullptr; p.Wcls = nullptr; p.bcls = nullptr; p.n_cls = 0; p.logits = nullptr;
   const int64_t n_tiles = ((int64_t)M + BM - 1) / BM;
   const int grid = grid_override((int)(n_tiles < num_sms() ? n_tiles : num_sms()));
+  return dispatch_fused(precision, MODE_STORE, mx, p, grid, stream);
+}
+
+extern "C" size_t mil_linear_tc_workspace_bytes(int N, int K) { return (size_t)N * K * 4 + 1024 + 64; }
+
+extern "C" int mil_linear_act_tc_f32(const float* X, int64_t M, int K, const float* W, const float* bias, int N, int act, float* pre_out,
+                                     float* Y, void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIL_CHECK_ARG(mil_device_supported(), "mil_linear_act_tc_f32: needs a compute-capability 10.x device");
+  MIL_CHECK_ARG(X && W && Y && ws && M > 0 && M < (1ll << 31) - 256, "mil_linear_act_tc_f32: bad argument");
+  MIL_CHECK_ARG(N >= 64 && N <= 512 && N % 64 == 0 && (N <= 256 || N == 512), "mil_linear_act_tc_f32: N=%d must be 64,128,192,256 or 512", N);
+  MIL_CHECK_ARG(K >= BK && K % BK == 0, "mil_linear_act_tc_f32: K=%d must be a positive multiple of %d", K, BK);
+  MIL_CHECK_ARG(precision >= 0 && precision <= 2, "mil_linear_act_tc_f32: bad precision");
+  MIL_CHECK_ARG((uintptr_t)X % 16 == 0 && (uintptr_t)W % 16 == 0 && (uintptr_t)Y % 16 == 0 && (!pre_out || (uintptr_t)pre_out % 16 == 0),
+                "mil_linear_act_tc_f32: pointers must be 16-byte aligned");
+  MIL_CHECK_ARG(ws_bytes >= mil_linear_tc_workspace_bytes(N, K), "mil_linear_act_tc_f32: workspace needs %zu bytes", mil_linear_tc_workspace_bytes(N, K));
+  uint8_t* w_img = (uint8_t*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  int* err = (int*)(w_img + (size_t)N * K * 4);
+  int rc;
+  if (!ws_ready) {
+    if ((rc = split_weights(W, N, K, w_img, precision, stream))) return rc;
+    MIL_CUDA(cudaMemsetAsync(err, 0, 4 * sizeof(int), stream));
+  }
+  CUtensorMap mx;
+  if ((rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)M, (uint64_t)K, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  FusedParams p;
+  p.N = M; p.D = K; p.nout = N; p.Da = 128; p.act = act; p.att_act = MIL_ACT_NONE;
+  p.b1 = bias; p.ba = nullptr; p.wc = nullptr; p.bc = nullptr; p.keep = nullptr; p.Wp = nullptr; p.C = 0;
+  p.s_out = nullptr; p.t_out = nullptr; p.h_out = pre_out; p.part = nullptr; p.c_out = Y; p.ldc = N; p.err = err; p.dbg = 0;
+  p.w1_img = w_img; p.wa_img = w_img; p.trace = nullptr;
+  p.stats = nullptr; p.pooled = nullptr; p.counter = nullptr; p.Wcls = nullptr; p.bcls = nullptr; p.n_cls = 0; p.logits = nullptr;
+  const int64_t n_tiles = (M + BM - 1) / BM;
+  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   return dispatch_fused(precision, MODE_STORE, mx, p, grid, stream);
 }

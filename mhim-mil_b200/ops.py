@@ -50,6 +50,66 @@ def _splitk_for(M, N, K):
     return int(max(1, min(want, (K + 511) // 512, 64)))
 
 
+# weight images of the tensor-core Linear, cached like the fused pass's (same validity rule)
+_TC_CACHE = {}
+TC_MIN_ROWS = 256            # below this the exact-fp32 CUDA-core GEMM is as fast and has no image to build
+
+
+def _tc_supported(M, N, K, W):
+    return (M >= TC_MIN_ROWS and K % 32 == 0 and K >= 32 and N % 64 == 0 and N >= 64 and W.is_contiguous() and W.data_ptr() % 16 == 0
+            and _lib.lib().mil_device_supported())
+
+
+def _tc_block(x, Wb, bb, act, pre_b, y_b, key_obj, blk, precision):
+    """One column block (<= 512 wide, contiguous rows of the weight) through mil_linear_act_tc_f32."""
+    import weakref
+    L = _lib.lib()
+    M, K = x.shape
+    N = Wb.shape[0]
+    key = (id(key_obj), blk, N, precision)
+    ver = (key_obj._version, key_obj.data_ptr(), tuple(key_obj.shape))
+    hit = _TC_CACHE.get(key)
+    if hit is not None and hit[0]() is key_obj and hit[1] == ver:
+        ws, ready = hit[2], 1
+    else:
+        ws, ready = _ws(L.mil_linear_tc_workspace_bytes(N, K), x.device), 0
+        if len(_TC_CACHE) > 256:
+            _TC_CACHE.clear()
+        _TC_CACHE[key] = (weakref.ref(key_obj), ver, ws)
+    check(L.mil_linear_act_tc_f32(ptr(x), M, K, ptr(Wb), ptr(bb), N, ACT[act], ptr(pre_b), ptr(y_b), ptr(ws), ws.numel(), ready,
+                                  PREC[precision], stream_ptr()), "mil_linear_act_tc_f32")
+
+
+def linear_forward(x, W, b, act, pre=None, precision=None):
+    """y = act(x W^T + b): tcgen05 path when the shape allows (column blocks of <= 512), else the fp32 CUDA-core GEMM."""
+    M, K = x.shape
+    N = W.shape[0]
+    precision = precision or DEFAULT_PRECISION
+    if not _tc_supported(M, N, K, W):
+        return sgemm(x, K, 1, W, K, 1, M, N, K, bias=b, act=act, pre_out=pre)
+    widths, left = [], N
+    while left > 0:                                   # 512-wide blocks, then one of 256 / 192 / 128 / 64
+        wdt = 512 if left >= 512 else (256 if left >= 256 else left)
+        widths.append(wdt)
+        left -= wdt
+    if len(widths) == 1:
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        _tc_block(x, W, b, act, pre, y, W, 0, precision)
+        return y
+    ys, o = [], 0
+    pres = []
+    for i, wdt in enumerate(widths):
+        y_b = torch.empty((M, wdt), dtype=torch.float32, device=x.device)
+        p_b = torch.empty((M, wdt), dtype=torch.float32, device=x.device) if pre is not None else None
+        _tc_block(x, W[o:o + wdt], None if b is None else b[o:o + wdt], act, p_b, y_b, W, i, precision)
+        ys.append(y_b)
+        pres.append(p_b)
+        o += wdt
+    if pre is not None:
+        pre.copy_(torch.cat(pres, dim=1))
+    return torch.cat(ys, dim=1)
+
+
 class _LinearAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, W, b, act):
@@ -59,7 +119,7 @@ class _LinearAct(torch.autograd.Function):
         N = W.shape[0]
         need_pre = act == "gelu" and (x.requires_grad or W.requires_grad)
         pre = torch.empty((M, N), dtype=torch.float32, device=x.device) if need_pre else None
-        y = sgemm(x, K, 1, W, K, 1, M, N, K, bias=b, act=act, pre_out=pre)
+        y = linear_forward(x, W, b, act, pre)
         ctx.act = act
         ctx.has_bias = b is not None
         ctx.save_for_backward(x, W, pre if need_pre else y)

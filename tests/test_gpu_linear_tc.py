@@ -1,0 +1,56 @@
+"""GPU: the tensor-core Linear(+bias+act) forward (mil_linear_act_tc_f32) against fp64, incl. multi-block widths and autograd."""
+import pytest
+import torch
+
+import cases
+from oracle import mil_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import mhimk
+    return mhimk.ops
+
+
+@pytest.mark.parametrize("M,N,Kd", [(256, 64, 32), (1000, 128, 512), (777, 192, 96), (3000, 512, 1024), (5000, 1536, 512), (2000, 1024, 512), (300, 320, 64)])
+@pytest.mark.parametrize("act", ["none", "relu", "gelu", "tanh"])
+def test_linear_forward_tc(K, M, N, Kd, act):
+    g = torch.Generator().manual_seed(M + N)
+    x, W, b = torch.randn(M, Kd, generator=g), torch.randn(N, Kd, generator=g) * 0.05, torch.randn(N, generator=g) * 0.1
+    pre = torch.empty(M, N, device="cuda")
+    y = K.linear_forward(x.cuda(), W.cuda(), b.cuda(), act, pre)
+    ref_pre = x.double() @ W.double().t() + b.double()
+    assert cases.rel_err(pre, ref_pre) < 2e-5
+    assert cases.rel_err(y, O.apply_act(ref_pre, act)) < 5e-5      # bf16x3 contraction (<= 1e-5) + the MUFU-based activation (<= 1e-6 abs)
+    y2 = K.linear_forward(x.cuda(), W.cuda(), None, act)
+    assert cases.rel_err(y2, O.apply_act(x.double() @ W.double().t(), act)) < 5e-5
+
+
+def test_linear_act_autograd_through_tc(K):
+    g = torch.Generator().manual_seed(4)
+    M, N, Kd = 1500, 512, 1024
+    x, W, b = torch.randn(M, Kd, generator=g), torch.randn(N, Kd, generator=g) * 0.03, torch.randn(N, generator=g) * 0.1
+    go = torch.randn(M, N, generator=g)
+    for act in ("gelu", "relu"):
+        Wd, bd = W.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+        yd = K.linear_act(x.cuda(), Wd, bd, act)
+        (yd * go.cuda()).sum().backward()
+        Wr, br = W.double().requires_grad_(True), b.double().requires_grad_(True)
+        pre_ref = x.double() @ Wr.t() + br
+        if act == "relu":
+            # ReLU's derivative is discontinuous: an element with |pre| ~ 1e-6 may sit on the other side of 0 in fp64 and flips a
+            # whole 1/M share of a gradient row.  Check the backward kernels against the gate the forward actually used.
+            gate = (yd.detach().cpu() > 0).double()
+            assert float((gate != (pre_ref.detach() > 0).double()).double().mean()) < 1e-4
+            ((pre_ref * gate) * go.double()).sum().backward()
+        else:
+            (O.apply_act(pre_ref, act) * go.double()).sum().backward()
+        assert cases.rel_err(Wd.grad, Wr.grad) < 1e-4 and cases.rel_err(bd.grad, br.grad) < 1e-4
+        with torch.no_grad():                                   # cached weight image must follow in-place updates
+            Wd.mul_(1.5)
+        y = K.linear_act(x.cuda(), Wd, bd, act)
+        assert cases.rel_err(y, O.apply_act(x.double() @ (1.5 * W.double()).t() + b.double(), act)) < 2e-5

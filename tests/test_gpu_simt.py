@@ -28,7 +28,7 @@ def test_sgemm_nt(K, M, N, Kd, act):
     g = torch.Generator().manual_seed(M * 31 + N)
     x, W, b = torch.randn(M, Kd, generator=g), torch.randn(N, Kd, generator=g) * 0.1, torch.randn(N, generator=g)
     ref = O.apply_act(x.double() @ W.double().t() + b.double(), act)
-    got = K.linear_act(dev(x), dev(W), dev(b), act)
+    got = K.sgemm(dev(x), Kd, 1, dev(W), Kd, 1, M, N, Kd, bias=dev(b), act=act)      # the exact-fp32 CUDA-core path
     assert cases.rel_err(got, ref) < (2e-5 if act in ('tanh', 'sigmoid') else 3e-6)   # fp32 accumulation over K, then a saturating act
 
 

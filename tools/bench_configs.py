@@ -1,0 +1,101 @@
+"""Step times of the BASELINE.json configs on one B200 (ours) next to the CPU oracle port, for profiles/round1_summary.md.
+cfg0 ABMIL gated fwd/bwd N=1024; cfg1 MHIM(attn) N=10k (teacher, student fwd, bwd); cfg2 MHIM(selfattn) N=50k forward_test /
+teacher; cfg3 MHIM(dsmil) N=10k D=1536; cfg4 is tools/bench_sharded.py (multi-GPU)."""
+import json, os, sys, time
+import torch
+import torch.nn.functional as F
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases, mhimk
+from mhimk import modules as M
+from oracle import mil_oracle as O
+
+dev = torch.device("cuda")
+LABEL = torch.tensor([1], device=dev)
+REPS = int(os.environ.get("CFG_REPS", 10))
+CPU = os.environ.get("CFG_CPU", "1") == "1"
+
+
+def gpu_time(fn, reps=REPS):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def cpu_time(fn, reps=3):
+    torch.set_num_threads(os.cpu_count())
+    fn()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+    return sorted(ts)[len(ts) // 2] * 1e3
+
+
+out = {}
+# ---- cfg0: gated ABMIL fwd+bwd, N=1024
+sd = cases.gated_state(1)
+g = M.AttentionGated(1024, 2, act="relu", dropout=0.0).to(dev).train(); g.load_state_dict({k: v.to(dev) for k, v in sd.items()})
+x = cases.make_bag(2, 1024, 1024).to(dev)
+def step0():
+    g.zero_grad(set_to_none=True)
+    F.cross_entropy(g(x), LABEL).backward()
+out["cfg0_gated_abmil_fwd_bwd_N1024_ms"] = gpu_time(step0)
+if CPU:
+    sdl = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xc = x.cpu()
+    def cpu0():
+        for v in sdl.values(): v.grad = None
+        F.cross_entropy(O.abmil_gated(sdl, xc, "relu"), torch.tensor([1])).backward()
+    out["cfg0_cpu_ms"] = cpu_time(cpu0)
+
+# ---- cfg1: MHIM(attn) N=10k D=1024, teacher + student fwd + bwd
+def mhim_cfg(base, N, D, tag, do_cpu=True, student=True):
+    kw = dict(cases.MHIM_KW, baseline=base, input_dim=D, dropout=0.0)
+    stu, tea = M.MHIM(**kw).to(dev).train(), M.MHIM(**kw).to(dev).train()
+    stu.load_state_dict({k: v.to(dev) for k, v in cases.mhim_state(1, base, D=D).items()})
+    tea.load_state_dict({k: v.to(dev) for k, v in cases.mhim_state(2, base, D=D).items()})
+    for m_ in list(stu.modules()) + list(tea.modules()):
+        if isinstance(m_, torch.nn.Dropout): m_.p = 0.0
+    xb = cases.make_bag(3, N, D).to(dev)
+    res = {}
+    def teacher():
+        return tea.forward_teacher(xb)
+    res["teacher_ms"] = gpu_time(teacher)
+    ct, sc = teacher()
+    tcf = ct[0] if base == "dsmil" else ct
+    if student:
+        def full():
+            stu.zero_grad(set_to_none=True)
+            ct_, sc_ = tea.forward_teacher(xb)
+            t_ = ct_[0] if base == "dsmil" else ct_
+            lg, loss, _, _ = stu(xb, sc_, t_, i=0)
+            lt = 0.5 * lg[0].view(1, -1) + 0.5 * lg[1].view(1, -1) if base == "dsmil" else lg
+            (F.cross_entropy(lt, LABEL) + 0.5 * loss).backward()
+        res["train_step_ms"] = gpu_time(full)
+    stu.eval()
+    res["forward_test_ms"] = gpu_time(lambda: stu.forward_test(xb))
+    if CPU and do_cpu:
+        cfg = O.MHIMConfig(**dict(cases.MHIM_KW, baseline=base, input_dim=D))
+        sds, sdt = cases.mhim_state(1, base, D=D), cases.mhim_state(2, base, D=D)
+        xc = xb.cpu()
+        with torch.no_grad():
+            res["cpu_forward_test_ms"] = cpu_time(lambda: O.mhim_forward_test(cfg, sds, xc), 2)
+            res["cpu_teacher_ms"] = cpu_time(lambda: O.mhim_forward_teacher(cfg, sdt, xc), 2)
+    out[tag] = res
+
+mhim_cfg("attn", 10000, 1024, "cfg1_mhim_attn_N10000_D1024")
+mhim_cfg("dsmil", 10000, 1536, "cfg3_mhim_dsmil_N10000_D1536")
+mhim_cfg("selfattn", 50000, 1024, "cfg2_mhim_selfattn_N50000_D1024", do_cpu=os.environ.get("CFG_CPU_BIG", "0") == "1", student=True)
+# plain TransMIL eval forward at N=50k
+t = M.TransMIL(1024, 2, dropout=0.0, act="relu").to(dev).eval()
+xb = cases.make_bag(5, 50000, 1024).to(dev)
+with torch.no_grad():
+    out["transmil_eval_fwd_N50000_ms"] = gpu_time(lambda: t(xb), 5)
+print(json.dumps(out, indent=1))
