@@ -29,18 +29,49 @@ __device__ __forceinline__ void warp_prefix(const int* sh, int warp, int& prefix
   total = t;
 }
 
-__global__ void __launch_bounds__(TK_THREADS) topk_kernel(const float* __restrict__ score, int64_t N, int64_t k, int largest,
+// Inclusive suffix sums over 256 histogram bins: suf[d] = sum_{d' >= d} hist[d'] for thread d < 256 (all threads must call).
+// Replaces a 256-step single-thread scan (a dependent chain of shared-memory loads: ~10k cycles per radix pass).
+__device__ __forceinline__ int64_t suffix_sum256(const int* hist, int64_t* wsum /*[8]*/) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int64_t v = 0;
+  if (tid < 256) {
+    v = hist[255 - tid];                                   // reversed: prefix over the reversed array = suffix
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) wsum[warp] = v;
+  }
+  __syncthreads();
+  if (tid < 256) {
+    for (int w = 0; w < warp; ++w) v += wsum[w];
+  }
+  __syncthreads();
+  return v;                                                // thread tid < 256 holds suf[255 - tid]
+}
+
+__global__ void __launch_bounds__(TK_THREADS) topk_kernel(const float* __restrict__ score, int64_t N, int64_t k, int largest, int64_t cap,
                                                           uint32_t* __restrict__ keyA, uint32_t* __restrict__ keyB,
                                                           int64_t* __restrict__ idxA, int64_t* __restrict__ idxB,
                                                           int64_t* __restrict__ idx_out) {
   __shared__ int hist[256];
   __shared__ int64_t base[256];
-  __shared__ int wcnt[32][256];
   __shared__ int cnt_gt[32], cnt_tie[32];
+  // dynamic shared memory: phases 1-2 cache the sortable keys of the first `cap` instances (4 B each: N = 50 000 fits), phase 3
+  // re-uses the same bytes for the per-warp digit counters of the stable scatter
+  extern __shared__ __align__(16) uint32_t dyn[];
+  uint32_t* skeys = dyn;
+  int (*wcnt)[256] = reinterpret_cast<int (*)[256]>(dyn);
   __shared__ uint32_t s_prefix;
   __shared__ int64_t s_need;
+  __shared__ int64_t wsum[8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
+
+  for (int64_t i = tid; i < min(N, cap); i += TK_THREADS) skeys[i] = sortable_key(score[i], largest);
+  __syncthreads();
+  auto key_at = [&](int64_t i) -> uint32_t { return i < cap ? skeys[i] : sortable_key(score[i], largest); };
 
   // ---- 1. radix select: T = key of the k-th element in descending key order; need = how many keys == T to take
   uint32_t prefix = 0, mask = 0;
@@ -48,20 +79,26 @@ __global__ void __launch_bounds__(TK_THREADS) topk_kernel(const float* __restric
   for (int shift = 24; shift >= 0; shift -= 8) {
     if (tid < 256) hist[tid] = 0;
     __syncthreads();
-    for (int64_t i = tid; i < N; i += TK_THREADS) {
-      const uint32_t key = sortable_key(score[i], largest);
-      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+    for (int64_t c0 = 0; c0 < N; c0 += TK_THREADS) {          // warp-uniform trip count (match_any needs the full warp)
+      const int64_t i = c0 + tid;
+      int d = 256 + lane;                                      // lanes without a candidate never match anybody
+      if (i < N) {
+        const uint32_t key = key_at(i);
+        if ((key & mask) == prefix) d = (int)((key >> shift) & 255u);
+      }
+      // the CAM scores sit on a few hundred values around 0.5, i.e. in one or two bins: aggregate per warp before the atomic
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      if (d < 256 && (peers & lt_mask) == 0) atomicAdd(&hist[d], __popc(peers));
     }
     __syncthreads();
-    if (tid == 0) {
-      int64_t cum = 0;
-      int d = 255;
-      for (; d > 0; --d) {
-        if (cum + hist[d] >= need) break;
-        cum += hist[d];
+    {
+      // the selected digit d is the largest one whose suffix count reaches `need`: suf[d] >= need > suf[d+1]
+      const int64_t suf = suffix_sum256(hist, wsum);         // thread t < 256: suf of digit 255 - t
+      if (tid < 256) {
+        const int d = 255 - tid;
+        const int64_t above = suf - hist[d];                 // keys with a larger digit
+        if (suf >= need && above < need) { s_need = need - above; s_prefix = prefix | ((uint32_t)d << shift); }
       }
-      s_need = need - cum;
-      s_prefix = prefix | ((uint32_t)d << shift);
     }
     __syncthreads();
     need = s_need;
@@ -79,7 +116,7 @@ __global__ void __launch_bounds__(TK_THREADS) topk_kernel(const float* __restric
     uint32_t key = 0;
     bool gt = false, tie = false;
     if (i < N) {
-      key = sortable_key(score[i], largest);
+      key = key_at(i);
       gt = key > T;
       tie = key == T;
     }
@@ -101,17 +138,23 @@ __global__ void __launch_bounds__(TK_THREADS) topk_kernel(const float* __restric
     __syncthreads();
   }
 
+  __syncthreads();                       // the key cache is dead from here on: its bytes become wcnt
   // ---- 3. stable LSD radix sort of the k winners by key, descending (stability keeps index-ascending among equals)
   uint32_t* kin = keyA; uint32_t* kout = keyB;
   int64_t* iin = idxA; int64_t* iout = idxB;
   for (int shift = 0; shift < 32; shift += 8) {
     if (tid < 256) hist[tid] = 0;
     __syncthreads();
-    for (int64_t i = tid; i < k; i += TK_THREADS) atomicAdd(&hist[(kin[i] >> shift) & 255u], 1);
+    for (int64_t c0 = 0; c0 < k; c0 += TK_THREADS) {
+      const int64_t i = c0 + tid;
+      const int d = i < k ? (int)((kin[i] >> shift) & 255u) : 256 + lane;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      if (d < 256 && (peers & lt_mask) == 0) atomicAdd(&hist[d], __popc(peers));
+    }
     __syncthreads();
-    if (tid == 0) {
-      int64_t run = 0;
-      for (int d = 255; d >= 0; --d) { base[d] = run; run += hist[d]; }
+    {
+      const int64_t suf = suffix_sum256(hist, wsum);
+      if (tid < 256) base[255 - tid] = suf - hist[255 - tid];  // descending order: bucket d starts after all larger digits
     }
     __syncthreads();
     for (int64_t c0 = 0; c0 < k; c0 += TK_THREADS) {
@@ -148,29 +191,32 @@ __global__ void __launch_bounds__(TK_THREADS) topk_kernel(const float* __restric
   for (int64_t i = tid; i < k; i += TK_THREADS) idx_out[i] = iin[i];
 }
 
-__global__ void __launch_bounds__(TK_THREADS) mask_from_indices_kernel(const int64_t* __restrict__ idx, int64_t k, int64_t N,
+__global__ void __launch_bounds__(TK_THREADS) mask_from_indices_kernel(const int64_t* __restrict__ idx, int64_t k, int64_t N, int64_t cap,
                                                                        int64_t* __restrict__ mask_ids, uint8_t* __restrict__ keep,
                                                                        int64_t* __restrict__ len_keep_out) {
   __shared__ int cnt[32];
+  extern __shared__ __align__(16) uint8_t sflag[];            // keep flags of the first `cap` instances (1 B each)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  for (int64_t i = tid; i < N; i += TK_THREADS) keep[i] = 1;
+  for (int64_t i = tid; i < min(N, cap); i += TK_THREADS) sflag[i] = 1;
+  for (int64_t i = cap + tid; i < N; i += TK_THREADS) keep[i] = 1;
   __syncthreads();
   for (int64_t j = tid; j < k; j += TK_THREADS) {
     const int64_t v = idx[j];
-    if (v >= 0 && v < N) keep[v] = 0;
+    if (v >= 0 && v < N) { if (v < cap) sflag[v] = 0; else keep[v] = 0; }
   }
   __syncthreads();
   int64_t run = 0;
   for (int64_t c0 = 0; c0 < N; c0 += TK_THREADS) {
     const int64_t i = c0 + tid;
-    const bool kp = i < N && keep[i];
+    const bool kp = i < N && (i < cap ? sflag[i] : keep[i]);
     const uint32_t b = __ballot_sync(0xffffffffu, kp);
     if (lane == 0) cnt[warp] = __popc(b);
     __syncthreads();
     int p, t;
     warp_prefix(cnt, warp, p, t);
     if (kp) mask_ids[run + p + __popc(b & lt_mask)] = i;
+    if (i < cap && i < N) keep[i] = kp ? 1 : 0;
     run += t;
     __syncthreads();
   }
@@ -195,7 +241,16 @@ extern "C" int mil_topk_f32(const float* score, int64_t N, int64_t k, int larges
   int64_t* idxB = idxA + N;
   uint32_t* keyA = (uint32_t*)(idxB + N);
   uint32_t* keyB = keyA + N;
-  topk_kernel<<<1, TK_THREADS, 0, (cudaStream_t)stream>>>(score, N, k, largest, keyA, keyB, idxA, idxB, idx_out);
+  // key cache: as many instances as fit next to the static buffers (>= the 32 KB the sort phase needs)
+  const size_t dyn_max = 200 * 1024, dyn_min = 32 * 256 * sizeof(int);
+  size_t dyn = (size_t)N * sizeof(uint32_t);
+  dyn = dyn < dyn_min ? dyn_min : (dyn > dyn_max ? dyn_max : dyn);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MIL_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max));
+    attr_set = true;
+  }
+  topk_kernel<<<1, TK_THREADS, dyn, (cudaStream_t)stream>>>(score, N, k, largest, (int64_t)(dyn / sizeof(uint32_t)), keyA, keyB, idxA, idxB, idx_out);
   MIL_LAUNCH_CHECK();
   return 0;
 }
@@ -204,7 +259,14 @@ extern "C" int mil_mask_from_indices(const int64_t* idx, int64_t k, int64_t N, i
                                      size_t ws_bytes, mil_stream_t stream) {
   (void)ws; (void)ws_bytes;
   MIL_CHECK_ARG(mask_ids && keep && len_keep_out && N > 0 && k >= 0 && k <= N && (idx || k == 0), "mil_mask_from_indices: bad arguments");
-  mask_from_indices_kernel<<<1, TK_THREADS, 0, (cudaStream_t)stream>>>(idx, k, N, mask_ids, keep, len_keep_out);
+  const size_t dyn_max = 200 * 1024;
+  const size_t dyn = (size_t)N < dyn_max ? (((size_t)N + 15) & ~(size_t)15) : dyn_max;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MIL_CUDA(cudaFuncSetAttribute(mask_from_indices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max));
+    attr_set = true;
+  }
+  mask_from_indices_kernel<<<1, TK_THREADS, dyn, (cudaStream_t)stream>>>(idx, k, N, (int64_t)dyn, mask_ids, keep, len_keep_out);
   MIL_LAUNCH_CHECK();
   return 0;
 }

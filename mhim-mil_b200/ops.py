@@ -146,8 +146,12 @@ class _LinearAct(torch.autograd.Function):
             ws = _ws(64 * N * 4, x.device)
             check(L.mil_colsum_f32(ptr(g_pre), M, N, ptr(gb), ptr(ws), ws.numel(), stream_ptr()), "mil_colsum_f32")
         if ctx.needs_input_grad[0]:
-            # gx[m,k] = sum_n g_pre[m,n] W[n,k]:  A(m,n) = g_pre[m*N + n], B(k,n) = W[n*K + k]
-            gx = sgemm(g_pre, N, 1, W, 1, K, M, K, N)
+            # gx[m,k] = sum_n g_pre[m,n] W[n,k].  With W^T materialised ([K,N], a few hundred KB) this is the NT form again and
+            # runs on the tensor cores; otherwise A(m,n) = g_pre[m*N + n], B(k,n) = W[n*K + k] on the CUDA cores.
+            if _tc_supported(M, K, N, W) and N % 32 == 0 and K % 64 == 0:
+                gx = linear_forward(g_pre.contiguous(), W.t().contiguous(), None, "none")
+            else:
+                gx = sgemm(g_pre, N, 1, W, 1, K, M, K, N)
         return gx, gW, gb, None
 
 
