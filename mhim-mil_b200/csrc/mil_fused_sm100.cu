@@ -13,14 +13,11 @@
 //
 // The same pipeline with a "store" epilogue is the tensor-core Linear(+bias+act) used to materialise h and as the
 // self-test of the TMA/UMMA plumbing (mil_umma_selftest_f32).
-#include <cuda.h>
 #include <stdlib.h>
 #include <utility>
 #include <vector>
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
 
-#include "mil_common.cuh"
+#include "mil_umma.cuh"
 
 namespace mil {
 
@@ -29,267 +26,15 @@ namespace mil {
 // ------------------------------------------------------------------------------------------------------------
 constexpr int BM = 128;                 // rows per tile (UMMA M)
 constexpr int BK = 32;                  // K elements per pipeline stage (two UMMA K=16 steps); 64-byte rows -> SWIZZLE_64B
-constexpr int HMAX = 512;               // accumulator columns = all of TMEM
 constexpr int XS = 3;                   // fp32 staging slots (128 rows x 32 floats, SWIZZLE_128B)
 constexpr int X_SLOT_BYTES = BM * BK * 4;           // 16384
 constexpr int A_OP_BYTES = BM * BK * 2;             // 8192  (one 16-bit operand tile)
 constexpr int B_OP_BYTES = HMAX * BK * 2;           // 32768
 constexpr int NUM_THREADS = 512;
 constexpr int EPI_WARP0 = 8;            // warps 8..15: epilogue; 4..7: converters; 0: X TMA; 1: MMA; 2: TMEM alloc; 3: W TMA
-constexpr uint64_t WAIT_TIMEOUT_CYCLES = 4000000000ull;   // ~2 s: trap instead of hanging the GPU on a pipeline bug
 
 enum { MODE_FUSED = 0, MODE_STORE = 1 };
 
-struct FusedParams {
-  int64_t N;            // rows
-  int D;                // K of GEMM1
-  int nout;             // N of GEMM1 (512 in fused mode)
-  int Da;               // N of GEMM2
-  int act, att_act;
-  const float* b1; const float* ba; const float* wc; const float* bc;
-  const uint8_t* keep; const float* Wp; int C;
-  float* s_out; float* t_out; float* h_out; float* part;
-  float* c_out; int64_t ldc;   // MODE_STORE
-  const uint8_t* w1_img; const uint8_t* wa_img;   // pre-swizzled 16-bit weight images (see split_weights_kernel)
-  float* stats; float* pooled; unsigned int* counter;      // in-kernel finalisation by the last CTA to finish
-  const float* Wcls; const float* bcls; int n_cls; float* logits;
-  int* err;
-  long long* trace;     // optional [16 tiles][16 slots] clock64 stamps of CTA 0 (MHIMK_TRACE=1), see tools/trace_fused.py
-  int dbg;              // MHIMK_DEBUG bitmask (timing attribution only): 1 skip W1 TMA, 2 skip X TMA, 4 skip GEMM1 MMA, 8 skip convert, 16 skip Wa TMA, 32 skip pooling, 64 skip GEMM2 MMA
-};
-
-// ------------------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if ((uint64_t)(clock64() - t0) > WAIT_TIMEOUT_CYCLES) {
-      if (err) atomicExch(err, code);
-      __threadfence_system();
-      asm volatile("trap;");
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-// 1-D bulk copy global -> shared (TMA engine, no tensor map): one request moves a whole pre-swizzled operand tile
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-#define TMEM_REGS32(v) \
-  "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), \
-  "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),  \
-  "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-#define TMEM_REGS32_IN(v) \
-  "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),   \
-  "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),    \
-  "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-
-// 32 lanes x 32 consecutive columns: lane i of the warp gets row (lane_base + i), v[j] = column (col + j)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
-      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : TMEM_REGS32(v) : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
-      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), TMEM_REGS32_IN(v) : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld();
-__device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float (&f)[32]) {
-  uint32_t v[32];
-  tmem_ld32(taddr, v);
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-}
-__device__ __forceinline__ void tmem_st32f(uint32_t taddr, const float (&f)[32]) {
-  uint32_t v[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(f[i]);
-  tmem_st32(taddr, v);
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-
-__device__ __forceinline__ void trace_stamp(const FusedParams& p, uint32_t tl, int slot) {
-  if (p.trace && blockIdx.x == 0 && tl < 16) p.trace[tl * 16 + slot] = clock64();
-}
-
-// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows are 64 B, 8-row groups are 512 B apart.
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address            bits [0,14)
-  d |= (uint64_t)1 << 16;                               // leading byte offset (unused for swizzled K-major) bits [16,30)
-  d |= (uint64_t)(512 >> 4) << 32;                      // stride byte offset = 512  bits [32,46)
-  d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell) bits [46,48)
-  d |= (uint64_t)4 << 61;                               // layout type SWIZZLE_64B  bits [61,64)
-  return d;
-}
-// cute::UMMA::InstrDescriptor for kind::f16: fp32 accumulate, A/B both K-major.
-__device__ __forceinline__ uint32_t make_idesc(int fp16, int n) {
-  const uint32_t fmt = fp16 ? 0u : 1u;                  // 0 = F16, 1 = BF16
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-
-// fp32 pair -> packed 16-bit hi (and the packed 16-bit rounding residual lo)
-template <bool FP16>
-__device__ __forceinline__ uint32_t pack_hi(float x0, float x1) {
-  uint32_t r;
-  if (FP16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
-  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
-  return r;
-}
-__device__ __forceinline__ uint32_t pack_lo_bf16(float x0, float x1, uint32_t hi) {
-  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xFFFF0000u);
-  return pack_hi<false>(x0 - h0, x1 - h1);
-}
-
-// Write one row (32 consecutive K elements) of a [128 x 32] 16-bit operand tile in the UMMA K-major SWIZZLE_64B layout.
-template <bool FP16, bool LO>
-__device__ __forceinline__ void write_operand_row(uint32_t a_hi, uint32_t a_lo, int row, const float (&x)[32]) {
-  const uint32_t row_off = (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 64u;
-  const uint32_t sw = (uint32_t)(row >> 1) & 3u;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      h[i] = pack_hi<FP16>(x[8 * c + 2 * i], x[8 * c + 2 * i + 1]);
-      if (LO) l[i] = pack_lo_bf16(x[8 * c + 2 * i], x[8 * c + 2 * i + 1], h[i]);
-    }
-    const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-    if (LO) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
-  }
-}
-
-// Short inline transcendental activations (MUFU ex2/rcp based).  Inlining libm's erff/tanhf/expf at every element made the
-// kernel 600 KB of SASS (instruction-cache bound) and calling them out of line cost ~250 cycles per element.
-//   tanh(x)    = 1 - 2 / (1 + e^{2x})                                   |abs err| <~ 5e-7
-//   sigmoid(x) = 1 / (1 + e^{-x})                                       |abs err| <~ 2e-7
-//   erf(z)     = 1 - (a1 t + ... + a5 t^5) e^{-z^2}, t = 1/(1 + p z)    |abs err| <= 1.5e-7 (Abramowitz-Stegun 7.1.26)
-__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.f - poly * t * __expf(-z * z);
-  return 0.5f * x * (1.f + copysignf(erf_abs, x));
-}
-// v[i] = act(v[i] + bias[i]); bias points into shared memory (broadcast reads).  ACT is a compile-time constant in the fused
-// kernel (one variant per instantiation keeps the epilogue small); ACT = -1 selects at run time (store mode only).
-template <int ACT>
-__device__ __forceinline__ void bias_act32(float (&v)[32], const float* bias, int act_rt) {
-#pragma unroll
-  for (int i = 0; i < 32; i += 4) {
-    const float4 b = *reinterpret_cast<const float4*>(bias + i);
-    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-  }
-  const int act = ACT >= 0 ? ACT : act_rt;
-  if (act == MIL_ACT_RELU) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-  } else if (act == MIL_ACT_GELU) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
-  } else if (act == MIL_ACT_TANH) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = tanh_fast(v[i]);
-  } else if (act == MIL_ACT_SIGMOID) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = sigmoid_fast(v[i]);
-  }
-}
-
-// column sums over the 32 lanes of a warp of v[0..31] (one value per column per lane): afterwards lane j holds sum_rows v_row[j].
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32]) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float keep = up ? v[i + s] : v[i];
-      const float give = up ? v[i] : v[i + s];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, give, s);
-    }
-  }
-  return v[0];
-}
-
-// two independent transposes interleaved (the single one is a 5-level dependent shuffle chain: latency bound)
-__device__ __forceinline__ void warp_transpose_sum2(float (&a)[32], float (&b)[32], float& ra, float& rb) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float ka = up ? a[i + s] : a[i], ga = up ? a[i] : a[i + s];
-      const float kb = up ? b[i + s] : b[i], gb = up ? b[i] : b[i + s];
-      a[i] = ka + __shfl_xor_sync(0xffffffffu, ga, s);
-      b[i] = kb + __shfl_xor_sync(0xffffffffu, gb, s);
-    }
-  }
-  ra = a[0];
-  rb = b[0];
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // the kernel
@@ -729,58 +474,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
         out[1] = l;
       }
 
-      // ---- grid-level finalisation: the last CTA to publish its partial merges all of them (log-sum-exp, fixed order ->
-      // deterministic), normalises the pooled vector and applies the classifier.  No extra launches on the critical path.
-      __threadfence();
-      named_bar_sync(1, 256);
-      int* flag = reinterpret_cast<int*>(s_part + 16);
-      if (et == 0) *flag = (atomicAdd(p.counter, 1u) == gridDim.x - 1) ? 1 : 0;
-      named_bar_sync(1, 256);
-      if (*flag) {
-        __threadfence();
-        const int np = (int)gridDim.x;                        // <= 148 partials
-        float* wgt = t_part;                                  // [np] exp(m_i - m)          (t_part holds 1024 floats)
-        float* sm_m = t_part + 256;                           // [np] m_i (-inf for idle partials)
-        float* sm_l = t_part + 512;                           // [np] l_i
-        for (int i = et; i < np; i += 256) {                  // independent, coalesced-ish loads: one L2 round trip
-          const float mi = __ldcg(p.part + (int64_t)i * (2 + HMAX)), li = __ldcg(p.part + (int64_t)i * (2 + HMAX) + 1);
-          sm_m[i] = li > 0.f ? mi : -INFINITY;
-          sm_l[i] = li;
-        }
-        named_bar_sync(1, 256);
-        float mg = -INFINITY;
-        for (int i = 0; i < np; ++i) mg = fmaxf(mg, sm_m[i]);
-        for (int i = et; i < np; i += 256) wgt[i] = sm_l[i] > 0.f ? expf(sm_m[i] - mg) : 0.f;
-        named_bar_sync(1, 256);
-        float lg = 0.f;
-        for (int i = 0; i < np; ++i) lg = fmaf(sm_l[i], wgt[i], lg);      // fixed order: identical in every thread
-        float* pooled_s = p_acc;                              // [512] merged pooled vector
-        {
-          const int c2 = et * 2;                              // 256 threads x 2 columns (records are 8-byte aligned: float2 loads)
-          float2 v = make_float2(0.f, 0.f);
-#pragma unroll 8
-          for (int i = 0; i < np; ++i) {
-            const float2 q2 = __ldcg(reinterpret_cast<const float2*>(p.part + (int64_t)i * (2 + HMAX) + 2 + c2));
-            const float wi = wgt[i];
-            v.x = fmaf(q2.x, wi, v.x); v.y = fmaf(q2.y, wi, v.y);
-          }
-          named_bar_sync(1, 256);                             // all reads of the old p_acc contents (CTA partial) are long done
-          v.x /= lg; v.y /= lg;
-          *reinterpret_cast<float2*>(pooled_s + c2) = v;
-          *reinterpret_cast<float2*>(p.pooled + c2) = v;
-        }
-        if (et == 0) { p.stats[0] = mg; p.stats[1] = lg; *p.counter = 0u; }
-        named_bar_sync(1, 256);
-        if (p.logits) {
-          const int wid = et >> 5;
-          for (int k = wid; k < p.n_cls; k += 8) {
-            float a = 0.f;
-            for (int c = lane; c < HMAX; c += 32) a = fmaf(pooled_s[c], p.Wcls[k * HMAX + c], a);
-            a = warp_sum(a);
-            if (lane == 0) p.logits[k] = a + (p.bcls ? p.bcls[k] : 0.f);
-          }
-        }
-      }
+      grid_finalize(p, et, lane, t_part, p_acc, reinterpret_cast<int*>(s_part + 16));
     }
   }
 
