@@ -8,12 +8,12 @@ OUT="$HERE/../libmhimk.so"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -I"$ROOT/include" -I"$HERE")
 mkdir -p "$HERE/build"
 pids=()
-for f in mil_api mil_simt mil_topk mil_fused_sm100; do
-  if [ ! -f "$HERE/build/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/build/$f.o" ] || [ "$HERE/mil_common.cuh" -nt "$HERE/build/$f.o" ] || [ "$ROOT/include/mhimk.h" -nt "$HERE/build/$f.o" ]; then
+for f in mil_api mil_simt mil_topk mil_fused_sm100 mil_fused2_sm100; do
+  if [ ! -f "$HERE/build/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/build/$f.o" ] || [ "$HERE/mil_common.cuh" -nt "$HERE/build/$f.o" ] || [ "$HERE/mil_umma.cuh" -nt "$HERE/build/$f.o" ] || [ "$ROOT/include/mhimk.h" -nt "$HERE/build/$f.o" ]; then
     "$NVCC" "${FLAGS[@]}" ${PTXAS_V:+-Xptxas -v} -c "$HERE/$f.cu" -o "$HERE/build/$f.o" &
     pids+=($!)
   fi
 done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
-"$NVCC" -shared -o "$OUT" "$HERE"/build/mil_api.o "$HERE"/build/mil_simt.o "$HERE"/build/mil_topk.o "$HERE"/build/mil_fused_sm100.o -lcudart
+"$NVCC" -shared -o "$OUT" "$HERE"/build/mil_api.o "$HERE"/build/mil_simt.o "$HERE"/build/mil_topk.o "$HERE"/build/mil_fused_sm100.o "$HERE"/build/mil_fused2_sm100.o -lcudart
 echo "built $OUT"

@@ -1,0 +1,587 @@
+// Pair pipeline of the fused ABMIL forward (sm_100a): two CTAs of a thread-block cluster (one TPC) share every
+// tcgen05.mma (cta_group::2, M = 128 -> 64 bag rows per CTA).  A 64-row x 512-column fp32 accumulator is 256 TMEM
+// columns, so TMEM holds TWO of them: GEMM1 of tile t+1 runs while the epilogue warps work on tile t, and the HBM stream of
+// the bag never pauses (the single-CTA pipeline of mil_fused_sm100.cu owns all 512 columns and has to serialise).
+//
+//   per CTA (rank r of the pair), per 128-row pair tile (its rows: tile * 128 + r * 64 .. + 64):
+//   HBM --TMA(SW128)--> fp32 staging [64 x 32] --converter warps--> 16-bit hi(/lo) A tiles (UMMA K-major SW64, 4 KB)
+//   L2  --TMA---------> W1 image tiles: this CTA's half (128 rows) of each 256-row N block; Wa image tiles (64 rows)
+//   leader CTA, one thread: tcgen05.mma.cta_group::2  pre[128 x 256] x 2 N blocks -> TMEM buffer (tile & 1)   (GEMM1)
+//   epilogue warps (both CTAs): h = act(pre + b1) -> 16-bit A2 tiles; h kept in TMEM / registers
+//   leader: tcgen05.mma.cta_group::2  u[128 x 128] = h Wa^T -> the first 64 columns of the same buffer          (GEMM2)
+//   epilogue warps: s = wc . f(u + ba) + bc, online softmax over rows, p += e^{s-m} h (warp-shuffle transposes)
+//
+// TMEM layout of a pair MMA with M = 128 ("2x2", cute::UMMA::tmem_frg_2sm): rows 0..63 of the CTA on lanes 0..63 for
+// columns n < N/2 and on lanes 64..127 for n >= N/2, N/2 TMEM columns per N block.
+//
+// Barriers: every "full" barrier (operands ready, accumulator drained) lives in the leader CTA and is arrived on by both
+// CTAs (remote mbarrier.arrive / cta_group::2 TMA complete_tx); every "empty"/"done" barrier is signalled in both CTAs by
+// one multicast tcgen05.commit.  All waits trap after ~2 s instead of hanging the GPU.
+#include <stdlib.h>
+
+#include "mil_umma.cuh"
+
+namespace mil {
+namespace pairk {
+
+constexpr int BMP = 128;                      // rows per pair tile (UMMA M)
+constexpr int BMC = 64;                       // rows per CTA
+constexpr int BK = 32;                        // K elements per stage (two UMMA K = 16 steps)
+constexpr int X_SLOT = BMC * BK * 4;          // 8192   fp32 staging slot
+constexpr int A_OP = BMC * BK * 2;            // 4096   one 16-bit A tile [64 x 32]
+constexpr int B_OP = 2 * 128 * BK * 2;        // 16384  this CTA's 128 rows of both 256-row N blocks: [blk 0 | blk 1]
+constexpr int A2_OP = A_OP;                   // 4096   GEMM2 A tile [64 x 32]
+constexpr int B2_OP = 64 * BK * 2;            // 4096   this CTA's 64 rows of Wa
+constexpr int G2S = 4;                        // GEMM2 ring slots (one per epilogue-warp column strip)
+constexpr int NUM_THREADS = 512;
+constexpr int EPI_WARP0 = 8;                  // warps 8..15 epilogue; 4..7 converters; 0 X TMA; 1 MMA; 2 TMEM alloc + Wa TMA; 3 W1 TMA
+constexpr int MISC_BYTES = 512 + 1024 + 4096 + 16 + (HMAX + 256) * 4 + 8 * 128 * 4;
+
+template <int NPROD, bool FP16, int NST, int XS, int ACT, int ATT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW1,
+                  const __grid_constant__ CUtensorMap mapWa, const FusedParams p) {
+  constexpr bool LO = NPROD == 3;
+  constexpr int NOP = LO ? 2 : 1;                              // operand tiles per stage (hi, lo)
+  constexpr uint32_t A_STAGE = NOP * A_OP, B_STAGE = NOP * B_OP, G2A_STAGE = NOP * A2_OP, G2B_STAGE = NOP * B2_OP;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sX = smem;                                          // XS x 8 KB
+  uint8_t* sA = sX + XS * X_SLOT;                              // NST x A_STAGE
+  uint8_t* sB = sA + NST * A_STAGE;                            // NST x B_STAGE
+  uint8_t* sA2 = sB + NST * B_STAGE;                           // G2S x G2A_STAGE
+  uint8_t* sB2 = sA2 + G2S * G2A_STAGE;                        // G2S x G2B_STAGE
+  uint8_t* sMisc = sB2 + G2S * G2B_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMisc);         // barrier block (512 B)
+  float* s_part = reinterpret_cast<float*>(sMisc + 512);       // [4 strips][64 rows] partial attention logits
+  float* t_part = s_part + 256;                                // [4 strips][64 rows][4] partial t (also grid_finalize scratch)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sMisc + 512 + 1024 + 4096);
+  float* c_b1 = reinterpret_cast<float*>(sMisc + 512 + 1024 + 4096 + 16);   // [512] feature bias
+  float* c_ba = c_b1 + HMAX;                                                 // [128] attention bias
+  float* c_wc = c_ba + 128;                                                  // [128] attention output weights
+  float* p_acc = c_wc + 128;                                                 // [8 warps][4 chunks][32 lanes] pooled partial sums
+
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  constexpr int B_XFULL = 0, B_XEMPTY = B_XFULL + XS, B_AFULL = B_XEMPTY + XS, B_BFULL = B_AFULL + NST, B_EMPTY = B_BFULL + NST,
+                B_ACCFULL = B_EMPTY + NST, B_ACCEMPTY = B_ACCFULL + 2, B_TAILFREE = B_ACCEMPTY + 2, B_UFULL = B_TAILFREE + 2,
+                B_G2AFULL = B_UFULL + 1, B_G2BFULL = B_G2AFULL + G2S, B_G2EMPTY = B_G2BFULL + G2S, B_COUNT = B_G2EMPTY + G2S;
+  static_assert(B_COUNT * 8 <= 512, "barrier block overflow");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                    // 0 = leader (issues every MMA of the pair)
+  auto LEADER = [&](int i) { return mapa_shared(BAR(i), 0); };  // cluster address of barrier i in the leader CTA
+  if (p.trace && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.trace[256 + 2 * blockIdx.x] = (long long)gt;
+  }
+  const int KS = p.D / BK;                                     // GEMM1 k-steps per tile
+  constexpr int NCH2 = HMAX / BK;                              // GEMM2 k-steps per tile (16)
+  const int64_t n_tiles = (p.N + BMP - 1) / BMP;
+  const int64_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < XS; ++i) { mbar_init(BAR(B_XFULL + i), 1); mbar_init(BAR(B_XEMPTY + i), 2); }
+    for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_AFULL + i), 4); mbar_init(BAR(B_BFULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACCFULL + i), 1); mbar_init(BAR(B_ACCEMPTY + i), 16); mbar_init(BAR(B_TAILFREE + i), 8); }
+    mbar_init(BAR(B_UFULL), 1);
+    for (int i = 0; i < G2S; ++i) { mbar_init(BAR(B_G2AFULL + i), 4); mbar_init(BAR(B_G2BFULL + i), 1); mbar_init(BAR(B_G2EMPTY + i), 1); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapW1); tma_prefetch_desc(&mapWa); }
+  if (warp == 2) tmem_alloc_pair(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                          // the peer's barriers are initialised before anyone signals them
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      // ===================== X producer: HBM -> fp32 staging (this CTA's 64 rows of the pair tile) =====================
+      if (lane == 0) {
+        uint32_t it = 0;
+        for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) {
+          const int row0 = (int)(tile * BMP + rank * BMC);
+          for (int ks = 0; ks < KS; ++ks, ++it) {
+            const uint32_t s = it % XS, ph = (it / XS) & 1;
+            mbar_wait(BAR(B_XEMPTY + s), ph ^ 1, p.err, 1);
+            mbar_expect_tx(BAR(B_XFULL + s), X_SLOT);
+            tma_load_2d(smem_u32(sX + s * X_SLOT), &mapX, BAR(B_XFULL + s), ks * BK, row0);
+          }
+        }
+      }
+    } else if (warp == 3) {
+      // ===================== W1 producer: L2 -> this CTA's half of the B operand of every k-step =====================
+      // Image rows are 256 B; one k-step of one CTA is NOP x 16 KB contiguous: [hi: N block 0 | N block 1][lo: ...].
+      if (lane == 0) {
+        uint32_t it = 0;
+        for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) {
+          for (int ks = 0; ks < KS; ++ks, ++it) {
+            const uint32_t s = it % NST, ph = (it / NST) & 1;
+            mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 2);
+            if (rank == 0) mbar_expect_tx(BAR(B_BFULL + s), 2 * B_STAGE);      // both CTAs' bytes land on the leader's barrier
+            tma_load_2d_pair(smem_u32(sB + s * B_STAGE), &mapW1, LEADER(B_BFULL + s), 0, (int)((ks * 2 + rank) * (B_STAGE / 256)));
+          }
+        }
+      }
+    } else if (warp == 2) {
+      // ===================== Wa producer: this CTA's 64 rows of every GEMM2 k-chunk =====================
+      if (lane == 0) {
+        uint32_t tl = 0;
+        for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs, ++tl) {
+          for (int c = 0; c < NCH2; ++c) {
+            const uint32_t r = c & 3, ph = (tl * 4 + (c >> 2)) & 1;
+            mbar_wait(BAR(B_G2EMPTY + r), ph ^ 1, p.err, 3);
+            if (rank == 0) mbar_expect_tx(BAR(B_G2BFULL + r), 2 * G2B_STAGE);
+            tma_load_2d_pair(smem_u32(sB2 + r * G2B_STAGE), &mapWa, LEADER(B_G2BFULL + r), 0, (int)((c * 2 + rank) * (G2B_STAGE / 256)));
+          }
+        }
+      }
+    } else if (warp == 1 && rank == 0) {
+      // ===================== MMA issuer (one thread of the leader CTA) =====================
+      // GEMM1 of tile t+1 and GEMM2 of tile t are interleaved by readiness: the thread never blocks on one of them.
+      if (lane == 0) {
+        const uint32_t idesc1 = make_idesc(FP16, 256, BMP), idesc2 = make_idesc(FP16, 128, BMP);
+        uint32_t T = 0;
+        for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) ++T;
+        uint32_t g1_t = 0, g1_ks = 0, it = 0, g2_t = 0, g2_c = 0;
+        bool acc_ok = false, tail_ok = false;
+        long long t_last = clock64();
+        while (g2_t < T) {
+          bool progress = false;
+          if (g2_t < g1_t) {                                   // GEMM1 of that tile has been issued completely
+            const uint32_t b2 = g2_t & 1;
+            if (!tail_ok) tail_ok = mbar_test_wait(BAR(B_TAILFREE + b2), (g2_t >> 1) & 1);
+            if (tail_ok) {
+              const uint32_t r = g2_c & 3, ph = (g2_t * 4 + (g2_c >> 2)) & 1;
+              if (mbar_test_wait(BAR(B_G2AFULL + r), ph) && mbar_test_wait(BAR(B_G2BFULL + r), ph)) {
+                tc_fence_after();
+                if (g2_c == 0) trace_stamp(p, g2_t, 2);
+                const uint32_t a0 = smem_u32(sA2 + r * G2A_STAGE), b0 = smem_u32(sB2 + r * G2B_STAGE);
+                const uint32_t d = tmem + b2 * 256;
+#pragma unroll
+                for (int k16 = 0; k16 < 2; ++k16) {
+                  const uint32_t acc = (g2_c | k16) ? 1u : 0u;
+                  const uint64_t ah = make_desc_sw64(a0 + k16 * 32), bh = make_desc_sw64(b0 + k16 * 32);
+                  umma_f16_pair(d, ah, bh, idesc2, acc);
+                  if (LO) {
+                    const uint64_t al = make_desc_sw64(a0 + A2_OP + k16 * 32), bl = make_desc_sw64(b0 + B2_OP + k16 * 32);
+                    umma_f16_pair(d, al, bh, idesc2, 1u);
+                    umma_f16_pair(d, ah, bl, idesc2, 1u);
+                  }
+                }
+                umma_commit_pair(BAR(B_G2EMPTY + r));
+                if (++g2_c == NCH2) {
+                  umma_commit_pair(BAR(B_UFULL));
+                  trace_stamp(p, g2_t, 3);
+                  g2_c = 0; ++g2_t; tail_ok = false;
+                }
+                progress = true;
+              }
+            }
+          }
+          if (g1_t < T) {
+            const uint32_t b1 = g1_t & 1;
+            if (!acc_ok) {
+              acc_ok = mbar_test_wait(BAR(B_ACCEMPTY + b1), ((g1_t >> 1) & 1) ^ 1);
+              if (acc_ok) { tc_fence_after(); trace_stamp(p, g1_t, 0); }
+            }
+            if (acc_ok) {
+              const uint32_t s = it % NST, ph = (it / NST) & 1;
+              if (mbar_test_wait(BAR(B_AFULL + s), ph) && mbar_test_wait(BAR(B_BFULL + s), ph)) {
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(sA + s * A_STAGE), b0 = smem_u32(sB + s * B_STAGE);
+#pragma unroll
+                for (int k16 = 0; k16 < 2; ++k16) {
+#pragma unroll
+                  for (int blk = 0; blk < 2; ++blk) {
+                    const uint32_t acc = (g1_ks | k16) ? 1u : 0u;
+                    const uint32_t d = tmem + b1 * 256 + blk * 128;
+                    const uint64_t ah = make_desc_sw64(a0 + k16 * 32), bh = make_desc_sw64(b0 + blk * 8192 + k16 * 32);
+                    umma_f16_pair(d, ah, bh, idesc1, acc);
+                    if (LO) {
+                      const uint64_t al = make_desc_sw64(a0 + A_OP + k16 * 32), bl = make_desc_sw64(b0 + B_OP + blk * 8192 + k16 * 32);
+                      umma_f16_pair(d, al, bh, idesc1, 1u);
+                      umma_f16_pair(d, ah, bl, idesc1, 1u);
+                    }
+                  }
+                }
+                umma_commit_pair(BAR(B_EMPTY + s));
+                ++it;
+                if (++g1_ks == (uint32_t)KS) {
+                  umma_commit_pair(BAR(B_ACCFULL + b1));
+                  trace_stamp(p, g1_t, 1);
+                  g1_ks = 0; ++g1_t; acc_ok = false;
+                }
+                progress = true;
+              }
+            }
+          }
+          if (progress) {
+            t_last = clock64();
+          } else if ((uint64_t)(clock64() - t_last) > WAIT_TIMEOUT_CYCLES) {
+            if (p.err) atomicExch(p.err, 100 + (int)(g1_t < T ? 1 : 0) + 2 * (int)(g2_t < g1_t ? 1 : 0) + 4 * (int)tail_ok + 8 * (int)acc_ok);
+            __threadfence_system();
+            asm volatile("trap;");
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    // ===================== converters: fp32 staging -> 16-bit hi/lo A tiles =====================
+    // Two groups of two warps alternate k-steps (one row of the 64-row slab per thread): each group has two k-step times
+    // for its wait -> load -> convert -> store -> fence -> arrive latency chain.
+    const int grp = (warp - 4) >> 1;
+    const int row = ((warp - 4) & 1) * 32 + lane;
+    uint32_t it = 0;
+    for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) {
+      for (int ks = 0; ks < KS; ++ks, ++it) {
+        if ((int)(it & 1) != grp) continue;
+        const uint32_t xs = it % XS, xph = (it / XS) & 1;
+        const uint32_t s = it % NST, ph = (it / NST) & 1;
+        mbar_wait(BAR(B_XFULL + xs), xph, p.err, 10);
+        float x[32];
+        const uint32_t src = smem_u32(sX + xs * X_SLOT) + (uint32_t)row * 128u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t a = src + (((uint32_t)j ^ ((uint32_t)row & 7u)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[4 * j]), "=f"(x[4 * j + 1]), "=f"(x[4 * j + 2]), "=f"(x[4 * j + 3]) : "r"(a));
+        }
+        mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 11);
+        const uint32_t a_hi = smem_u32(sA + s * A_STAGE);
+        write_operand_row<FP16, LO>(a_hi, a_hi + A_OP, row, x);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive_cluster(LEADER(B_AFULL + s)); mbar_arrive(BAR(B_XEMPTY + xs)); }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+    // ===================== epilogue warps =====================
+    // Warp (q, half): TMEM lanes 32 q .. +32 = rows (q & 1) * 32 + lane of this CTA; feature group g = q >> 1 (lanes 64..127
+    // hold the upper 128 columns of each 256-wide N block); half = N block.  Its strip: 128 features f0 .. f0 + 128, four
+    // 32-column chunks at TMEM columns half * 128 + 32 j of the tile's buffer.  strip id = half * 2 + g = its GEMM2 ring slot.
+    const int q = warp & 3, half = (warp - EPI_WARP0) >> 2, g = q >> 1, rg = q & 1;
+    const int row = rg * 32 + lane;
+    const int strip = half * 2 + g;
+    const int f0 = half * 256 + g * 128;
+    const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+    const int et = threadIdx.x - EPI_WARP0 * 32;             // 0..255
+    uint32_t tl = 0;
+
+    for (int i = et; i < HMAX; i += 256) c_b1[i] = p.b1 ? p.b1[i] : 0.f;
+    for (int i = et; i < 128; i += 256) { c_ba[i] = p.ba ? p.ba[i] : 0.f; c_wc[i] = p.wc[i]; }
+    named_bar_sync(1, 256);
+
+    float m_run = -INFINITY, l_run = 0.f;
+    float* prun = p_acc + (warp - EPI_WARP0) * 128;          // prun[j * 32 + lane] = feature f0 + 32 j + lane
+#pragma unroll
+    for (int j = 0; j < 4; ++j) prun[j * 32 + lane] = 0.f;
+    const float bc = p.bc ? p.bc[0] : 0.f;
+    const uint32_t a2_hi = smem_u32(sA2 + strip * G2A_STAGE);
+
+    for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs, ++tl) {
+      const uint32_t b = tl & 1;
+      const int64_t grow = tile * BMP + rank * BMC + row;
+      const uint32_t tb = tq + b * 256 + (uint32_t)(half * 128);        // this warp's strip in the tile's accumulator buffer
+      mbar_wait(BAR(B_ACCFULL + b), (tl >> 1) & 1, p.err, 13);
+      tc_fence_after();
+      if (et == 0) trace_stamp(p, tl, 4);
+
+      // E1 (N-block-0 warps): vacate the buffer's first 64 columns (they become GEMM2's accumulator); keep h in registers
+      float keep_h[2][32];
+      if (half == 0) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          tmem_ld32f(tb + (uint32_t)(j * 32), keep_h[j]);
+          bias_act32<ACT>(keep_h[j], c_b1 + f0 + j * 32, p.act);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(LEADER(B_TAILFREE + b));
+      }
+      if (et == 0) trace_stamp(p, tl, 5);
+
+      // E2: h chunk -> 16-bit A2 tile of this strip's ring slot (+ h back into TMEM for the pooling pass, + optional outputs)
+      float tacc[4] = {0.f, 0.f, 0.f, 0.f};
+      auto emit_chunk = [&](int j, const float (&hv)[32]) {
+        const int fc = f0 + j * 32;
+        if (p.h_out && grow < p.N) {
+          float* dst = p.h_out + grow * HMAX + fc;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(hv[i], hv[i + 1], hv[i + 2], hv[i + 3]);
+        }
+        if (p.t_out) {
+#pragma unroll 1
+          for (int cc = 0; cc < p.C; ++cc) {
+            const float4* wp = reinterpret_cast<const float4*>(p.Wp + cc * HMAX + fc);
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 w4 = __ldg(wp + i);
+              a = fmaf(hv[4 * i], w4.x, a); a = fmaf(hv[4 * i + 1], w4.y, a); a = fmaf(hv[4 * i + 2], w4.z, a); a = fmaf(hv[4 * i + 3], w4.w, a);
+            }
+            tacc[cc] += a;
+          }
+        }
+        const uint32_t ph = (tl * 4 + (uint32_t)j) & 1u;
+        mbar_wait(BAR(B_G2EMPTY + strip), ph ^ 1, p.err, 14);
+        write_operand_row<FP16, LO>(a2_hi, a2_hi + A2_OP, row, hv);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(LEADER(B_G2AFULL + strip));
+      };
+      if (half == 0) {
+        emit_chunk(0, keep_h[0]);
+        emit_chunk(1, keep_h[1]);
+      }
+#pragma unroll 1
+      for (int j = (half == 0 ? 2 : 0); j < 4; ++j) {
+        float hv[32];
+        tmem_ld32f(tb + (uint32_t)(j * 32), hv);
+        bias_act32<ACT>(hv, c_b1 + f0 + j * 32, p.act);
+        tmem_st32f(tb + (uint32_t)(j * 32), hv);
+        emit_chunk(j, hv);
+      }
+      tmem_wait_st();
+      if (et == 0) trace_stamp(p, tl, 6);
+
+      // E3: attention logit of every row: s = wc . f(u + ba) + bc.  u (N = 128) sits in the buffer's first 64 columns:
+      // lanes 0..63 hold Da 0..63, lanes 64..127 hold Da 64..127; this warp takes 32 of its 64 columns.
+      mbar_wait(BAR(B_UFULL), tl & 1, p.err, 15);
+      tc_fence_after();
+      if (et == 0) trace_stamp(p, tl, 7);
+      {
+        const int da0 = g * 64 + half * 32;
+        float uv[32];
+        tmem_ld32f(tq + b * 256 + (uint32_t)(half * 32), uv);
+        bias_act32<ATT>(uv, c_ba + da0, p.att_act);
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(c_wc + da0 + i);
+          s4[0] = fmaf(uv[i], w4.x, s4[0]); s4[1] = fmaf(uv[i + 1], w4.y, s4[1]);
+          s4[2] = fmaf(uv[i + 2], w4.z, s4[2]); s4[3] = fmaf(uv[i + 3], w4.w, s4[3]);
+        }
+        s_part[strip * 64 + row] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      }
+      if (p.t_out)
+        for (int cc = 0; cc < p.C; ++cc) t_part[(strip * 64 + row) * 4 + cc] = tacc[cc];
+      named_bar_sync(1, 256);
+      float sv = ((s_part[row] + s_part[64 + row]) + (s_part[128 + row] + s_part[192 + row])) + bc;
+      const bool valid = grow < p.N && (!p.keep || p.keep[grow]);
+      if (!valid) sv = -INFINITY;
+      if (strip == 0 && grow < p.N) {
+        if (p.s_out) p.s_out[grow] = sv;
+        if (p.t_out)
+          for (int cc = 0; cc < p.C; ++cc)
+            p.t_out[grow * p.C + cc] = (t_part[row * 4 + cc] + t_part[(64 + row) * 4 + cc]) + (t_part[(128 + row) * 4 + cc] + t_part[(192 + row) * 4 + cc]);
+      }
+      named_bar_sync(1, 256);                               // s_part / t_part may be overwritten by the next tile after this
+      if (et == 0) trace_stamp(p, tl, 8);
+
+      // online softmax over the 32 rows of this warp (the four warps that share these rows compute identical m, l)
+      const float m_new = fmaxf(m_run, warp_max(sv));
+      float w = 0.f, scale = 1.f;
+      if (m_new > -INFINITY) {
+        scale = (m_run > -INFINITY) ? expf(m_run - m_new) : 0.f;
+        w = valid ? expf(sv - m_new) : 0.f;
+      }
+      l_run = l_run * scale + warp_sum(w);
+      m_run = m_new;
+
+      // E4: p += sum_rows w * h over this warp's 128 features, two chunks per transpose step
+      if (half == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { keep_h[0][i] *= w; keep_h[1][i] *= w; }
+        float r0, r1;
+        warp_transpose_sum2(keep_h[0], keep_h[1], r0, r1);
+        prun[lane] = prun[lane] * scale + r0;
+        prun[32 + lane] = prun[32 + lane] * scale + r1;
+      }
+#pragma unroll 1
+      for (int j = (half == 0 ? 2 : 0); j < 4; j += 2) {
+        float ha[32], hb[32];
+        uint32_t va[32], vb[32];
+        tmem_ld32(tb + (uint32_t)(j * 32), va);
+        tmem_ld32(tb + (uint32_t)((j + 1) * 32), vb);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { ha[i] = __uint_as_float(va[i]) * w; hb[i] = __uint_as_float(vb[i]) * w; }
+        float r0, r1;
+        warp_transpose_sum2(ha, hb, r0, r1);
+        prun[j * 32 + lane] = prun[j * 32 + lane] * scale + r0;
+        prun[(j + 1) * 32 + lane] = prun[(j + 1) * 32 + lane] * scale + r1;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(LEADER(B_ACCEMPTY + b));
+      if (et == 0) trace_stamp(p, tl, 9);
+    }
+
+    // CTA partial: merge the 2 row groups -> part[blockIdx] = (m, l, P[512])
+    float* red_m = s_part;                                  // [2]
+    float* red_l = s_part + 2;                              // [2]
+    named_bar_sync(1, 256);
+    if (strip == 0 && lane == 0) { red_m[rg] = m_run; red_l[rg] = l_run; }
+    named_bar_sync(1, 256);
+    const float m_cta = fmaxf(red_m[0], red_m[1]);
+    const float f_0 = (red_m[0] > -INFINITY) ? expf(red_m[0] - m_cta) : 0.f, f_1 = (red_m[1] > -INFINITY) ? expf(red_m[1] - m_cta) : 0.f;
+    float* out = p.part + (int64_t)blockIdx.x * (2 + HMAX);
+    for (int c = et; c < HMAX; c += 256) {
+      const int hf = c >> 8, gg = (c >> 7) & 1, j = (c >> 5) & 3, ln = c & 31;
+      const float* base = p_acc + (hf * 4 + gg * 2) * 128 + j * 32 + ln;     // warp (hf, q = 2 gg + rg)
+      out[2 + c] = fmaf(base[0], f_0, base[128] * f_1);
+    }
+    if (et == 0) {
+      out[0] = m_cta;
+      out[1] = red_l[0] * f_0 + red_l[1] * f_1;
+    }
+    grid_finalize(p, et, lane, t_part, p_acc, reinterpret_cast<int*>(s_part + 16));
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                        // nobody exits while the peer may still signal its barriers
+  if (p.trace && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.trace[256 + 2 * blockIdx.x + 1] = (long long)gt;
+  }
+  if (warp == 2) { tc_fence_after(); tmem_dealloc_pair(tmem, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// fp32 weights -> pre-swizzled 16-bit operand images in the pair layout (once per weight version).
+// Every tile is the exact shared-memory image of a UMMA K-major SWIZZLE_64B operand tile (rows of 64 B = 32 elements):
+//   byte(r, c, e) = (r/8)*512 + (r%8)*64 + ((c ^ ((r>>1)&3))*16) + 2e,  c = 16-byte chunk inside the row.
+// W1 image: for k-step ks, CTA rank, operand op (hi, lo), N block blk: the 128 rows  blk*256 + rank*128 + [0,128)  (8 KB);
+//           order (ks, rank, op, blk) -> one k-step of one CTA is NOP x 16 KB contiguous.
+// Wa image: GEMM2 chunk c = 4 j + half*2 + g covers features half*256 + g*128 + 32 j .. + 32 (the order in which the epilogue
+//           strips produce A2 tiles); for chunk c, CTA rank, operand op: the 64 rows rank*64 + [0,64) (4 KB); order (c, rank, op).
+// ------------------------------------------------------------------------------------------------------------
+template <bool FP16, bool LO>
+__global__ void pair_split_w1_kernel(const float* __restrict__ w, int H, int K, uint8_t* __restrict__ img) {
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (row f, 16-byte chunk kc = k / 8)
+  const int kchunks = K / 8;
+  if (item >= (int64_t)H * kchunks) return;
+  const int f = (int)(item / kchunks), kc = (int)(item % kchunks);
+  const int ks = kc >> 2, c = kc & 3;
+  const int blk = f >> 8, rank = (f >> 7) & 1, r = f & 127;
+  const float4 a = *reinterpret_cast<const float4*>(w + (int64_t)f * K + kc * 8);
+  const float4 b = *reinterpret_cast<const float4*>(w + (int64_t)f * K + kc * 8 + 4);
+  uint32_t h[4], l[4];
+  h[0] = pack_hi<FP16>(a.x, a.y); h[1] = pack_hi<FP16>(a.z, a.w); h[2] = pack_hi<FP16>(b.x, b.y); h[3] = pack_hi<FP16>(b.z, b.w);
+  constexpr int NOPK = LO ? 2 : 1;
+  const size_t off = (size_t)(r >> 3) * 512 + (size_t)(r & 7) * 64 + (size_t)((c ^ ((r >> 1) & 3)) << 4);
+  uint8_t* dst = img + ((size_t)(ks * 2 + rank) * NOPK) * 16384 + (size_t)blk * 8192 + off;
+  *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (LO) {
+    l[0] = pack_lo_bf16(a.x, a.y, h[0]); l[1] = pack_lo_bf16(a.z, a.w, h[1]); l[2] = pack_lo_bf16(b.x, b.y, h[2]); l[3] = pack_lo_bf16(b.z, b.w, h[3]);
+    *reinterpret_cast<uint4*>(dst + 16384) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+template <bool FP16, bool LO>
+__global__ void pair_split_wa_kernel(const float* __restrict__ w, int Da, int K, uint8_t* __restrict__ img) {
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (row d, 16-byte chunk kc)
+  const int kchunks = K / 8;
+  if (item >= (int64_t)Da * kchunks) return;
+  const int d = (int)(item / kchunks), kc = (int)(item % kchunks);
+  const int fi = kc >> 2, c = kc & 3;                                       // fi = feature / 32
+  const int half = fi >> 3, g = (fi >> 2) & 1, j = fi & 3;
+  const int chunk = 4 * j + half * 2 + g;
+  const int rank = d >> 6, r = d & 63;
+  const float4 a = *reinterpret_cast<const float4*>(w + (int64_t)d * K + kc * 8);
+  const float4 b = *reinterpret_cast<const float4*>(w + (int64_t)d * K + kc * 8 + 4);
+  uint32_t h[4], l[4];
+  h[0] = pack_hi<FP16>(a.x, a.y); h[1] = pack_hi<FP16>(a.z, a.w); h[2] = pack_hi<FP16>(b.x, b.y); h[3] = pack_hi<FP16>(b.z, b.w);
+  constexpr int NOPK = LO ? 2 : 1;
+  const size_t off = (size_t)(r >> 3) * 512 + (size_t)(r & 7) * 64 + (size_t)((c ^ ((r >> 1) & 3)) << 4);
+  uint8_t* dst = img + ((size_t)(chunk * 2 + rank) * NOPK) * 4096 + off;
+  *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (LO) {
+    l[0] = pack_lo_bf16(a.x, a.y, h[0]); l[1] = pack_lo_bf16(a.z, a.w, h[1]); l[2] = pack_lo_bf16(b.x, b.y, h[2]); l[3] = pack_lo_bf16(b.z, b.w, h[3]);
+    *reinterpret_cast<uint4*>(dst + 4096) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+template <int NPROD, bool FP16, int NST, int XS, int ACT, int ATT>
+static int launch_pair(const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mwa, const FusedParams& p, int grid, cudaStream_t stream) {
+  constexpr int NOP = NPROD == 3 ? 2 : 1;
+  const size_t smem = 1024 + (size_t)XS * X_SLOT + (size_t)NST * NOP * (A_OP + B_OP) + (size_t)G2S * NOP * (A2_OP + B2_OP) + MISC_BYTES;
+  auto kern = mil_fused2_kernel<NPROD, FP16, NST, XS, ACT, ATT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  prof_begin(stream);
+  kern<<<grid, NUM_THREADS, smem, stream>>>(mx, mw1, mwa, p);
+  prof_end(stream);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int ACT, int ATT>
+static int dispatch_prec(int precision, const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mwa, const FusedParams& p, int grid,
+                         cudaStream_t stream) {
+  if (precision == MIL_PREC_BF16X3) return launch_pair<3, false, 3, 3, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+  if (precision == MIL_PREC_FP16) return launch_pair<1, true, 6, 6, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+  return launch_pair<1, false, 6, 6, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+}
+
+}  // namespace pairk
+
+size_t pair_weight_image_bytes(int D, int H, int Da) { return ((size_t)H * D + (size_t)Da * H) * 2 * sizeof(uint16_t); }
+
+int pair_build_images(const float* W1, int H, int D, const float* Wa, int Da, uint8_t* w1_img, uint8_t* wa_img, int precision, cudaStream_t stream) {
+  using namespace pairk;
+  const int64_t i1 = (int64_t)H * (D / 8), i2 = (int64_t)Da * (H / 8);
+  const unsigned b1 = (unsigned)((i1 + 255) / 256), b2 = (unsigned)((i2 + 255) / 256);
+  if (precision == MIL_PREC_BF16X3) {
+    pair_split_w1_kernel<false, true><<<b1, 256, 0, stream>>>(W1, H, D, w1_img);
+    pair_split_wa_kernel<false, true><<<b2, 256, 0, stream>>>(Wa, Da, H, wa_img);
+  } else if (precision == MIL_PREC_FP16) {
+    pair_split_w1_kernel<true, false><<<b1, 256, 0, stream>>>(W1, H, D, w1_img);
+    pair_split_wa_kernel<true, false><<<b2, 256, 0, stream>>>(Wa, Da, H, wa_img);
+  } else {
+    pair_split_w1_kernel<false, false><<<b1, 256, 0, stream>>>(W1, H, D, w1_img);
+    pair_split_wa_kernel<false, false><<<b2, 256, 0, stream>>>(Wa, Da, H, wa_img);
+  }
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+// p: every field of the fused pass filled in by the caller (mil_abmil_fused_fwd_f32), w1_img / wa_img in the pair layout.
+int pair_fused_launch(const float* X, FusedParams p, int precision, cudaStream_t stream) {
+  using namespace pairk;
+  const int NOP = precision == MIL_PREC_BF16X3 ? 2 : 1;
+  CUtensorMap mx, mw1, mwa;
+  int rc;
+  if ((rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)p.N, (uint64_t)p.D, BMC, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  const uint64_t w1_rows = (uint64_t)HMAX * p.D * 2 * NOP / 256, wa_rows = (uint64_t)128 * HMAX * 2 * NOP / 256;
+  if ((rc = make_map_2d(&mw1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, p.w1_img, w1_rows, 256, (uint32_t)(NOP * B_OP / 256), 256, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  if ((rc = make_map_2d(&mwa, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, p.wa_img, wa_rows, 256, (uint32_t)(NOP * B2_OP / 256), 256, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  const int64_t n_tiles = (p.N + BMP - 1) / BMP;
+  int pairs = num_sms() / 2;
+  if (n_tiles < pairs) pairs = (int)n_tiles;
+  const char* e = getenv("MHIMK_GRID");
+  if (e && atoi(e) >= 2 && atoi(e) / 2 < pairs) pairs = atoi(e) / 2;
+  const int grid = 2 * pairs;
+#define MIL_CASE(A, T) if (p.act == A && p.att_act == T) return dispatch_prec<A, T>(precision, mx, mw1, mwa, p, grid, stream);
+  MIL_CASE(MIL_ACT_RELU, MIL_ACT_TANH) MIL_CASE(MIL_ACT_GELU, MIL_ACT_TANH)
+  MIL_CASE(MIL_ACT_RELU, MIL_ACT_RELU) MIL_CASE(MIL_ACT_GELU, MIL_ACT_RELU)
+  MIL_CASE(MIL_ACT_RELU, MIL_ACT_GELU) MIL_CASE(MIL_ACT_GELU, MIL_ACT_GELU)
+#undef MIL_CASE
+  set_error("fused pass: unsupported activation pair act=%d att_act=%d (use the composed path)", p.act, p.att_act);
+  return -1;
+}
+
+}  // namespace mil

@@ -533,7 +533,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                        uint32_t box_cols, CUtensorMapSwizzle sw) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -2; }
@@ -551,6 +551,21 @@ static int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, c
 static bool g_profile = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 
+static cudaEvent_t g_prof_open = nullptr;
+void prof_begin(cudaStream_t stream) {
+  if (!g_profile) return;
+  cudaEventCreate(&g_prof_open);
+  cudaEventRecord(g_prof_open, stream);
+}
+void prof_end(cudaStream_t stream) {
+  if (!g_profile || !g_prof_open) return;
+  cudaEvent_t e1;
+  cudaEventCreate(&e1);
+  cudaEventRecord(e1, stream);
+  g_prof_events.push_back({g_prof_open, e1});
+  g_prof_open = nullptr;
+}
+
 template <int NPROD, bool FP16, int NST, int MODE, int ACT, int ATT>
 static int launch_fused(const CUtensorMap& mx, const FusedParams& p, int grid, cudaStream_t stream) {
   constexpr int NOP = NPROD == 3 ? 2 : 1;
@@ -561,15 +576,14 @@ static int launch_fused(const CUtensorMap& mx, const FusedParams& p, int grid, c
     MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (g_profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
+  prof_begin(stream);
   kern<<<grid, NUM_THREADS, smem, stream>>>(mx, p);
-  if (g_profile) { cudaEventRecord(e1, stream); g_prof_events.push_back({e0, e1}); }
+  prof_end(stream);
   MIL_LAUNCH_CHECK();
   return 0;
 }
 
-static int debug_mask() {
+int debug_mask() {
   const char* e = getenv("MHIMK_DEBUG");
   return e ? atoi(e) : 0;
 }
@@ -642,6 +656,15 @@ extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, 
                                        float* stats, float* pooled, const float* Wcls, const float* bcls, int n_cls, float* logits,
                                        void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  // bits 8..15 of `precision` select the pipeline: 0 = default (pair), MIL_PIPE_SINGLE, MIL_PIPE_PAIR; MHIMK_PIPELINE=1|2 overrides the default
+  int pipeline = (precision >> 8) & 0xFF;
+  precision &= 0xFF;
+  if (pipeline == 0) {
+    const char* e = getenv("MHIMK_PIPELINE");
+    pipeline = e ? atoi(e) : 0;
+    if (pipeline != 1 && pipeline != 2) pipeline = 2;
+  }
+  MIL_CHECK_ARG(pipeline == 1 || pipeline == 2, "mil_abmil_fused_fwd_f32: bad pipeline %d", pipeline);
   MIL_CHECK_ARG(mil_device_supported(), "mil_abmil_fused_fwd_f32: needs a compute-capability 10.x device (tcgen05/TMEM/TMA)");
   MIL_CHECK_ARG(X && W1 && b1 && Wa && wc && part && stats && pooled && ws, "mil_abmil_fused_fwd_f32: null argument");
   MIL_CHECK_ARG(N > 0 && N < (1ll << 31) - 256, "mil_abmil_fused_fwd_f32: N=%lld out of range", (long long)N);
@@ -662,12 +685,16 @@ extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, 
   MIL_CHECK_ARG(!logits || (Wcls && n_cls >= 1 && n_cls <= 64), "mil_abmil_fused_fwd_f32: logits needs Wcls and 1 <= n_cls <= 64");
   if (!ws_ready) {   // 16-bit operand images of the weights: reusable across calls until the weights change (ws_ready = 1)
     MIL_CHECK_ARG((uintptr_t)W1 % 16 == 0 && (uintptr_t)Wa % 16 == 0, "mil_abmil_fused_fwd_f32: weights must be 16-byte aligned");
-    if ((rc = split_weights(W1, H, D, w1_img, precision, stream))) return rc;
-    if ((rc = split_weights(Wa, Da, H, wa_img, precision, stream))) return rc;
+    if (pipeline == 2) {
+      if ((rc = pair_build_images(W1, H, D, Wa, Da, w1_img, wa_img, precision, stream))) return rc;
+    } else {
+      if ((rc = split_weights(W1, H, D, w1_img, precision, stream))) return rc;
+      if ((rc = split_weights(Wa, Da, H, wa_img, precision, stream))) return rc;
+    }
     MIL_CUDA(cudaMemsetAsync(err, 0, 4 * sizeof(int), stream));
   }
   CUtensorMap mx;
-  if ((rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)N, (uint64_t)D, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if (pipeline == 1 && (rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)N, (uint64_t)D, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
 
   FusedParams p;
   p.N = N; p.D = D; p.nout = H; p.Da = Da; p.act = act; p.att_act = att_act;
@@ -675,6 +702,7 @@ extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, 
   p.s_out = s_out; p.t_out = t_out; p.h_out = h_out; p.part = part; p.c_out = nullptr; p.ldc = 0; p.err = err; p.dbg = debug_mask(); p.w1_img = w1_img; p.wa_img = wa_img;
   p.stats = stats; p.pooled = pooled; p.counter = (unsigned int*)(err + 1); p.Wcls = Wcls; p.bcls = bcls; p.n_cls = n_cls; p.logits = logits;
   p.trace = getenv("MHIMK_TRACE") ? (long long*)(((uintptr_t)(err + 4) + 63) & ~(uintptr_t)63) : nullptr;
+  if (pipeline == 2) return pair_fused_launch(X, p, precision, stream);
   const int64_t n_tiles = (N + BM - 1) / BM;
   const int grid = grid_override((int)(n_tiles < num_sms() ? n_tiles : num_sms()));
   return dispatch_fused(precision, MODE_FUSED, mx, p, grid, stream);

@@ -271,10 +271,23 @@ def mask_from_indices(idx: torch.Tensor, n: int):
 _WS_CACHE = {}
 
 
-def _fused_workspace(W1, Wa, precision):
+PIPELINES = {"single": 1, "pair": 2}
+
+
+def _pipeline(name):
+    """'pair' (default: two CTAs share every MMA, double-buffered TMEM) or 'single' (one CTA per tile); MHIMK_PIPELINE=1|2 sets the default."""
+    import os
+    if name in (None, "auto"):
+        name = {"1": "single", "2": "pair"}.get(os.environ.get("MHIMK_PIPELINE", ""), "pair")
+    if name not in PIPELINES:
+        raise ValueError(f"mhimk: unknown fused pipeline {name!r}")
+    return name
+
+
+def _fused_workspace(W1, Wa, precision, pipeline="pair"):
     import weakref
     L = _lib.lib()
-    key = (id(W1), id(Wa), precision)
+    key = (id(W1), id(Wa), precision, pipeline)
     ver = (W1._version, Wa._version, W1.data_ptr(), Wa.data_ptr(), tuple(W1.shape), tuple(Wa.shape))
     hit = _WS_CACHE.get(key)
     if hit is not None and hit[0]() is W1 and hit[1]() is Wa and hit[2] == ver:
@@ -288,7 +301,7 @@ def _fused_workspace(W1, Wa, precision):
 
 @torch.no_grad()
 def abmil_fused_forward(x, W1, b1, act, Wa, ba, wc, bc, att_act="tanh", keep=None, Wp=None, want_scores=False, want_h=False,
-                        precision: str = DEFAULT_PRECISION, Wcls=None, bcls=None):
+                        precision: str = DEFAULT_PRECISION, Wcls=None, bcls=None, pipeline=None):
     """One streaming pass over x [N,D]: returns dict(pooled[H], stats[2] = (m, l), s[N]?, t[N,C]?, h[N,H]?, part).
 
     h = act(x W1^T + b1); s = wc . att_act(Wa h + ba) + bc; pooled = softmax_N(s) @ h; logits = Wcls pooled + bcls when a
@@ -309,10 +322,12 @@ def abmil_fused_forward(x, W1, b1, act, Wa, ba, wc, bc, att_act="tanh", keep=Non
     h = torch.empty((N, H), dtype=torch.float32, device=dev) if want_h else None
     ncls = Wcls.shape[0] if Wcls is not None else 0
     logits = torch.empty((1, ncls), dtype=torch.float32, device=dev) if Wcls is not None else None
-    ws, ready = _fused_workspace(W1, Wa, precision)
+    pipeline = _pipeline(pipeline)
+    ws, ready = _fused_workspace(W1, Wa, precision, pipeline)
     check(L.mil_abmil_fused_fwd_f32(ptr(x), N, D, H, ptr(W1), ptr(b1), ACT[act], ptr(Wa), ptr(ba), None, None, Da, ACT[att_act], ptr(wc),
                                     ptr(bc), ptr(keep), ptr(Wp), C, ptr(s), ptr(t), ptr(h), ptr(part), ptr(stats), ptr(pooled),
-                                    ptr(Wcls), ptr(bcls), ncls, ptr(logits), ptr(ws), ws.numel(), ready, PREC[precision], stream_ptr()),
+                                    ptr(Wcls), ptr(bcls), ncls, ptr(logits), ptr(ws), ws.numel(), ready, PREC[precision] | (PIPELINES[pipeline] << 8),
+                                    stream_ptr()),
           "mil_abmil_fused_fwd_f32")
     return {"pooled": pooled, "stats": stats, "s": s, "t": t, "h": h, "part": part, "logits": logits}
 

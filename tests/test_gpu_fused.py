@@ -30,10 +30,11 @@ def run_oracle(sd, x, act, keep=None):
     return h, s, a @ h
 
 
+@pytest.mark.parametrize("pipe", ["pair", "single"])
 @pytest.mark.parametrize("prec", ["bf16x3", "fp16", "bf16"])
 @pytest.mark.parametrize("N,act,kind", [(1, "relu", "randn"), (100, "gelu", "randn"), (128, "relu", "randn"), (129, "relu", "relu"),
                                         (1024, "gelu", "randn"), (4099, "relu", "randn"), (50000, "relu", "randn")])
-def test_fused_forward(K, prec, N, act, kind):
+def test_fused_forward(K, pipe, prec, N, act, kind):
     sd = cases.abmil_state(100 + N)
     x = cases.make_bag(200 + N, N, 1024, kind)
     h_ref, s_ref, p_ref = run_oracle(sd, x, act)
@@ -41,7 +42,7 @@ def test_fused_forward(K, prec, N, act, kind):
     Wp = torch.randn(2, 512, generator=torch.Generator().manual_seed(1)) * 0.05
     out = K.abmil_fused_forward(x[0].cuda(), c["feature.0.weight"], c["feature.0.bias"], act, c["attention.0.weight"], c["attention.0.bias"],
                                 c["attention.2.weight"], c["attention.2.bias"], "tanh", Wp=Wp.cuda(), want_scores=True, want_h=(N <= 4099),
-                                precision=prec, Wcls=c["classifier.weight"], bcls=c["classifier.bias"])
+                                precision=prec, Wcls=c["classifier.weight"], bcls=c["classifier.bias"], pipeline=pipe)
     torch.cuda.synchronize()
     assert cases.rel_err(out["pooled"], p_ref) < TOL[prec]
     assert cases.rel_err(out["s"], s_ref) < TOL[prec] * 3
@@ -57,7 +58,8 @@ def test_fused_forward(K, prec, N, act, kind):
     assert cases.rel_err(stats[1], torch.exp(s_ref - s_ref.max()).sum()) < 30 * TOL[prec]
 
 
-def test_fused_forward_with_keep_mask(K):
+@pytest.mark.parametrize("pipe", ["pair", "single"])
+def test_fused_forward_with_keep_mask(K, pipe):
     N = 3000
     sd = cases.abmil_state(7)
     x = cases.make_bag(8, N, 1024)
@@ -65,7 +67,7 @@ def test_fused_forward_with_keep_mask(K):
     _, s_ref, p_ref = run_oracle(sd, x, "gelu", keep)
     c = {k: v.cuda() for k, v in sd.items()}
     out = K.abmil_fused_forward(x[0].cuda(), c["feature.0.weight"], c["feature.0.bias"], "gelu", c["attention.0.weight"], c["attention.0.bias"],
-                                c["attention.2.weight"], c["attention.2.bias"], "tanh", keep=keep.cuda(), want_scores=True)
+                                c["attention.2.weight"], c["attention.2.bias"], "tanh", keep=keep.cuda(), want_scores=True, pipeline=pipe)
     assert cases.rel_err(out["pooled"], p_ref) < 1e-4
     sk = out["s"].cpu()
     assert torch.isinf(sk[keep == 0]).all() and cases.rel_err(sk[keep == 1], s_ref[keep == 1]) < 3e-4
