@@ -33,9 +33,15 @@ constexpr int B_OP = 2 * 128 * BK * 2;        // 16384  this CTA's 128 rows of b
 constexpr int A2_OP = A_OP;                   // 4096   GEMM2 A tile [64 x 32]
 constexpr int B2_OP = 64 * BK * 2;            // 4096   this CTA's 64 rows of Wa
 constexpr int G2S = 4;                        // GEMM2 ring slots (one per epilogue-warp column strip)
+constexpr int QD = 2;                         // GEMM1 k-steps the issuer keeps queued in the tensor pipe
 constexpr int NUM_THREADS = 512;
-constexpr int EPI_WARP0 = 8;                  // warps 8..15 epilogue; 4..7 converters; 0 X TMA; 1 MMA; 2 TMEM alloc + Wa TMA; 3 W1 TMA
+constexpr int EPI_WARP0 = 8;                  // warps 8..15 epilogue; 4..7 converters; 0 bag + W1 TMA; 1 GEMM1 issue; 2 TMEM alloc + Wa TMA; 3 GEMM2 issue
 constexpr int MISC_BYTES = 512 + 1024 + 4096 + 16 + (HMAX + 256) * 4 + 8 * 128 * 4;
+
+// k-step stamps of CTA 0 (MHIMK_TRACE=1): series x first 64 k-steps, see tools/trace_ksteps.py
+__device__ __forceinline__ void kstamp(const FusedParams& p, int series, uint32_t it) {
+  if (p.trace && blockIdx.x == 0 && it < 64) p.trace[1024 + series * 64 + it] = clock64();
+}
 
 template <int NPROD, bool FP16, int NST, int XS, int ACT, int ATT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
@@ -64,9 +70,10 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  constexpr int B_XFULL = 0, B_XEMPTY = B_XFULL + XS, B_AFULL = B_XEMPTY + XS, B_BFULL = B_AFULL + NST, B_EMPTY = B_BFULL + NST,
+  // FULL[s] (leader): 4 converter warps of the pair + the W1 producer's expect_tx arrival + both CTAs' W1 bytes; G2FULL[r] likewise
+  constexpr int B_XFULL = 0, B_XEMPTY = B_XFULL + XS, B_FULL = B_XEMPTY + XS, B_EMPTY = B_FULL + NST,
                 B_ACCFULL = B_EMPTY + NST, B_ACCEMPTY = B_ACCFULL + 2, B_TAILFREE = B_ACCEMPTY + 2, B_UFULL = B_TAILFREE + 2,
-                B_G2AFULL = B_UFULL + 1, B_G2BFULL = B_G2AFULL + G2S, B_G2EMPTY = B_G2BFULL + G2S, B_COUNT = B_G2EMPTY + G2S;
+                B_G2FULL = B_UFULL + 1, B_G2EMPTY = B_G2FULL + G2S, B_COUNT = B_G2EMPTY + G2S;
   static_assert(B_COUNT * 8 <= 512, "barrier block overflow");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,10 +91,10 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < XS; ++i) { mbar_init(BAR(B_XFULL + i), 1); mbar_init(BAR(B_XEMPTY + i), 2); }
-    for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_AFULL + i), 4); mbar_init(BAR(B_BFULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_FULL + i), 5); mbar_init(BAR(B_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACCFULL + i), 1); mbar_init(BAR(B_ACCEMPTY + i), 16); mbar_init(BAR(B_TAILFREE + i), 8); }
     mbar_init(BAR(B_UFULL), 1);
-    for (int i = 0; i < G2S; ++i) { mbar_init(BAR(B_G2AFULL + i), 4); mbar_init(BAR(B_G2BFULL + i), 1); mbar_init(BAR(B_G2EMPTY + i), 1); }
+    for (int i = 0; i < G2S; ++i) { mbar_init(BAR(B_G2FULL + i), 5); mbar_init(BAR(B_G2EMPTY + i), 1); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -102,30 +109,38 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
-      // ===================== X producer: HBM -> fp32 staging (this CTA's 64 rows of the pair tile) =====================
+      // ===================== bag + W1 producer =====================
+      // X: HBM -> fp32 staging (this CTA's 64 rows of the pair tile).  W1: L2 -> this CTA's half of the B operand of every
+      // k-step (image rows are 256 B; one k-step of one CTA is NOP x 16 KB contiguous: [hi: N block 0 | N block 1][lo: ...]).
+      // One thread drives both streams; the W1 stream trails the bag stream by XS k-steps so that the bag prefetch keeps its
+      // full depth (XS staging slots + NST converted stages) when the operand ring is full.
       if (lane == 0) {
-        uint32_t it = 0;
-        for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) {
-          const int row0 = (int)(tile * BMP + rank * BMC);
-          for (int ks = 0; ks < KS; ++ks, ++it) {
+        uint32_t total = 0;
+        for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) total += (uint32_t)KS;
+        int64_t xtile = pair_id;
+        int xks = 0, wks = 0;
+        for (uint32_t it = 0; it < total + XS; ++it) {
+          if (it < total) {
             const uint32_t s = it % XS, ph = (it / XS) & 1;
             mbar_wait(BAR(B_XEMPTY + s), ph ^ 1, p.err, 1);
-            mbar_expect_tx(BAR(B_XFULL + s), X_SLOT);
-            tma_load_2d(smem_u32(sX + s * X_SLOT), &mapX, BAR(B_XFULL + s), ks * BK, row0);
+            kstamp(p, 6, it);
+            if (p.dbg & 2) mbar_arrive(BAR(B_XFULL + s));
+            else {
+              mbar_expect_tx(BAR(B_XFULL + s), X_SLOT);
+              tma_load_2d(smem_u32(sX + s * X_SLOT), &mapX, BAR(B_XFULL + s), xks * BK, (int)(xtile * BMP + rank * BMC));
+            }
+            if (++xks == KS) { xks = 0; xtile += n_pairs; }
           }
-        }
-      }
-    } else if (warp == 3) {
-      // ===================== W1 producer: L2 -> this CTA's half of the B operand of every k-step =====================
-      // Image rows are 256 B; one k-step of one CTA is NOP x 16 KB contiguous: [hi: N block 0 | N block 1][lo: ...].
-      if (lane == 0) {
-        uint32_t it = 0;
-        for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) {
-          for (int ks = 0; ks < KS; ++ks, ++it) {
-            const uint32_t s = it % NST, ph = (it / NST) & 1;
+          if (it >= (uint32_t)XS) {
+            const uint32_t iw = it - XS, s = iw % NST, ph = (iw / NST) & 1;
             mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 2);
-            if (rank == 0) mbar_expect_tx(BAR(B_BFULL + s), 2 * B_STAGE);      // both CTAs' bytes land on the leader's barrier
-            tma_load_2d_pair(smem_u32(sB + s * B_STAGE), &mapW1, LEADER(B_BFULL + s), 0, (int)((ks * 2 + rank) * (B_STAGE / 256)));
+            kstamp(p, 0, iw);
+            if (p.dbg & 1) { if (rank == 0) mbar_arrive(BAR(B_FULL + s)); }
+            else {
+              if (rank == 0) mbar_expect_tx(BAR(B_FULL + s), 2 * B_STAGE);     // both CTAs' bytes land on the leader's barrier
+              tma_load_2d_pair(smem_u32(sB + s * B_STAGE), &mapW1, LEADER(B_FULL + s), 0, (int)((wks * 2 + rank) * (B_STAGE / 256)));
+            }
+            if (++wks == KS) wks = 0;
           }
         }
       }
@@ -137,98 +152,84 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           for (int c = 0; c < NCH2; ++c) {
             const uint32_t r = c & 3, ph = (tl * 4 + (c >> 2)) & 1;
             mbar_wait(BAR(B_G2EMPTY + r), ph ^ 1, p.err, 3);
-            if (rank == 0) mbar_expect_tx(BAR(B_G2BFULL + r), 2 * G2B_STAGE);
-            tma_load_2d_pair(smem_u32(sB2 + r * G2B_STAGE), &mapWa, LEADER(B_G2BFULL + r), 0, (int)((c * 2 + rank) * (G2B_STAGE / 256)));
+            if (rank == 0) mbar_expect_tx(BAR(B_G2FULL + r), 2 * G2B_STAGE);
+            tma_load_2d_pair(smem_u32(sB2 + r * G2B_STAGE), &mapWa, LEADER(B_G2FULL + r), 0, (int)((c * 2 + rank) * (G2B_STAGE / 256)));
           }
         }
       }
     } else if (warp == 1 && rank == 0) {
-      // ===================== MMA issuer (one thread of the leader CTA) =====================
-      // GEMM1 of tile t+1 and GEMM2 of tile t are interleaved by readiness: the thread never blocks on one of them.
+      // ===================== GEMM1 issuer (one thread of the leader CTA) =====================
       if (lane == 0) {
-        const uint32_t idesc1 = make_idesc(FP16, 256, BMP), idesc2 = make_idesc(FP16, 128, BMP);
-        uint32_t T = 0;
-        for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) ++T;
-        uint32_t g1_t = 0, g1_ks = 0, it = 0, g2_t = 0, g2_c = 0;
-        bool acc_ok = false, tail_ok = false;
-        long long t_last = clock64();
-        while (g2_t < T) {
-          bool progress = false;
-          if (g2_t < g1_t) {                                   // GEMM1 of that tile has been issued completely
-            const uint32_t b2 = g2_t & 1;
-            if (!tail_ok) tail_ok = mbar_test_wait(BAR(B_TAILFREE + b2), (g2_t >> 1) & 1);
-            if (tail_ok) {
-              const uint32_t r = g2_c & 3, ph = (g2_t * 4 + (g2_c >> 2)) & 1;
-              if (mbar_test_wait(BAR(B_G2AFULL + r), ph) && mbar_test_wait(BAR(B_G2BFULL + r), ph)) {
-                tc_fence_after();
-                if (g2_c == 0) trace_stamp(p, g2_t, 2);
-                const uint32_t a0 = smem_u32(sA2 + r * G2A_STAGE), b0 = smem_u32(sB2 + r * G2B_STAGE);
-                const uint32_t d = tmem + b2 * 256;
+        const uint32_t idesc1 = make_idesc(FP16, 256, BMP);
+        const uint32_t qd_dbg = ((uint32_t)p.dbg >> 8) & 15u, qd = qd_dbg ? (qd_dbg < (uint32_t)NST ? qd_dbg : (uint32_t)NST - 1) : (uint32_t)QD;
+        uint32_t it = 0, tl = 0;
+        for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs, ++tl) {
+          const uint32_t b1 = tl & 1;
+          mbar_wait(BAR(B_ACCEMPTY + b1), ((tl >> 1) & 1) ^ 1, p.err, 4);
+          tc_fence_after();
+          trace_stamp(p, tl, 0);
+          for (int ks = 0; ks < KS; ++ks, ++it) {
+            const uint32_t s = it % NST, ph = (it / NST) & 1;
+            // keep at most QD k-steps queued in the tensor pipe: GEMM2's short MMAs (other thread) queue behind them
+            if (it >= qd) { const uint32_t io = it - qd; mbar_wait(BAR(B_EMPTY + io % NST), (io / NST) & 1, p.err, 5); }
+            kstamp(p, 2, it);
+            mbar_wait(BAR(B_FULL + s), ph, p.err, 6);
+            kstamp(p, 1, it);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sA + s * A_STAGE), b0 = smem_u32(sB + s * B_STAGE);
 #pragma unroll
-                for (int k16 = 0; k16 < 2; ++k16) {
-                  const uint32_t acc = (g2_c | k16) ? 1u : 0u;
-                  const uint64_t ah = make_desc_sw64(a0 + k16 * 32), bh = make_desc_sw64(b0 + k16 * 32);
-                  umma_f16_pair(d, ah, bh, idesc2, acc);
-                  if (LO) {
-                    const uint64_t al = make_desc_sw64(a0 + A2_OP + k16 * 32), bl = make_desc_sw64(b0 + B2_OP + k16 * 32);
-                    umma_f16_pair(d, al, bh, idesc2, 1u);
-                    umma_f16_pair(d, ah, bl, idesc2, 1u);
-                  }
+            for (int k16 = 0; k16 < 2; ++k16) {
+              if (p.dbg & 4) break;
+#pragma unroll
+              for (int blk = 0; blk < 2; ++blk) {
+                const uint32_t acc = (ks | k16) ? 1u : 0u;
+                const uint32_t d = tmem + b1 * 256 + blk * 128;
+                const uint64_t ah = make_desc_sw64(a0 + k16 * 32), bh = make_desc_sw64(b0 + blk * 8192 + k16 * 32);
+                umma_f16_pair(d, ah, bh, idesc1, acc);
+                if (LO) {
+                  const uint64_t al = make_desc_sw64(a0 + A_OP + k16 * 32), bl = make_desc_sw64(b0 + B_OP + blk * 8192 + k16 * 32);
+                  umma_f16_pair(d, al, bh, idesc1, 1u);
+                  umma_f16_pair(d, ah, bl, idesc1, 1u);
                 }
-                umma_commit_pair(BAR(B_G2EMPTY + r));
-                if (++g2_c == NCH2) {
-                  umma_commit_pair(BAR(B_UFULL));
-                  trace_stamp(p, g2_t, 3);
-                  g2_c = 0; ++g2_t; tail_ok = false;
-                }
-                progress = true;
               }
             }
+            umma_commit_pair(BAR(B_EMPTY + s));
           }
-          if (g1_t < T) {
-            const uint32_t b1 = g1_t & 1;
-            if (!acc_ok) {
-              acc_ok = mbar_test_wait(BAR(B_ACCEMPTY + b1), ((g1_t >> 1) & 1) ^ 1);
-              if (acc_ok) { tc_fence_after(); trace_stamp(p, g1_t, 0); }
-            }
-            if (acc_ok) {
-              const uint32_t s = it % NST, ph = (it / NST) & 1;
-              if (mbar_test_wait(BAR(B_AFULL + s), ph) && mbar_test_wait(BAR(B_BFULL + s), ph)) {
-                tc_fence_after();
-                const uint32_t a0 = smem_u32(sA + s * A_STAGE), b0 = smem_u32(sB + s * B_STAGE);
+          umma_commit_pair(BAR(B_ACCFULL + b1));
+          trace_stamp(p, tl, 1);
+        }
+      }
+    } else if (warp == 3 && rank == 0) {
+      // ===================== GEMM2 issuer (another thread of the leader CTA; runs against the epilogue of tile t while GEMM1 is on t+1) =====
+      if (lane == 0) {
+        const uint32_t idesc2 = make_idesc(FP16, 128, BMP);
+        uint32_t tl = 0;
+        for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs, ++tl) {
+          const uint32_t b2 = tl & 1;
+          mbar_wait(BAR(B_TAILFREE + b2), (tl >> 1) & 1, p.err, 7);             // u's columns are vacated (implies GEMM1 of the tile is complete)
+          tc_fence_after();
+          trace_stamp(p, tl, 2);
+          const uint32_t d = tmem + b2 * 256;
+          for (int c = 0; c < NCH2; ++c) {
+            const uint32_t r = c & 3, ph = (tl * 4 + (c >> 2)) & 1;
+            mbar_wait(BAR(B_G2FULL + r), ph, p.err, 8);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sA2 + r * G2A_STAGE), b0 = smem_u32(sB2 + r * G2B_STAGE);
 #pragma unroll
-                for (int k16 = 0; k16 < 2; ++k16) {
-#pragma unroll
-                  for (int blk = 0; blk < 2; ++blk) {
-                    const uint32_t acc = (g1_ks | k16) ? 1u : 0u;
-                    const uint32_t d = tmem + b1 * 256 + blk * 128;
-                    const uint64_t ah = make_desc_sw64(a0 + k16 * 32), bh = make_desc_sw64(b0 + blk * 8192 + k16 * 32);
-                    umma_f16_pair(d, ah, bh, idesc1, acc);
-                    if (LO) {
-                      const uint64_t al = make_desc_sw64(a0 + A_OP + k16 * 32), bl = make_desc_sw64(b0 + B_OP + blk * 8192 + k16 * 32);
-                      umma_f16_pair(d, al, bh, idesc1, 1u);
-                      umma_f16_pair(d, ah, bl, idesc1, 1u);
-                    }
-                  }
-                }
-                umma_commit_pair(BAR(B_EMPTY + s));
-                ++it;
-                if (++g1_ks == (uint32_t)KS) {
-                  umma_commit_pair(BAR(B_ACCFULL + b1));
-                  trace_stamp(p, g1_t, 1);
-                  g1_ks = 0; ++g1_t; acc_ok = false;
-                }
-                progress = true;
+            for (int k16 = 0; k16 < 2; ++k16) {
+              const uint32_t acc = (c | k16) ? 1u : 0u;
+              const uint64_t ah = make_desc_sw64(a0 + k16 * 32), bh = make_desc_sw64(b0 + k16 * 32);
+              umma_f16_pair(d, ah, bh, idesc2, acc);
+              if (LO) {
+                const uint64_t al = make_desc_sw64(a0 + A2_OP + k16 * 32), bl = make_desc_sw64(b0 + B2_OP + k16 * 32);
+                umma_f16_pair(d, al, bh, idesc2, 1u);
+                umma_f16_pair(d, ah, bl, idesc2, 1u);
               }
             }
+            umma_commit_pair(BAR(B_G2EMPTY + r));
           }
-          if (progress) {
-            t_last = clock64();
-          } else if ((uint64_t)(clock64() - t_last) > WAIT_TIMEOUT_CYCLES) {
-            if (p.err) atomicExch(p.err, 100 + (int)(g1_t < T ? 1 : 0) + 2 * (int)(g2_t < g1_t ? 1 : 0) + 4 * (int)tail_ok + 8 * (int)acc_ok);
-            __threadfence_system();
-            asm volatile("trap;");
-          }
+          umma_commit_pair(BAR(B_UFULL));
+          trace_stamp(p, tl, 3);
         }
       }
     }
@@ -246,6 +247,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const uint32_t xs = it % XS, xph = (it / XS) & 1;
         const uint32_t s = it % NST, ph = (it / NST) & 1;
         mbar_wait(BAR(B_XFULL + xs), xph, p.err, 10);
+        if (lane == 0 && ((warp - 4) & 1) == 0) kstamp(p, 5, it);
         float x[32];
         const uint32_t src = smem_u32(sX + xs * X_SLOT) + (uint32_t)row * 128u;
 #pragma unroll
@@ -254,11 +256,12 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[4 * j]), "=f"(x[4 * j + 1]), "=f"(x[4 * j + 2]), "=f"(x[4 * j + 3]) : "r"(a));
         }
         mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 11);
+        if (lane == 0 && ((warp - 4) & 1) == 0) kstamp(p, 3, it);
         const uint32_t a_hi = smem_u32(sA + s * A_STAGE);
-        write_operand_row<FP16, LO>(a_hi, a_hi + A_OP, row, x);
-        fence_proxy_async();
+        if (!(p.dbg & 8)) write_operand_row<FP16, LO>(a_hi, a_hi + A_OP, row, x);
+        if (!(p.dbg & 128)) fence_proxy_async();
         __syncwarp();
-        if (lane == 0) { mbar_arrive_cluster(LEADER(B_AFULL + s)); mbar_arrive(BAR(B_XEMPTY + xs)); }
+        if (lane == 0) { mbar_arrive_cluster(LEADER(B_FULL + s)); mbar_arrive(BAR(B_XEMPTY + xs)); if (((warp - 4) & 1) == 0) kstamp(p, 4, it); }
       }
     }
   } else {
@@ -335,7 +338,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         write_operand_row<FP16, LO>(a2_hi, a2_hi + A2_OP, row, hv);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(LEADER(B_G2AFULL + strip));
+        if (lane == 0) mbar_arrive_cluster(LEADER(B_G2FULL + strip));
       };
       if (half == 0) {
         emit_chunk(0, keep_h[0]);
@@ -407,6 +410,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       }
 #pragma unroll 1
       for (int j = (half == 0 ? 2 : 0); j < 4; j += 2) {
+        if (p.dbg & 32) break;
         float ha[32], hb[32];
         uint32_t va[32], vb[32];
         tmem_ld32(tb + (uint32_t)(j * 32), va);
