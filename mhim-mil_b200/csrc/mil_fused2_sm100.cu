@@ -32,10 +32,17 @@ constexpr int A_OP = BMC * BK * 2;            // 4096   one 16-bit A tile [64 x 
 constexpr int B_OP = 2 * 128 * BK * 2;        // 16384  this CTA's 128 rows of both 256-row N blocks: [blk 0 | blk 1]
 constexpr int A2_OP = A_OP;                   // 4096   GEMM2 A tile [64 x 32]
 constexpr int B2_OP = 64 * BK * 2;            // 4096   this CTA's 64 rows of Wa
-constexpr int G2S = 4;                        // GEMM2 ring slots (one per epilogue-warp column strip)
-constexpr int QD = 2;                         // GEMM1 k-steps the issuer keeps queued in the tensor pipe
+constexpr int G2S = 4;                        // GEMM2 A2 slots (one per epilogue-warp column strip)
+constexpr int G2B_BUF = 16384;                // one Wa load group (GS chunks x NOP x 4 KB); two buffers
+
 constexpr int NUM_THREADS = 512;
-constexpr int EPI_WARP0 = 8;                  // warps 8..15 epilogue; 4..7 converters; 0 bag + W1 TMA; 1 GEMM1 issue; 2 TMEM alloc + Wa TMA; 3 GEMM2 issue
+// Warp roles.  The SM's warp arbiter favours the highest warp id among eligible warps, and here the epilogue of tile t runs
+// concurrently with the operand pipeline of tile t+1: the short latency-critical loops (producers, MMA issue, converters) get the
+// high ids, the ALU-heavy epilogue warps the low ones.  (The other way round the control warps were starved of issue slots: ~1000
+// cycles per 64-wide stage with every TMA and MMA switched off.)
+constexpr int EPI_WARP0 = 0;                  // warps 0..7 epilogue
+constexpr int CONV_WARP0 = 8;                 // warps 8..11 converters
+constexpr int W_X = 12, W_MMA1 = 13, W_W1 = 14, W_MMA2 = 15;   // bag TMA; GEMM1 issue; TMEM alloc + W1 TMA; Wa TMA + GEMM2 issue
 constexpr int MISC_BYTES = 512 + 1024 + 4096 + 16 + (HMAX + 256) * 4 + 8 * 128 * 4;
 
 // k-step stamps of CTA 0 (MHIMK_TRACE=1): series x first 64 k-steps, see tools/trace_ksteps.py
@@ -43,13 +50,17 @@ __device__ __forceinline__ void kstamp(const FusedParams& p, int series, uint32_
   if (p.trace && blockIdx.x == 0 && it < 64) p.trace[1024 + series * 64 + it] = clock64();
 }
 
-template <int NPROD, bool FP16, int NST, int XS, int ACT, int ATT>
+template <int NPROD, bool FP16, int NST, int XS, int KSUB, int ACT, int ATT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW1,
                   const __grid_constant__ CUtensorMap mapWa, const FusedParams p) {
   constexpr bool LO = NPROD == 3;
   constexpr int NOP = LO ? 2 : 1;                              // operand tiles per stage (hi, lo)
-  constexpr uint32_t A_STAGE = NOP * A_OP, B_STAGE = NOP * B_OP, G2A_STAGE = NOP * A2_OP, G2B_STAGE = NOP * B2_OP;
+  // one pipeline stage = KSUB sub-steps of 32 K elements: the fixed cost of a stage hand-over (two mbarrier round trips, a commit,
+  // ~300 issue-latency-bound cycles in the MMA warp) is amortised over KSUB x 4 (x3) MMAs
+  constexpr uint32_t A_SUB = NOP * A_OP, B_SUB = NOP * B_OP, A_STAGE = KSUB * A_SUB, B_STAGE = KSUB * B_SUB, G2A_STAGE = NOP * A2_OP;
+  constexpr int GS = 4 / NOP;                                  // GEMM2 k-chunks per Wa load (16 KB), NG groups per tile
+  constexpr int NG = 16 / GS;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -57,8 +68,8 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   uint8_t* sA = sX + XS * X_SLOT;                              // NST x A_STAGE
   uint8_t* sB = sA + NST * A_STAGE;                            // NST x B_STAGE
   uint8_t* sA2 = sB + NST * B_STAGE;                           // G2S x G2A_STAGE
-  uint8_t* sB2 = sA2 + G2S * G2A_STAGE;                        // G2S x G2B_STAGE
-  uint8_t* sMisc = sB2 + G2S * G2B_STAGE;
+  uint8_t* sB2 = sA2 + G2S * G2A_STAGE;                        // 2 x 16 KB Wa group buffers
+  uint8_t* sMisc = sB2 + 2 * G2B_BUF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sMisc);         // barrier block (512 B)
   float* s_part = reinterpret_cast<float*>(sMisc + 512);       // [4 strips][64 rows] partial attention logits
   float* t_part = s_part + 256;                                // [4 strips][64 rows][4] partial t (also grid_finalize scratch)
@@ -73,7 +84,8 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   // FULL[s] (leader): 4 converter warps of the pair + the W1 producer's expect_tx arrival + both CTAs' W1 bytes; G2FULL[r] likewise
   constexpr int B_XFULL = 0, B_XEMPTY = B_XFULL + XS, B_FULL = B_XEMPTY + XS, B_EMPTY = B_FULL + NST,
                 B_ACCFULL = B_EMPTY + NST, B_ACCEMPTY = B_ACCFULL + 2, B_TAILFREE = B_ACCEMPTY + 2, B_UFULL = B_TAILFREE + 2,
-                B_G2FULL = B_UFULL + 1, B_G2EMPTY = B_G2FULL + G2S, B_COUNT = B_G2EMPTY + G2S;
+                B_G2AFULL = B_UFULL + 1, B_G2AEMPTY = B_G2AFULL + G2S, B_G2BFULL = B_G2AEMPTY + G2S, B_G2BEMPTY = B_G2BFULL + 2,
+                B_COUNT = B_G2BEMPTY + 2;
   static_assert(B_COUNT * 8 <= 512, "barrier block overflow");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -83,171 +95,212 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     p.trace[256 + 2 * blockIdx.x] = (long long)gt;
+    if (blockIdx.x == 0) p.trace[238] = clock64();
   }
-  const int KS = p.D / BK;                                     // GEMM1 k-steps per tile
+  const int KS = p.D / BK;                                     // GEMM1 32-wide k sub-steps per tile
+  const int KST = KS / KSUB;                                   // pipeline stages per tile
   constexpr int NCH2 = HMAX / BK;                              // GEMM2 k-steps per tile (16)
   const int64_t n_tiles = (p.N + BMP - 1) / BMP;
   const int64_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < XS; ++i) { mbar_init(BAR(B_XFULL + i), 1); mbar_init(BAR(B_XEMPTY + i), 2); }
-    for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_FULL + i), 5); mbar_init(BAR(B_EMPTY + i), 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_FULL + i), ((p.dbg & 64) ? 2 : 4) * KSUB + 1); mbar_init(BAR(B_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACCFULL + i), 1); mbar_init(BAR(B_ACCEMPTY + i), 16); mbar_init(BAR(B_TAILFREE + i), 8); }
     mbar_init(BAR(B_UFULL), 1);
-    for (int i = 0; i < G2S; ++i) { mbar_init(BAR(B_G2FULL + i), 5); mbar_init(BAR(B_G2EMPTY + i), 1); }
+    for (int i = 0; i < G2S; ++i) { mbar_init(BAR(B_G2AFULL + i), 4); mbar_init(BAR(B_G2AEMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_G2BFULL + i), 1); mbar_init(BAR(B_G2BEMPTY + i), 1); }
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapW1); tma_prefetch_desc(&mapWa); }
-  if (warp == 2) tmem_alloc_pair(smem_u32(tmem_slot), 512);
+  if (warp == W_X && lane == 0) { tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapW1); tma_prefetch_desc(&mapWa); }
+  if (warp == W_W1) tmem_alloc_pair(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                          // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // warp-uniform for the compiler
 
-  if (warp < 4) {
+  if (warp >= W_X) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp == 0) {
-      // ===================== bag + W1 producer =====================
-      // X: HBM -> fp32 staging (this CTA's 64 rows of the pair tile).  W1: L2 -> this CTA's half of the B operand of every
-      // k-step (image rows are 256 B; one k-step of one CTA is NOP x 16 KB contiguous: [hi: N block 0 | N block 1][lo: ...]).
-      // One thread drives both streams; the W1 stream trails the bag stream by XS k-steps so that the bag prefetch keeps its
-      // full depth (XS staging slots + NST converted stages) when the operand ring is full.
-      if (lane == 0) {
-        uint32_t total = 0;
-        for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) total += (uint32_t)KS;
-        int64_t xtile = pair_id;
-        int xks = 0, wks = 0;
-        for (uint32_t it = 0; it < total + XS; ++it) {
-          if (it < total) {
-            const uint32_t s = it % XS, ph = (it / XS) & 1;
-            mbar_wait(BAR(B_XEMPTY + s), ph ^ 1, p.err, 1);
-            kstamp(p, 6, it);
-            if (p.dbg & 2) mbar_arrive(BAR(B_XFULL + s));
+    // Control warps run their loops CONVERGED (all 32 lanes wait on the barriers and compute the uniform operands; one
+    // elected lane issues the TMA / MMA / commit).  A lone diverged lane made ptxas move every descriptor into uniform
+    // registers through an ELECT + 5 x R2UR waterfall per instruction: ~700 cycles per k-step, 3x the MMA time.
+    if (warp == W_X) {
+      // ===================== bag producer: HBM -> fp32 staging (this CTA's 64 rows of the pair tile) =====================
+      // The staging ring (XS x 8 KB) cannot hold an HBM round trip of the bag stream (~1800 cycles x 32 B/cycle = 58 KB), so the
+      // tiles are first pulled into L2 PF sub-steps ahead (cp.async.bulk.prefetch.tensor); the staged load then sees L2 latency.
+      uint32_t s = 0, ph = 1, xit = 0;
+      const uint32_t sx0 = smem_u32(sX);
+      constexpr int PF = 24;
+      int64_t ptile = pair_id;
+      int pks = 0;
+      auto prefetch_next = [&]() {                                               // one box further down this CTA's stream
+        if (ptile < n_tiles) {
+          if (elect_one()) tma_prefetch_2d(&mapX, pks * BK, (int)(ptile * BMP + rank * BMC));
+          __syncwarp();
+          if (++pks == KS) { pks = 0; ptile += n_pairs; }
+        }
+      };
+      if (!(p.dbg & 2))
+        for (int i = 0; i < PF; ++i) prefetch_next();
+      for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) {
+        const int row0 = (int)(tile * BMP + rank * BMC);
+        for (int ks = 0; ks < KS; ++ks) {
+          if (!(p.dbg & 2)) prefetch_next();
+          mbar_wait(BAR(B_XEMPTY + s), ph, p.err, 1);
+          if (lane == 0) kstamp(p, 6, xit++);
+          if (elect_one()) {
+            if (p.dbg & 2) mbar_arrive(BAR(B_XFULL + s));                          // timing attribution: no bag traffic
             else {
               mbar_expect_tx(BAR(B_XFULL + s), X_SLOT);
-              tma_load_2d(smem_u32(sX + s * X_SLOT), &mapX, BAR(B_XFULL + s), xks * BK, (int)(xtile * BMP + rank * BMC));
+              tma_load_2d(sx0 + s * X_SLOT, &mapX, BAR(B_XFULL + s), ks * BK, row0);
             }
-            if (++xks == KS) { xks = 0; xtile += n_pairs; }
           }
-          if (it >= (uint32_t)XS) {
-            const uint32_t iw = it - XS, s = iw % NST, ph = (iw / NST) & 1;
-            mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 2);
-            kstamp(p, 0, iw);
-            if (p.dbg & 1) { if (rank == 0) mbar_arrive(BAR(B_FULL + s)); }
+          __syncwarp();
+          if (++s == (uint32_t)XS) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == W_W1) {
+      // ===================== W1 producer: L2 -> this CTA's half of the B operand of every k-step =====================
+      // Image rows are 256 B; one stage of one CTA is KSUB x NOP x 16 KB contiguous: per sub-step [hi: N block 0 | N block 1][lo: ...].
+      uint32_t s = 0, ph = 1, wit = 0;
+      const uint32_t full0 = LEADER(B_FULL), sb0 = smem_u32(sB);
+      for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) {
+        for (int kst = 0; kst < KST; ++kst) {
+          mbar_wait(BAR(B_EMPTY + s), ph, p.err, 2);
+          if (lane == 0) kstamp(p, 0, wit++);
+          if (elect_one()) {
+            if (p.dbg & 1) { if (rank == 0) mbar_arrive(BAR(B_FULL + s)); }        // timing attribution: no W1 traffic
             else {
-              if (rank == 0) mbar_expect_tx(BAR(B_FULL + s), 2 * B_STAGE);     // both CTAs' bytes land on the leader's barrier
-              tma_load_2d_pair(smem_u32(sB + s * B_STAGE), &mapW1, LEADER(B_FULL + s), 0, (int)((wks * 2 + rank) * (B_STAGE / 256)));
+              if (rank == 0) mbar_expect_tx(BAR(B_FULL + s), 2 * B_STAGE);       // both CTAs' bytes land on the leader's barrier
+              tma_load_2d_pair(sb0 + s * B_STAGE, &mapW1, full0 + 8u * s, 0, (int)((kst * 2 + rank) * (B_STAGE / 256)));
             }
-            if (++wks == KS) wks = 0;
           }
+          __syncwarp();
+          if (++s == (uint32_t)NST) { s = 0; ph ^= 1; }
         }
       }
-    } else if (warp == 2) {
-      // ===================== Wa producer: this CTA's 64 rows of every GEMM2 k-chunk =====================
-      if (lane == 0) {
-        uint32_t tl = 0;
-        for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs, ++tl) {
-          for (int c = 0; c < NCH2; ++c) {
-            const uint32_t r = c & 3, ph = (tl * 4 + (c >> 2)) & 1;
-            mbar_wait(BAR(B_G2EMPTY + r), ph ^ 1, p.err, 3);
-            if (rank == 0) mbar_expect_tx(BAR(B_G2FULL + r), 2 * G2B_STAGE);
-            tma_load_2d_pair(smem_u32(sB2 + r * G2B_STAGE), &mapWa, LEADER(B_G2FULL + r), 0, (int)((c * 2 + rank) * (G2B_STAGE / 256)));
-          }
-        }
-      }
-    } else if (warp == 1 && rank == 0) {
-      // ===================== GEMM1 issuer (one thread of the leader CTA) =====================
-      if (lane == 0) {
-        const uint32_t idesc1 = make_idesc(FP16, 256, BMP);
-        const uint32_t qd_dbg = ((uint32_t)p.dbg >> 8) & 15u, qd = qd_dbg ? (qd_dbg < (uint32_t)NST ? qd_dbg : (uint32_t)NST - 1) : (uint32_t)QD;
-        uint32_t it = 0, tl = 0;
-        for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs, ++tl) {
-          const uint32_t b1 = tl & 1;
-          mbar_wait(BAR(B_ACCEMPTY + b1), ((tl >> 1) & 1) ^ 1, p.err, 4);
+    } else if (warp == W_MMA1 && rank == 0) {
+      // ===================== GEMM1 issuer (leader CTA) =====================
+      const uint32_t idesc1 = make_idesc(FP16, 256, BMP);
+      const uint32_t sa0 = smem_u32(sA), sb0 = smem_u32(sB);
+      uint32_t s = 0, ph = 0, tl = 0, iit = 0;
+      for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs, ++tl) {
+        const uint32_t b1 = tl & 1;
+        mbar_wait(BAR(B_ACCEMPTY + b1), ((tl >> 1) & 1) ^ 1, p.err, 4);
+        tc_fence_after();
+        if (lane == 0) trace_stamp(p, tl, 0);
+        const uint32_t d0 = tmem + b1 * 256;
+        for (int kst = 0; kst < KST; ++kst) {
+          if (lane == 0) kstamp(p, 2, iit);
+          mbar_wait(BAR(B_FULL + s), ph, p.err, 6);
+          if (lane == 0) kstamp(p, 1, iit++);
           tc_fence_after();
-          trace_stamp(p, tl, 0);
-          for (int ks = 0; ks < KS; ++ks, ++it) {
-            const uint32_t s = it % NST, ph = (it / NST) & 1;
-            // keep at most QD k-steps queued in the tensor pipe: GEMM2's short MMAs (other thread) queue behind them
-            if (it >= qd) { const uint32_t io = it - qd; mbar_wait(BAR(B_EMPTY + io % NST), (io / NST) & 1, p.err, 5); }
-            kstamp(p, 2, it);
-            mbar_wait(BAR(B_FULL + s), ph, p.err, 6);
-            kstamp(p, 1, it);
-            tc_fence_after();
-            const uint32_t a0 = smem_u32(sA + s * A_STAGE), b0 = smem_u32(sB + s * B_STAGE);
+          const uint32_t a0 = sa0 + s * A_STAGE, b0 = sb0 + s * B_STAGE;
+          const uint64_t ah0 = make_desc_sw64(a0), bh0 = make_desc_sw64(b0), al0 = make_desc_sw64(a0 + A_OP), bl0 = make_desc_sw64(b0 + B_OP);
+          if (elect_one()) {
 #pragma unroll
-            for (int k16 = 0; k16 < 2; ++k16) {
-              if (p.dbg & 4) break;
+            for (int sub = 0; sub < KSUB; ++sub) {
 #pragma unroll
-              for (int blk = 0; blk < 2; ++blk) {
-                const uint32_t acc = (ks | k16) ? 1u : 0u;
-                const uint32_t d = tmem + b1 * 256 + blk * 128;
-                const uint64_t ah = make_desc_sw64(a0 + k16 * 32), bh = make_desc_sw64(b0 + blk * 8192 + k16 * 32);
-                umma_f16_pair(d, ah, bh, idesc1, acc);
-                if (LO) {
-                  const uint64_t al = make_desc_sw64(a0 + A_OP + k16 * 32), bl = make_desc_sw64(b0 + B_OP + blk * 8192 + k16 * 32);
-                  umma_f16_pair(d, al, bh, idesc1, 1u);
-                  umma_f16_pair(d, ah, bl, idesc1, 1u);
+              for (int k16 = 0; k16 < 2; ++k16) {
+                if (p.dbg & 4) break;                                              // timing attribution: no GEMM1 MMAs
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                  // descriptor start addresses are in 16-byte units: +2 per K = 16 step (32 B), +512 per N block (8 KB)
+                  const uint64_t oa = (uint64_t)(sub * (A_SUB / 16) + k16 * 2), ob = (uint64_t)(sub * (B_SUB / 16) + blk * 512 + k16 * 2);
+                  const uint32_t acc = (kst | sub | k16) ? 1u : 0u;
+                  umma_f16_pair(d0 + blk * 128, ah0 + oa, bh0 + ob, idesc1, acc);
+                  if (LO) {
+                    umma_f16_pair(d0 + blk * 128, al0 + oa, bh0 + ob, idesc1, 1u);
+                    umma_f16_pair(d0 + blk * 128, ah0 + oa, bl0 + ob, idesc1, 1u);
+                  }
                 }
               }
             }
             umma_commit_pair(BAR(B_EMPTY + s));
+            if (kst == KST - 1) umma_commit_pair(BAR(B_ACCFULL + b1));
           }
-          umma_commit_pair(BAR(B_ACCFULL + b1));
-          trace_stamp(p, tl, 1);
+          __syncwarp();
+          if (++s == (uint32_t)NST) { s = 0; ph ^= 1; }
         }
+        if (lane == 0) trace_stamp(p, tl, 1);
       }
-    } else if (warp == 3 && rank == 0) {
-      // ===================== GEMM2 issuer (another thread of the leader CTA; runs against the epilogue of tile t while GEMM1 is on t+1) =====
-      if (lane == 0) {
-        const uint32_t idesc2 = make_idesc(FP16, 128, BMP);
-        uint32_t tl = 0;
-        for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs, ++tl) {
-          const uint32_t b2 = tl & 1;
+    } else if (warp == W_MMA2) {
+      // ===================== Wa producer (both CTAs) + GEMM2 issuer (leader) =====================
+      // GEMM2 of tile t runs against the epilogue of tile t while GEMM1 is on tile t+1.  Wa arrives in groups of GS k-chunks
+      // (16 KB per CTA: this CTA's 64 rows of each chunk), double-buffered; group G+1 is requested when group G starts.
+      const uint32_t idesc2 = make_idesc(FP16, 128, BMP);
+      const uint32_t bfull0 = LEADER(B_G2BFULL), sa20 = smem_u32(sA2), sb20 = smem_u32(sB2);
+      uint32_t T = 0;
+      for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) ++T;
+      const uint32_t total = T * NG;
+      auto load_group = [&](uint32_t G) {                      // G-th group of this CTA's sequence (groups repeat every NG)
+        const uint32_t bf = G & 1;
+        mbar_wait(BAR(B_G2BEMPTY + bf), ((G >> 1) & 1) ^ 1, p.err, 3);
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(BAR(B_G2BFULL + bf), 2 * G2B_BUF);
+          tma_load_2d_pair(sb20 + bf * G2B_BUF, &mapWa, bfull0 + 8u * bf, 0, (int)(((G % NG) * 2 + rank) * (G2B_BUF / 256)));
+        }
+        __syncwarp();
+      };
+      load_group(0);
+      uint32_t G = 0;
+      for (uint32_t tl = 0; tl < T; ++tl) {
+        const uint32_t b2 = tl & 1;
+        if (rank == 0) {
           mbar_wait(BAR(B_TAILFREE + b2), (tl >> 1) & 1, p.err, 7);             // u's columns are vacated (implies GEMM1 of the tile is complete)
           tc_fence_after();
-          trace_stamp(p, tl, 2);
-          const uint32_t d = tmem + b2 * 256;
-          for (int c = 0; c < NCH2; ++c) {
-            const uint32_t r = c & 3, ph = (tl * 4 + (c >> 2)) & 1;
-            mbar_wait(BAR(B_G2FULL + r), ph, p.err, 8);
-            tc_fence_after();
-            const uint32_t a0 = smem_u32(sA2 + r * G2A_STAGE), b0 = smem_u32(sB2 + r * G2B_STAGE);
-#pragma unroll
-            for (int k16 = 0; k16 < 2; ++k16) {
-              const uint32_t acc = (c | k16) ? 1u : 0u;
-              const uint64_t ah = make_desc_sw64(a0 + k16 * 32), bh = make_desc_sw64(b0 + k16 * 32);
-              umma_f16_pair(d, ah, bh, idesc2, acc);
-              if (LO) {
-                const uint64_t al = make_desc_sw64(a0 + A2_OP + k16 * 32), bl = make_desc_sw64(b0 + B2_OP + k16 * 32);
-                umma_f16_pair(d, al, bh, idesc2, 1u);
-                umma_f16_pair(d, ah, bl, idesc2, 1u);
-              }
-            }
-            umma_commit_pair(BAR(B_G2EMPTY + r));
-          }
-          umma_commit_pair(BAR(B_UFULL));
-          trace_stamp(p, tl, 3);
+          if (lane == 0) trace_stamp(p, tl, 2);
         }
+        const uint32_t d = tmem + b2 * 256;
+        for (int g = 0; g < NG; ++g, ++G) {
+          if (G + 1 < total) load_group(G + 1);
+          if (rank != 0) continue;
+          const uint32_t bf = G & 1;
+          mbar_wait(BAR(B_G2BFULL + bf), (G >> 1) & 1, p.err, 8);
+#pragma unroll
+          for (int sg = 0; sg < GS; ++sg) {
+            const uint32_t c = (uint32_t)(g * GS + sg), strip = c & 3, j = c >> 2;
+            mbar_wait(BAR(B_G2AFULL + strip), (tl * 4 + j) & 1, p.err, 9);
+            tc_fence_after();
+            const uint32_t a0 = sa20 + strip * G2A_STAGE, b0 = sb20 + bf * G2B_BUF + sg * NOP * B2_OP;
+            const uint64_t ah0 = make_desc_sw64(a0), bh0 = make_desc_sw64(b0), al0 = make_desc_sw64(a0 + A2_OP), bl0 = make_desc_sw64(b0 + B2_OP);
+            if (elect_one()) {
+#pragma unroll
+              for (int k16 = 0; k16 < 2; ++k16) {
+                const uint64_t ah = ah0 + (uint64_t)(k16 * 2), bh = bh0 + (uint64_t)(k16 * 2);
+                umma_f16_pair(d, ah, bh, idesc2, (c | (uint32_t)k16) ? 1u : 0u);
+                if (LO) {
+                  umma_f16_pair(d, al0 + (uint64_t)(k16 * 2), bh, idesc2, 1u);
+                  umma_f16_pair(d, ah, bl0 + (uint64_t)(k16 * 2), idesc2, 1u);
+                }
+              }
+              umma_commit_pair(BAR(B_G2AEMPTY + strip));
+              if (sg == GS - 1) umma_commit_pair(BAR(B_G2BEMPTY + bf));
+              if (sg == GS - 1 && g == NG - 1) umma_commit_pair(BAR(B_UFULL));
+            }
+            __syncwarp();
+          }
+        }
+        if (rank == 0 && lane == 0) trace_stamp(p, tl, 3);
       }
     }
-  } else if (warp < 8) {
+  } else if (warp >= CONV_WARP0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
     // ===================== converters: fp32 staging -> 16-bit hi/lo A tiles =====================
     // Two groups of two warps alternate k-steps (one row of the 64-row slab per thread): each group has two k-step times
     // for its wait -> load -> convert -> store -> fence -> arrive latency chain.
-    const int grp = (warp - 4) >> 1;
-    const int row = ((warp - 4) & 1) * 32 + lane;
+    const int grp = (warp - CONV_WARP0) >> 1;
+    const int row = ((warp - CONV_WARP0) & 1) * 32 + lane;
     uint32_t it = 0;
     for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) {
       for (int ks = 0; ks < KS; ++ks, ++it) {
         if ((int)(it & 1) != grp) continue;
         const uint32_t xs = it % XS, xph = (it / XS) & 1;
-        const uint32_t s = it % NST, ph = (it / NST) & 1;
+        const uint32_t st = it / KSUB, sub = it % KSUB, s = st % NST, ph = (st / NST) & 1;
         mbar_wait(BAR(B_XFULL + xs), xph, p.err, 10);
-        if (lane == 0 && ((warp - 4) & 1) == 0) kstamp(p, 5, it);
+        if (lane == 0 && ((warp - CONV_WARP0) & 1) == 0) kstamp(p, 5, it);
         float x[32];
         const uint32_t src = smem_u32(sX + xs * X_SLOT) + (uint32_t)row * 128u;
 #pragma unroll
@@ -255,13 +308,18 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           const uint32_t a = src + (((uint32_t)j ^ ((uint32_t)row & 7u)) << 4);
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[4 * j]), "=f"(x[4 * j + 1]), "=f"(x[4 * j + 2]), "=f"(x[4 * j + 3]) : "r"(a));
         }
-        mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 11);
-        if (lane == 0 && ((warp - 4) & 1) == 0) kstamp(p, 3, it);
-        const uint32_t a_hi = smem_u32(sA + s * A_STAGE);
-        if (!(p.dbg & 8)) write_operand_row<FP16, LO>(a_hi, a_hi + A_OP, row, x);
-        if (!(p.dbg & 128)) fence_proxy_async();
+        uint32_t hi[16], lo[16];
+        pack_operand_row<FP16, LO>(x, hi, lo);                                      // consumes every staged value
+        asm volatile("" ::"r"(hi[0]), "r"(hi[5]), "r"(hi[10]), "r"(hi[15]) : "memory");
         __syncwarp();
-        if (lane == 0) { mbar_arrive_cluster(LEADER(B_FULL + s)); mbar_arrive(BAR(B_XEMPTY + xs)); if (((warp - 4) & 1) == 0) kstamp(p, 4, it); }
+        if (lane == 0) mbar_arrive(BAR(B_XEMPTY + xs));                             // the slot is in registers: hand it back at once
+        mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 11);
+        if (lane == 0 && ((warp - CONV_WARP0) & 1) == 0) kstamp(p, 3, it);
+        const uint32_t a_hi = smem_u32(sA + s * A_STAGE + sub * A_SUB);
+        store_operand_row<LO>(a_hi, a_hi + A_OP, row, hi, lo);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && !((p.dbg & 64) && rank != 0)) { mbar_arrive_cluster(LEADER(B_FULL + s)); if (((warp - CONV_WARP0) & 1) == 0) kstamp(p, 4, it); }
       }
     }
   } else {
@@ -296,6 +354,19 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       mbar_wait(BAR(B_ACCFULL + b), (tl >> 1) & 1, p.err, 13);
       tc_fence_after();
       if (et == 0) trace_stamp(p, tl, 4);
+      if (p.dbg & 512) {                                    // timing attribution: handshakes only, no epilogue work
+        if (half == 0) { __syncwarp(); if (lane == 0) mbar_arrive_cluster(LEADER(B_TAILFREE + b)); }
+        for (int j = 0; j < 4; ++j) {
+          mbar_wait(BAR(B_G2AEMPTY + strip), ((tl * 4 + (uint32_t)j) & 1u) ^ 1, p.err, 14);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(LEADER(B_G2AFULL + strip));
+        }
+        mbar_wait(BAR(B_UFULL), tl & 1, p.err, 15);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(LEADER(B_ACCEMPTY + b));
+        continue;
+      }
 
       // E1 (N-block-0 warps): vacate the buffer's first 64 columns (they become GEMM2's accumulator); keep h in registers
       float keep_h[2][32];
@@ -334,11 +405,11 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           }
         }
         const uint32_t ph = (tl * 4 + (uint32_t)j) & 1u;
-        mbar_wait(BAR(B_G2EMPTY + strip), ph ^ 1, p.err, 14);
+        mbar_wait(BAR(B_G2AEMPTY + strip), ph ^ 1, p.err, 14);
         write_operand_row<FP16, LO>(a2_hi, a2_hi + A2_OP, row, hv);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(LEADER(B_G2FULL + strip));
+        if (lane == 0) mbar_arrive_cluster(LEADER(B_G2AFULL + strip));
       };
       if (half == 0) {
         emit_chunk(0, keep_h[0]);
@@ -410,7 +481,6 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       }
 #pragma unroll 1
       for (int j = (half == 0 ? 2 : 0); j < 4; j += 2) {
-        if (p.dbg & 32) break;
         float ha[32], hb[32];
         uint32_t va[32], vb[32];
         tmem_ld32(tb + (uint32_t)(j * 32), va);
@@ -457,8 +527,9 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     p.trace[256 + 2 * blockIdx.x + 1] = (long long)gt;
+    if (blockIdx.x == 0) p.trace[239] = clock64();
   }
-  if (warp == 2) { tc_fence_after(); tmem_dealloc_pair(tmem, 512); }
+  if (warp == W_W1) { tc_fence_after(); tmem_dealloc_pair(tmem, 512); }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -466,12 +537,12 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 // Every tile is the exact shared-memory image of a UMMA K-major SWIZZLE_64B operand tile (rows of 64 B = 32 elements):
 //   byte(r, c, e) = (r/8)*512 + (r%8)*64 + ((c ^ ((r>>1)&3))*16) + 2e,  c = 16-byte chunk inside the row.
 // W1 image: for k-step ks, CTA rank, operand op (hi, lo), N block blk: the 128 rows  blk*256 + rank*128 + [0,128)  (8 KB);
-//           order (ks, rank, op, blk) -> one k-step of one CTA is NOP x 16 KB contiguous.
+//           order (stage = ks / ksub, rank, sub = ks % ksub, op, blk) -> one pipeline stage of one CTA is ksub x NOP x 16 KB contiguous.
 // Wa image: GEMM2 chunk c = 4 j + half*2 + g covers features half*256 + g*128 + 32 j .. + 32 (the order in which the epilogue
 //           strips produce A2 tiles); for chunk c, CTA rank, operand op: the 64 rows rank*64 + [0,64) (4 KB); order (c, rank, op).
 // ------------------------------------------------------------------------------------------------------------
 template <bool FP16, bool LO>
-__global__ void pair_split_w1_kernel(const float* __restrict__ w, int H, int K, uint8_t* __restrict__ img) {
+__global__ void pair_split_w1_kernel(const float* __restrict__ w, int H, int K, uint8_t* __restrict__ img, int ksub) {
   const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (row f, 16-byte chunk kc = k / 8)
   const int kchunks = K / 8;
   if (item >= (int64_t)H * kchunks) return;
@@ -484,7 +555,7 @@ __global__ void pair_split_w1_kernel(const float* __restrict__ w, int H, int K, 
   h[0] = pack_hi<FP16>(a.x, a.y); h[1] = pack_hi<FP16>(a.z, a.w); h[2] = pack_hi<FP16>(b.x, b.y); h[3] = pack_hi<FP16>(b.z, b.w);
   constexpr int NOPK = LO ? 2 : 1;
   const size_t off = (size_t)(r >> 3) * 512 + (size_t)(r & 7) * 64 + (size_t)((c ^ ((r >> 1) & 3)) << 4);
-  uint8_t* dst = img + ((size_t)(ks * 2 + rank) * NOPK) * 16384 + (size_t)blk * 8192 + off;
+  uint8_t* dst = img + ((size_t)(((ks / ksub) * 2 + rank) * ksub + ks % ksub) * NOPK) * 16384 + (size_t)blk * 8192 + off;
   *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
   if (LO) {
     l[0] = pack_lo_bf16(a.x, a.y, h[0]); l[1] = pack_lo_bf16(a.z, a.w, h[1]); l[2] = pack_lo_bf16(b.x, b.y, h[2]); l[3] = pack_lo_bf16(b.z, b.w, h[3]);
@@ -508,7 +579,8 @@ __global__ void pair_split_wa_kernel(const float* __restrict__ w, int Da, int K,
   h[0] = pack_hi<FP16>(a.x, a.y); h[1] = pack_hi<FP16>(a.z, a.w); h[2] = pack_hi<FP16>(b.x, b.y); h[3] = pack_hi<FP16>(b.z, b.w);
   constexpr int NOPK = LO ? 2 : 1;
   const size_t off = (size_t)(r >> 3) * 512 + (size_t)(r & 7) * 64 + (size_t)((c ^ ((r >> 1) & 3)) << 4);
-  uint8_t* dst = img + ((size_t)(chunk * 2 + rank) * NOPK) * 4096 + off;
+  constexpr int GSK = 4 / NOPK;                                             // chunks per 16 KB load group
+  uint8_t* dst = img + ((size_t)((chunk / GSK) * 2 + rank) * GSK + (size_t)(chunk % GSK)) * NOPK * 4096 + off;
   *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
   if (LO) {
     l[0] = pack_lo_bf16(a.x, a.y, h[0]); l[1] = pack_lo_bf16(a.z, a.w, h[1]); l[2] = pack_lo_bf16(b.x, b.y, h[2]); l[3] = pack_lo_bf16(b.z, b.w, h[3]);
@@ -516,11 +588,11 @@ __global__ void pair_split_wa_kernel(const float* __restrict__ w, int Da, int K,
   }
 }
 
-template <int NPROD, bool FP16, int NST, int XS, int ACT, int ATT>
+template <int NPROD, bool FP16, int NST, int XS, int KSUB, int ACT, int ATT>
 static int launch_pair(const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mwa, const FusedParams& p, int grid, cudaStream_t stream) {
   constexpr int NOP = NPROD == 3 ? 2 : 1;
-  const size_t smem = 1024 + (size_t)XS * X_SLOT + (size_t)NST * NOP * (A_OP + B_OP) + (size_t)G2S * NOP * (A2_OP + B2_OP) + MISC_BYTES;
-  auto kern = mil_fused2_kernel<NPROD, FP16, NST, XS, ACT, ATT>;
+  const size_t smem = 1024 + (size_t)XS * X_SLOT + (size_t)NST * KSUB * NOP * (A_OP + B_OP) + (size_t)G2S * NOP * A2_OP + 2 * (size_t)G2B_BUF + MISC_BYTES;
+  auto kern = mil_fused2_kernel<NPROD, FP16, NST, XS, KSUB, ACT, ATT>;
   static bool attr_set = false;
   if (!attr_set) {
     MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -536,12 +608,19 @@ static int launch_pair(const CUtensorMap& mx, const CUtensorMap& mw1, const CUte
 template <int ACT, int ATT>
 static int dispatch_prec(int precision, const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mwa, const FusedParams& p, int grid,
                          cudaStream_t stream) {
-  if (precision == MIL_PREC_BF16X3) return launch_pair<3, false, 3, 3, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
-  if (precision == MIL_PREC_FP16) return launch_pair<1, true, 6, 6, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
-  return launch_pair<1, false, 6, 6, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+  if (precision == MIL_PREC_BF16X3) return launch_pair<3, false, 3, 3, 1, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+  if (p.D % 64 == 0) {
+    if (precision == MIL_PREC_FP16) return launch_pair<1, true, 3, 5, 2, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+    return launch_pair<1, false, 3, 5, 2, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+  }
+  if (precision == MIL_PREC_FP16) return launch_pair<1, true, 6, 5, 1, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+  return launch_pair<1, false, 6, 5, 1, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
 }
 
 }  // namespace pairk
+
+// 64-wide stages (two 32-wide sub-steps) for the single-product modes when D allows; the 3-product mode has no room for them
+static int pair_ksub(int precision, int D) { return (precision != MIL_PREC_BF16X3 && D % 64 == 0) ? 2 : 1; }
 
 size_t pair_weight_image_bytes(int D, int H, int Da) { return ((size_t)H * D + (size_t)Da * H) * 2 * sizeof(uint16_t); }
 
@@ -550,13 +629,13 @@ int pair_build_images(const float* W1, int H, int D, const float* Wa, int Da, ui
   const int64_t i1 = (int64_t)H * (D / 8), i2 = (int64_t)Da * (H / 8);
   const unsigned b1 = (unsigned)((i1 + 255) / 256), b2 = (unsigned)((i2 + 255) / 256);
   if (precision == MIL_PREC_BF16X3) {
-    pair_split_w1_kernel<false, true><<<b1, 256, 0, stream>>>(W1, H, D, w1_img);
+    pair_split_w1_kernel<false, true><<<b1, 256, 0, stream>>>(W1, H, D, w1_img, pair_ksub(precision, D));
     pair_split_wa_kernel<false, true><<<b2, 256, 0, stream>>>(Wa, Da, H, wa_img);
   } else if (precision == MIL_PREC_FP16) {
-    pair_split_w1_kernel<true, false><<<b1, 256, 0, stream>>>(W1, H, D, w1_img);
+    pair_split_w1_kernel<true, false><<<b1, 256, 0, stream>>>(W1, H, D, w1_img, pair_ksub(precision, D));
     pair_split_wa_kernel<true, false><<<b2, 256, 0, stream>>>(Wa, Da, H, wa_img);
   } else {
-    pair_split_w1_kernel<false, false><<<b1, 256, 0, stream>>>(W1, H, D, w1_img);
+    pair_split_w1_kernel<false, false><<<b1, 256, 0, stream>>>(W1, H, D, w1_img, pair_ksub(precision, D));
     pair_split_wa_kernel<false, false><<<b2, 256, 0, stream>>>(Wa, Da, H, wa_img);
   }
   MIL_LAUNCH_CHECK();
@@ -571,8 +650,8 @@ int pair_fused_launch(const float* X, FusedParams p, int precision, cudaStream_t
   int rc;
   if ((rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)p.N, (uint64_t)p.D, BMC, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   const uint64_t w1_rows = (uint64_t)HMAX * p.D * 2 * NOP / 256, wa_rows = (uint64_t)128 * HMAX * 2 * NOP / 256;
-  if ((rc = make_map_2d(&mw1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, p.w1_img, w1_rows, 256, (uint32_t)(NOP * B_OP / 256), 256, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
-  if ((rc = make_map_2d(&mwa, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, p.wa_img, wa_rows, 256, (uint32_t)(NOP * B2_OP / 256), 256, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  if ((rc = make_map_2d(&mw1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, p.w1_img, w1_rows, 256, (uint32_t)(pair_ksub(precision, p.D) * NOP * B_OP / 256), 256, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  if ((rc = make_map_2d(&mwa, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, p.wa_img, wa_rows, 256, (uint32_t)(G2B_BUF / 256), 256, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   const int64_t n_tiles = (p.N + BMP - 1) / BMP;
   int pairs = num_sms() / 2;
   if (n_tiles < pairs) pairs = (int)n_tiles;

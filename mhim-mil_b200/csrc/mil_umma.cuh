@@ -74,6 +74,10 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// pull one box of a tensor map into L2 (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -91,6 +95,13 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// one lane of a fully converged warp (always the same one)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- thread-block cluster / CTA-pair (cta_group::2) variants ----
@@ -235,6 +246,28 @@ __device__ __forceinline__ void write_operand_row(uint32_t a_hi, uint32_t a_lo, 
   }
 }
 
+// The same in two phases (pack in registers, store later): lets a converter hand its fp32 staging slot back before it waits for
+// the operand stage.  The packs consume every loaded value, so all staging loads have completed when they are done.
+template <bool FP16, bool LO>
+__device__ __forceinline__ void pack_operand_row(const float (&x)[32], uint32_t (&h)[16], uint32_t (&l)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    h[i] = pack_hi<FP16>(x[2 * i], x[2 * i + 1]);
+    l[i] = LO ? pack_lo_bf16(x[2 * i], x[2 * i + 1], h[i]) : 0u;
+  }
+}
+template <bool LO>
+__device__ __forceinline__ void store_operand_row(uint32_t a_hi, uint32_t a_lo, int row, const uint32_t (&h)[16], const uint32_t (&l)[16]) {
+  const uint32_t row_off = (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 64u;
+  const uint32_t sw = (uint32_t)(row >> 1) & 3u;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(h[4 * c]), "r"(h[4 * c + 1]), "r"(h[4 * c + 2]), "r"(h[4 * c + 3]) : "memory");
+    if (LO) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(l[4 * c]), "r"(l[4 * c + 1]), "r"(l[4 * c + 2]), "r"(l[4 * c + 3]) : "memory");
+  }
+}
+
 // Short inline transcendental activations (MUFU ex2/rcp based).  Inlining libm's erff/tanhf/expf at every element made the
 // kernel 600 KB of SASS (instruction-cache bound) and calling them out of line cost ~250 cycles per element.
 //   tanh(x)    = 1 - 2 / (1 + e^{2x})                                   |abs err| <~ 5e-7
@@ -324,7 +357,10 @@ __device__ __forceinline__ void grid_finalize(const FusedParams& p, int et, int 
   if (et == 0) *flag = (atomicAdd(p.counter, 1u) == gridDim.x - 1) ? 1 : 0;
   named_bar_sync(1, 256);
   if (!*flag) return;
+  auto fstamp = [&](int k) { if (p.trace && et == 0) p.trace[224 + k] = clock64(); };
+  fstamp(0);
   __threadfence();
+  fstamp(1);
   const int np = (int)gridDim.x;                        // <= 256 partials
   float* wgt = scratch;                                 // [np] exp(m_i - m)
   float* sm_m = scratch + 256;                          // [np] m_i (-inf for idle partials)
@@ -335,12 +371,15 @@ __device__ __forceinline__ void grid_finalize(const FusedParams& p, int et, int 
     sm_l[i] = li;
   }
   named_bar_sync(1, 256);
+  fstamp(2);
   float mg = -INFINITY;
   for (int i = 0; i < np; ++i) mg = fmaxf(mg, sm_m[i]);
   for (int i = et; i < np; i += 256) wgt[i] = sm_l[i] > 0.f ? expf(sm_m[i] - mg) : 0.f;
   named_bar_sync(1, 256);
+  fstamp(3);
   float lg = 0.f;
   for (int i = 0; i < np; ++i) lg = fmaf(sm_l[i], wgt[i], lg);      // fixed order: identical in every thread
+  fstamp(4);
   {
     const int c2 = et * 2;                              // 256 threads x 2 columns (records are 8-byte aligned: float2 loads)
     float2 v = make_float2(0.f, 0.f);
@@ -358,6 +397,7 @@ __device__ __forceinline__ void grid_finalize(const FusedParams& p, int et, int 
         v.x = fmaf(q2[j].x, wi, v.x); v.y = fmaf(q2[j].y, wi, v.y);
       }
     }
+    fstamp(5);
     named_bar_sync(1, 256);                             // pooled_s may alias the CTA's own partial sums: all reads are done
     v.x /= lg; v.y /= lg;
     *reinterpret_cast<float2*>(pooled_s + c2) = v;
@@ -374,6 +414,7 @@ __device__ __forceinline__ void grid_finalize(const FusedParams& p, int et, int 
       if (lane == 0) p.logits[k] = a + (p.bcls ? p.bcls[k] : 0.f);
     }
   }
+  fstamp(6);
 }
 
 // ---- host helpers shared by the fused-pass translation units (defined in mil_fused_sm100.cu) ----

@@ -34,6 +34,13 @@ for prec in os.environ.get("PROF_PREC", "bf16x3,fp16").split(","):
     print(f"== {prec}: kernel span {(t_last - t_first) / 1e3:.1f} us; CTA start spread {(int(g[:, 0].max()) - t_first) / 1e3:.1f} us; "
           f"per-CTA duration min {dur.min():.1f} / median {dur.median():.1f} / max {dur.max():.1f} us; "
           f"3-tile CTAs (0..94) median {dur[:95].median():.1f}, 2-tile CTAs median {dur[95:].median():.1f}")
+    fl = t.view(-1)
+    print(f"   CTA 0: {int(fl[239]) - int(fl[238])} cycles in {(int(g[0, 1]) - int(g[0, 0])) / 1e3:.1f} us -> {(int(fl[239]) - int(fl[238])) / max(int(g[0, 1]) - int(g[0, 0]), 1):.3f} GHz")
+    print("   grid_finalize stamps (cycles since entry): " + " ".join(str(int(fl[224 + k]) - int(fl[224])) for k in range(7)))
+    order = torch.argsort(g[:, 1], descending=True)[:6]
+    print("   last CTAs to finish (block, start us, end us): " + ", ".join(f"({int(i)}, {(int(g[i, 0]) - t_first) / 1e3:.1f}, {(int(g[i, 1]) - t_first) / 1e3:.1f})" for i in order))
+    ends = torch.sort((g[:, 1] - t_first).double() / 1e3).values
+    print("   end-time percentiles us: " + ", ".join(f"p{q}={float(ends[int(q / 100 * (len(ends) - 1))]):.1f}" for q in (0, 10, 50, 90, 100)))
     print(f"== {prec}: per-tile phase stamps of CTA 0, cycles relative to g1_start of tile 0")
     t0 = int(t[0, 0])
     for tl in range(4):

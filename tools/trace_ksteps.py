@@ -25,7 +25,7 @@ err = a + 512 * 1024 * 4 + 128 * 512 * 4
 tr = ((err + 16) + 63) & ~63
 off = tr - base
 t = ws[off + 1024 * 8: off + (1024 + 7 * 64) * 8].view(torch.int64).view(7, 64).cpu()
-names = ["W:empty", "I:full", "I:qd", "C:empty", "C:arrived", "C:xfull", "X:xempty"]
+names = ["W:empty/st", "I:full/st", "I:top/st", "C:empty", "C:arrived", "C:xfull", "X:xempty"]
 t0 = int(t[2, 0])
 print("k-step  " + "  ".join(f"{n:>10s}" for n in names))
 for it in range(64):
