@@ -85,7 +85,8 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   constexpr int B_XFULL = 0, B_XEMPTY = B_XFULL + XS, B_FULL = B_XEMPTY + XS, B_EMPTY = B_FULL + NST,
                 B_ACCFULL = B_EMPTY + NST, B_ACCEMPTY = B_ACCFULL + 2, B_TAILFREE = B_ACCEMPTY + 2, B_UFULL = B_TAILFREE + 2,
                 B_G2AFULL = B_UFULL + 1, B_G2AEMPTY = B_G2AFULL + G2S, B_G2BFULL = B_G2AEMPTY + G2S, B_G2BEMPTY = B_G2BFULL + 2,
-                B_COUNT = B_G2BEMPTY + 2;
+                B_FIN = B_G2BEMPTY + 2,
+                B_COUNT = B_FIN + 2;
   static_assert(B_COUNT * 8 <= 512, "barrier block overflow");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,7 +110,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACCFULL + i), 1); mbar_init(BAR(B_ACCEMPTY + i), 16); mbar_init(BAR(B_TAILFREE + i), 8); }
     mbar_init(BAR(B_UFULL), 1);
     for (int i = 0; i < G2S; ++i) { mbar_init(BAR(B_G2AFULL + i), 4); mbar_init(BAR(B_G2AEMPTY + i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_G2BFULL + i), 1); mbar_init(BAR(B_G2BEMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_G2BFULL + i), 1); mbar_init(BAR(B_G2BEMPTY + i), 1); mbar_init(BAR(B_FIN + i), 1); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -297,6 +298,9 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) {
       for (int ks = 0; ks < KS; ++ks, ++it) {
         if ((int)(it & 1) != grp) continue;
+        // Parity waits are only sound if the waiter sees every phase of its barrier: the rings are even (XS) or shared by both groups
+        // within every stage (KSUB == 2), so a staging slot / stage always belongs to the same group.
+        static_assert(!(XS & 1) && (KSUB == 2 || !(NST & 1)), "two converter groups need even rings");
         const uint32_t xs = it % XS, xph = (it / XS) & 1;
         const uint32_t st = it / KSUB, sub = it % KSUB, s = st % NST, ph = (st / NST) & 1;
         mbar_wait(BAR(B_XFULL + xs), xph, p.err, 10);
@@ -517,7 +521,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       out[0] = m_cta;
       out[1] = red_l[0] * f_0 + red_l[1] * f_1;
     }
-    grid_finalize(p, et, lane, t_part, p_acc, reinterpret_cast<int*>(s_part + 16));
+    grid_finalize(p, et, lane, t_part, smem, (uint32_t)(sMisc - smem), BAR(B_FIN), reinterpret_cast<int*>(s_part + 16));
   }
 
   tc_fence_before();
@@ -598,6 +602,7 @@ static int launch_pair(const CUtensorMap& mx, const CUtensorMap& mw1, const CUte
     MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
+  mil_set_notrap();
   prof_begin(stream);
   kern<<<grid, NUM_THREADS, smem, stream>>>(mx, mw1, mwa, p);
   prof_end(stream);
@@ -608,13 +613,13 @@ static int launch_pair(const CUtensorMap& mx, const CUtensorMap& mw1, const CUte
 template <int ACT, int ATT>
 static int dispatch_prec(int precision, const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mwa, const FusedParams& p, int grid,
                          cudaStream_t stream) {
-  if (precision == MIL_PREC_BF16X3) return launch_pair<3, false, 3, 3, 1, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+  if (precision == MIL_PREC_BF16X3) return launch_pair<3, false, 2, 4, 1, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
   if (p.D % 64 == 0) {
-    if (precision == MIL_PREC_FP16) return launch_pair<1, true, 3, 5, 2, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
-    return launch_pair<1, false, 3, 5, 2, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+    if (precision == MIL_PREC_FP16) return launch_pair<1, true, 3, 4, 2, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+    return launch_pair<1, false, 3, 4, 2, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
   }
-  if (precision == MIL_PREC_FP16) return launch_pair<1, true, 6, 5, 1, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
-  return launch_pair<1, false, 6, 5, 1, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+  if (precision == MIL_PREC_FP16) return launch_pair<1, true, 6, 4, 1, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+  return launch_pair<1, false, 6, 4, 1, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
 }
 
 }  // namespace pairk

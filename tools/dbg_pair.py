@@ -28,5 +28,6 @@ for N in [int(v) for v in os.environ.get("NS", "64,128,200,1000,20000").split(",
             msg += f" h {e(out['h'], h):.2e}"
             bad = ((out["h"].double() - h).abs() > 1e-2 * h.abs().max()).nonzero()
             if len(bad):
-                msg += f" first bad h idx {bad[:4].tolist()} n_bad {len(bad)}"
+                rows = torch.unique(bad[:, 0]).tolist()
+                msg += f" n_bad {len(bad)} bad rows {rows[:12]} (mod 128: {[r % 128 for r in rows[:12]]})"
         print(msg, flush=True)

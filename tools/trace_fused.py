@@ -36,7 +36,7 @@ for prec in os.environ.get("PROF_PREC", "bf16x3,fp16").split(","):
           f"3-tile CTAs (0..94) median {dur[:95].median():.1f}, 2-tile CTAs median {dur[95:].median():.1f}")
     fl = t.view(-1)
     print(f"   CTA 0: {int(fl[239]) - int(fl[238])} cycles in {(int(g[0, 1]) - int(g[0, 0])) / 1e3:.1f} us -> {(int(fl[239]) - int(fl[238])) / max(int(g[0, 1]) - int(g[0, 0]), 1):.3f} GHz")
-    print("   grid_finalize stamps (cycles since entry): " + " ".join(str(int(fl[224 + k]) - int(fl[224])) for k in range(7)))
+    print("   grid_finalize stamps (cycles since entry): " + " ".join(str(int(fl[224 + k]) - int(fl[224])) for k in range(5)))
     order = torch.argsort(g[:, 1], descending=True)[:6]
     print("   last CTAs to finish (block, start us, end us): " + ", ".join(f"({int(i)}, {(int(g[i, 0]) - t_first) / 1e3:.1f}, {(int(g[i, 1]) - t_first) / 1e3:.1f})" for i in order))
     ends = torch.sort((g[:, 1] - t_first).double() / 1e3).values
