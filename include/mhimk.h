@@ -35,6 +35,15 @@ enum {
   MIL_PREC_BF16   = 2  /* single bf16 product (fastest, ~2^-9 operand rounding) */
 };
 
+/* pipeline of the fused pass, OR-ed into `precision` as (pipeline << 8); 0 = library default */
+enum {
+  MIL_PIPE_DEFAULT = 0,
+  MIL_PIPE_SINGLE  = 1, /* one CTA per 128-row tile (cta_group::1, M = 128): the accumulator fills TMEM, the epilogue of a tile
+                           runs after its GEMM1 */
+  MIL_PIPE_PAIR    = 2  /* two CTAs of a cluster share every MMA (cta_group::2, M = 128 -> 64 rows per CTA): the accumulator is
+                           256 TMEM columns, double-buffered, so the epilogue of tile t overlaps GEMM1 of tile t+1 */
+};
+
 typedef void* mil_stream_t; /* cudaStream_t */
 
 int         mil_abi_version(void);
@@ -54,13 +63,15 @@ int         mil_device_supported(void);
  * s_out     nullable float[N]: raw attention logits (-inf for skipped rows).
  * t_out     nullable float[N,C]: t_{n,c} = h_n . Wp_c (needs Wp [C,H], C <= 4) -- input of mil_cam_score_f32.
  * h_out     nullable float[N,H]: materialised embedding (training / return_act).
- * part      float[n_part,(2+H)] scratch for the per-CTA partials, n_part = mil_fused_num_partials().
+ * part      float[n_part,(2+H)] scratch for the per-CTA partials, n_part = mil_fused_num_partials() (one record more than
+ *           CTAs are launched: the bulk copies of the in-kernel merge round up to 16 bytes).
  * stats     float[2] = (m, l); pooled float[H]: written by the last CTA to finish (in-kernel log-sum-exp merge of the partials).
  * logits    nullable float[n_cls] = Wcls pooled + bcls (classifier fused into the same tail; replaces abmil.py:238 /
  *           mhim.py:267); Wcls [n_cls, H], bcls nullable.
  * ws / ws_bytes: scratch of at least mil_fused_workspace_bytes(D, H, Da, gated) bytes; it holds the 16-bit hi/lo images of
  *           W1 and Wa.  ws_ready = 0: the images are (re)built by this call; ws_ready = 1: the caller guarantees `ws` was
- *           filled by an earlier call with the same weights and precision (skips two small kernels per bag).
+ *           filled by an earlier call with the same weights, precision AND pipeline (skips two small kernels per bag).
+ * precision MIL_PREC_* | (MIL_PIPE_* << 8).
  */
 int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H,
                             const float* W1, const float* b1, int act,

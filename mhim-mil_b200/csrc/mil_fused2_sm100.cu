@@ -92,6 +92,10 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();                    // 0 = leader (issues every MMA of the pair)
   auto LEADER = [&](int i) { return mapa_shared(BAR(i), 0); };  // cluster address of barrier i in the leader CTA
+  auto ARRIVE_LEADER = [&](int i) {                            // the leader takes the plain shared::cta path for its own barriers
+    if (rank == 0) mbar_arrive(BAR(i));
+    else mbar_arrive_cluster(mapa_shared(BAR(i), 0));
+  };
   if (p.trace && threadIdx.x == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
@@ -106,7 +110,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < XS; ++i) { mbar_init(BAR(B_XFULL + i), 1); mbar_init(BAR(B_XEMPTY + i), 2); }
-    for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_FULL + i), ((p.dbg & 64) ? 2 : 4) * KSUB + 1); mbar_init(BAR(B_EMPTY + i), 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_FULL + i), 4 * KSUB + 1); mbar_init(BAR(B_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACCFULL + i), 1); mbar_init(BAR(B_ACCEMPTY + i), 16); mbar_init(BAR(B_TAILFREE + i), 8); }
     mbar_init(BAR(B_UFULL), 1);
     for (int i = 0; i < G2S; ++i) { mbar_init(BAR(B_G2AFULL + i), 4); mbar_init(BAR(B_G2AEMPTY + i), 1); }
@@ -290,8 +294,9 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   } else if (warp >= CONV_WARP0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
     // ===================== converters: fp32 staging -> 16-bit hi/lo A tiles =====================
-    // Two groups of two warps alternate k-steps (one row of the 64-row slab per thread): each group has two k-step times
-    // for its wait -> load -> convert -> store -> fence -> arrive latency chain.
+    {
+    // Two groups of two warps alternate sub-steps (one row of the 64-row slab per thread): each group has two sub-step times for
+    // its wait -> load -> convert -> store -> fence -> arrive latency chain.
     const int grp = (warp - CONV_WARP0) >> 1;
     const int row = ((warp - CONV_WARP0) & 1) * 32 + lane;
     uint32_t it = 0;
@@ -304,7 +309,6 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const uint32_t xs = it % XS, xph = (it / XS) & 1;
         const uint32_t st = it / KSUB, sub = it % KSUB, s = st % NST, ph = (st / NST) & 1;
         mbar_wait(BAR(B_XFULL + xs), xph, p.err, 10);
-        if (lane == 0 && ((warp - CONV_WARP0) & 1) == 0) kstamp(p, 5, it);
         float x[32];
         const uint32_t src = smem_u32(sX + xs * X_SLOT) + (uint32_t)row * 128u;
 #pragma unroll
@@ -318,13 +322,13 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_XEMPTY + xs));                             // the slot is in registers: hand it back at once
         mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 11);
-        if (lane == 0 && ((warp - CONV_WARP0) & 1) == 0) kstamp(p, 3, it);
         const uint32_t a_hi = smem_u32(sA + s * A_STAGE + sub * A_SUB);
         store_operand_row<LO>(a_hi, a_hi + A_OP, row, hi, lo);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0 && !((p.dbg & 64) && rank != 0)) { mbar_arrive_cluster(LEADER(B_FULL + s)); if (((warp - CONV_WARP0) & 1) == 0) kstamp(p, 4, it); }
+        if (lane == 0) ARRIVE_LEADER(B_FULL + s);
       }
+    }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");

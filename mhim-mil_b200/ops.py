@@ -275,10 +275,11 @@ PIPELINES = {"single": 1, "pair": 2}
 
 
 def _pipeline(name):
-    """'pair' (default: two CTAs share every MMA, double-buffered TMEM) or 'single' (one CTA per tile); MHIMK_PIPELINE=1|2 sets the default."""
+    """'single' (default: one CTA per 128-row tile) or 'pair' (two CTAs share every MMA, double-buffered TMEM accumulators, the
+    epilogue overlaps the next tile's GEMM1; measured on par with 'single' so far); MHIMK_PIPELINE=1|2 sets the default."""
     import os
     if name in (None, "auto"):
-        name = {"1": "single", "2": "pair"}.get(os.environ.get("MHIMK_PIPELINE", ""), "pair")
+        name = {"1": "single", "2": "pair"}.get(os.environ.get("MHIMK_PIPELINE", ""), "single")
     if name not in PIPELINES:
         raise ValueError(f"mhimk: unknown fused pipeline {name!r}")
     return name
