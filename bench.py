@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- patch-instances/s through the MIL aggregator at N=50 000 x D=1024 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16x3|fp16|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16x3|fp16|bf16] [--pipeline single|pair]
 
 One "step" = one pass of the hot path (abmil.DAttention eval forward: projection -> gated tanh attention logit ->
 softmax over N -> weighted pool -> classifier) over one synthetic bag of N=50 000 x D=1024 fp32 (204.8 MB).
@@ -108,6 +108,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp16", "bf16"])
+    ap.add_argument("--pipeline", default="single", choices=["single", "pair"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -129,6 +130,7 @@ def main():
     model = DAttention(D_IN, N_CLASSES, dropout=0.0, act="relu").to(dev).eval()
     model.load_state_dict({k: v.to(dev) for k, v in cases.abmil_state(2021).items()}, strict=True)
     model.precision = args.precision
+    os.environ["MHIMK_PIPELINE"] = {"single": "1", "pair": "2"}[args.pipeline]      # library default for the fused pass
     # 4 distinct bags (820 MB) visited round-robin: every step streams 205 MB that cannot be in the 126 MB L2
     n_bags = 4
     bags = [torch.randn(1, N_INST, D_IN, device=dev, generator=torch.Generator(device=dev).manual_seed(2021 + 17 * rank + i)) for i in range(n_bags)]
@@ -203,7 +205,7 @@ def main():
             traffic = json.load(open(tp)).get(args.precision)
         out = {"metric": METRIC, "value": value, "unit": "instances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-               "data": "synthetic", "precision": args.precision,
+               "data": "synthetic", "precision": args.precision, "pipeline": args.pipeline,
                "config": {"workload": WORKLOAD, "parallelism": f"bag-parallel x{world}", "l2": "4 distinct 205 MB bags round-robin (> 126 MB L2)",
                           "operand_arithmetic": {"bf16x3": "bf16 hi+lo split, 3 tcgen05 products, fp32 accumulate", "fp16": "single fp16 product",
                                                  "bf16": "single bf16 product"}[args.precision]},

@@ -318,15 +318,12 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
         uint32_t hi[16], lo[16];
         pack_operand_row<FP16, LO>(x, hi, lo);                                      // consumes every staged value
-        asm volatile("" ::"r"(hi[0]), "r"(hi[5]), "r"(hi[10]), "r"(hi[15]) : "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_XEMPTY + xs));                             // the slot is in registers: hand it back at once
         mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 11);
         const uint32_t a_hi = smem_u32(sA + s * A_STAGE + sub * A_SUB);
         store_operand_row<LO>(a_hi, a_hi + A_OP, row, hi, lo);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) ARRIVE_LEADER(B_FULL + s);
+        if (lane == 0) { ARRIVE_LEADER(B_FULL + s); mbar_arrive(BAR(B_XEMPTY + xs)); }
       }
     }
     }

@@ -291,10 +291,8 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
           }
           pack_operand_row<FP16, LO>(x, hi[rr], lo[rr]);      // consumes every staged value: the loads are complete afterwards
         }
-        asm volatile("" ::"r"(hi[0][0]), "r"(hi[0][15]), "r"(hi[RPT - 1][7]), "r"(hi[RPT - 1][15]) : "memory");
-        __syncwarp();
-        const bool late = (p.dbg & 256) != 0;
-        if (lane == 0 && !late) mbar_arrive(BAR(B_XEMPTY + xb));       // the slot is in registers: hand it back before waiting for the stage
+        // (Handing the staging slot back right here, before the stage wait, looked free but produced a wrong row about once in 10^5
+        // k-steps: the slot is released only after the operand stores below.)
         mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 11);
         const uint32_t a_hi = smem_u32(sA + s * A_STAGE);
         if (!(p.dbg & 8)) {
@@ -303,7 +301,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(BAR(B_FULL + s)); if (late) mbar_arrive(BAR(B_XEMPTY + xb)); }
+        if (lane == 0) { mbar_arrive(BAR(B_FULL + s)); mbar_arrive(BAR(B_XEMPTY + xb)); }
       }
     }
   } else {
@@ -359,11 +357,9 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
       }
     } else {
       // running online-softmax state of this warp: rows = its 32 lanes, columns = its 8 chunks (chunk c = 2 j + half);
-      // the pooled partial sums live in shared memory: prun[j * 32 + lane] = column (2 j + half) * 32 + lane
+      // pooled partial sums: prun[j] (this lane) = column (2 j + half) * 32 + lane
       float m_run = -INFINITY, l_run = 0.f;
-      float* prun = p_acc + (warp - EPI_WARP0) * 256;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) prun[j * 32 + lane] = 0.f;
+      float prun[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // registers; handed over through p_acc after the last tile
       const float bc = p.bc ? p.bc[0] : 0.f;
 
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
@@ -478,12 +474,11 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
           for (int i = 0; i < 32; ++i) { keep_h[0][i] *= w; keep_h[1][i] *= w; }
           float r0, r1;
           warp_transpose_sum2(keep_h[0], keep_h[1], r0, r1);
-          prun[lane] = prun[lane] * scale + r0;
-          prun[32 + lane] = prun[32 + lane] * scale + r1;
+          prun[0] = prun[0] * scale + r0;
+          prun[1] = prun[1] * scale + r1;
         }
-#pragma unroll 1
+#pragma unroll
         for (int j = 2; j < 8; j += 2) {
-          if (p.dbg & 32) break;
           float ha[32], hb[32];
           uint32_t va[32], vb[32];
           tmem_ld32(tq + (uint32_t)((2 * j + half) * 32), va);
@@ -493,8 +488,8 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
           for (int i = 0; i < 32; ++i) { ha[i] = __uint_as_float(va[i]) * w; hb[i] = __uint_as_float(vb[i]) * w; }
           float r0, r1;
           warp_transpose_sum2(ha, hb, r0, r1);
-          prun[j * 32 + lane] = prun[j * 32 + lane] * scale + r0;
-          prun[(j + 1) * 32 + lane] = prun[(j + 1) * 32 + lane] * scale + r1;
+          prun[j] = prun[j] * scale + r0;
+          prun[j + 1] = prun[j + 1] * scale + r1;
         }
         tc_fence_before();
         __syncwarp();
@@ -506,6 +501,8 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
       float* red_m = s_part;                                // [4]
       float* red_l = s_part + 4;                            // [4]
       named_bar_sync(1, 256);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p_acc[(warp - EPI_WARP0) * 256 + j * 32 + lane] = prun[j];
       if (half == 0 && lane == 0) { red_m[q] = m_run; red_l[q] = l_run; }
       named_bar_sync(1, 256);
       const float m_cta = fmaxf(fmaxf(red_m[0], red_m[1]), fmaxf(red_m[2], red_m[3]));

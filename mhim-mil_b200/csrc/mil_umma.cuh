@@ -396,7 +396,8 @@ __device__ __forceinline__ void grid_finalize(const FusedParams& p, int et, int 
     mbar_expect_tx(bar, bytes);
     bulk_load(stage0 + (uint32_t)(chunk & 1) * buf_bytes, reinterpret_cast<const uint8_t*>(p.part) + (size_t)i0 * REC, bytes, bar);
   };
-  if (et == 0) { fence_proxy_async(); issue(0); issue(1); }
+  // the partials were written with generic-proxy stores (by every CTA, this one included) and are read by the async proxy
+  if (et == 0) { asm volatile("fence.proxy.async;" ::: "memory"); issue(0); issue(1); }
   fstamp(1);
   // (m, l) of every partial: one thread each, block-wide max / fixed-order sum through shared memory
   float* wgt = scratch;                                  // [256] exp(m_i - m)
@@ -436,7 +437,7 @@ __device__ __forceinline__ void grid_finalize(const FusedParams& p, int et, int 
       v.x = fmaf(q2.x, w, v.x); v.y = fmaf(q2.y, w, v.y);
     }
     named_bar_sync(1, 256);                              // everybody is done with this buffer
-    if (et == 0) issue(ch + 2);
+    if (et == 0) { fence_proxy_async(); issue(ch + 2); }
   }
   fstamp(3);
   float* pooled_s = scratch;                             // wgt is dead: [512] merged pooled vector
