@@ -30,9 +30,10 @@ xs = [torch.randn(hi - lo, DIM, device=dev, generator=torch.Generator(device=dev
 
 
 def step(i):
-    if world > 1:
-        return D.sharded_abmil_forward(m, xs[i % 3])[0]
-    return m(xs[i % 3][None])
+    with torch.no_grad():                       # inference path on every rank count (without it the 1-GPU arm ran the autograd path)
+        if world > 1:
+            return D.sharded_abmil_forward(m, xs[i % 3])[0]
+        return m(xs[i % 3][None])
 
 
 for i in range(5):
