@@ -109,8 +109,8 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   const int64_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < XS; ++i) { mbar_init(BAR(B_XFULL + i), 1); mbar_init(BAR(B_XEMPTY + i), 2); }
-    for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_FULL + i), 4 * KSUB + 1); mbar_init(BAR(B_EMPTY + i), 1); }
+    for (int i = 0; i < XS; ++i) { mbar_init(BAR(B_XFULL + i), 1); mbar_init(BAR(B_XEMPTY + i), LO ? 4 : 2); }
+    for (int i = 0; i < NST; ++i) { mbar_init(BAR(B_FULL + i), (LO ? 8 : 4) * KSUB + 1); mbar_init(BAR(B_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_ACCFULL + i), 1); mbar_init(BAR(B_ACCEMPTY + i), 16); mbar_init(BAR(B_TAILFREE + i), 8); }
     mbar_init(BAR(B_UFULL), 1);
     for (int i = 0; i < G2S; ++i) { mbar_init(BAR(B_G2AFULL + i), 4); mbar_init(BAR(B_G2AEMPTY + i), 1); }
@@ -294,9 +294,46 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   } else if (warp >= CONV_WARP0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
     // ===================== converters: fp32 staging -> 16-bit hi/lo A tiles =====================
-    {
-    // Two groups of two warps alternate sub-steps (one row of the 64-row slab per thread): each group has two sub-step times for
-    // its wait -> load -> convert -> store -> fence -> arrive latency chain.
+    if (LO) {
+      // 3-product mode (768 MMA cycles per sub-step): all four warps work on every sub-step, half a row (16 values) per thread.
+      // No group alternation, so any ring size is sound for the parity waits.
+      const int tid = threadIdx.x - CONV_WARP0 * 32, row = tid >> 1, hf = tid & 1;
+      const uint32_t row_off = (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 64u, sw = (uint32_t)(row >> 1) & 3u;
+      uint32_t it = 0;
+      for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) {
+        for (int ks = 0; ks < KS; ++ks, ++it) {
+          const uint32_t xs = it % XS, xph = (it / XS) & 1;
+          const uint32_t st = it / KSUB, sub = it % KSUB, s = st % NST, ph = (st / NST) & 1;
+          mbar_wait(BAR(B_XFULL + xs), xph, p.err, 10);
+          float x[16];
+          const uint32_t src = smem_u32(sX + xs * X_SLOT) + (uint32_t)row * 128u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t a = src + ((((uint32_t)(4 * hf + j)) ^ ((uint32_t)row & 7u)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[4 * j]), "=f"(x[4 * j + 1]), "=f"(x[4 * j + 2]), "=f"(x[4 * j + 3]) : "r"(a));
+          }
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            hi[i] = pack_hi<FP16>(x[2 * i], x[2 * i + 1]);
+            lo[i] = pack_lo_bf16(x[2 * i], x[2 * i + 1], hi[i]);
+          }
+          mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 11);
+          const uint32_t a_hi = smem_u32(sA + s * A_STAGE + sub * A_SUB) + row_off;
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const uint32_t off = (((uint32_t)(2 * hf + cc)) ^ sw) << 4;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(hi[4 * cc]), "r"(hi[4 * cc + 1]), "r"(hi[4 * cc + 2]), "r"(hi[4 * cc + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + A_OP + off), "r"(lo[4 * cc]), "r"(lo[4 * cc + 1]), "r"(lo[4 * cc + 2]), "r"(lo[4 * cc + 3]) : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) { ARRIVE_LEADER(B_FULL + s); mbar_arrive(BAR(B_XEMPTY + xs)); }
+        }
+      }
+    } else {
+    // Single-product modes: two groups of two warps alternate sub-steps (one row of the 64-row slab per thread): each group has two
+    // sub-step times for its wait -> load -> convert -> store -> fence -> arrive latency chain.
     const int grp = (warp - CONV_WARP0) >> 1;
     const int row = ((warp - CONV_WARP0) & 1) * 32 + lane;
     uint32_t it = 0;
@@ -305,7 +342,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         if ((int)(it & 1) != grp) continue;
         // Parity waits are only sound if the waiter sees every phase of its barrier: the rings are even (XS) or shared by both groups
         // within every stage (KSUB == 2), so a staging slot / stage always belongs to the same group.
-        static_assert(!(XS & 1) && (KSUB == 2 || !(NST & 1)), "two converter groups need even rings");
+        static_assert(LO || (!(XS & 1) && (KSUB == 2 || !(NST & 1))), "two converter groups need even rings");
         const uint32_t xs = it % XS, xph = (it / XS) & 1;
         const uint32_t st = it / KSUB, sub = it % KSUB, s = st % NST, ph = (st / NST) & 1;
         mbar_wait(BAR(B_XFULL + xs), xph, p.err, 10);
@@ -614,7 +651,7 @@ static int launch_pair(const CUtensorMap& mx, const CUtensorMap& mw1, const CUte
 template <int ACT, int ATT>
 static int dispatch_prec(int precision, const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mwa, const FusedParams& p, int grid,
                          cudaStream_t stream) {
-  if (precision == MIL_PREC_BF16X3) return launch_pair<3, false, 2, 4, 1, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+  if (precision == MIL_PREC_BF16X3) return launch_pair<3, false, 3, 3, 1, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
   if (p.D % 64 == 0) {
     if (precision == MIL_PREC_FP16) return launch_pair<1, true, 3, 4, 2, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
     return launch_pair<1, false, 3, 4, 2, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
