@@ -10,6 +10,7 @@ for p in bf16x3 fp16; do
   timeout 600 python bench.py --steps 50 --warmup 5 --precision $p > gpurun_out/bench_$p.json 2> gpurun_out/bench_$p.err; tail -1 gpurun_out/bench_$p.json
 done
 timeout 600 python bench.py --steps 50 --warmup 5 --precision fp16 --pipeline pair --no-cpu-baseline > gpurun_out/bench_fp16_pair.json 2> gpurun_out/bench_fp16_pair.err; tail -1 gpurun_out/bench_fp16_pair.json
+timeout 600 python bench.py --steps 50 --warmup 5 --precision bf16x3 --pipeline single --no-cpu-baseline > gpurun_out/bench_bf16x3_single.json 2> gpurun_out/bench_bf16x3_single.err; tail -1 gpurun_out/bench_bf16x3_single.json
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference.json 2>&1; tail -1 gpurun_out/bench_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
    python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
@@ -18,4 +19,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:mil_
 timeout 300 env PROF_REPS=10 python tools/prof_fused.py > gpurun_out/prof_fused.log 2>&1; cat gpurun_out/prof_fused.log
 timeout 300 python tools/trace_fused.py > gpurun_out/trace_fused.log 2>&1; tail -30 gpurun_out/trace_fused.log
 MHIMK_PIPELINE=2 PROF_PREC=fp16 timeout 300 python tools/trace_fused.py > gpurun_out/trace_fused_pair.log 2>&1; tail -12 gpurun_out/trace_fused_pair.log
+MHIMK_PIPELINE=1 PROF_PREC=bf16x3 timeout 300 python tools/trace_fused.py > gpurun_out/trace_fused_single_bf16x3.log 2>&1; tail -8 gpurun_out/trace_fused_single_bf16x3.log
 ls -la gpurun_out

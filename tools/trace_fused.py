@@ -19,7 +19,7 @@ for prec in os.environ.get("PROF_PREC", "bf16x3,fp16").split(","):
         ops.abmil_fused_forward(x, sd["feature.0.weight"], sd["feature.0.bias"], os.environ.get("PROF_ACT", "relu"), sd["attention.0.weight"],
                                 sd["attention.0.bias"], sd["attention.2.weight"], sd["attention.2.bias"], "tanh", precision=prec)
     torch.cuda.synchronize()
-    ws, _ = ops._fused_workspace(sd["feature.0.weight"], sd["attention.0.weight"], prec, ops._pipeline(None))
+    ws, _ = ops._fused_workspace(sd["feature.0.weight"], sd["attention.0.weight"], prec, ops._pipeline(None, prec))
     L = mhimk._lib.lib()
     total = L.mil_fused_workspace_bytes(1024, 512, 128, 0)
     base = ws.data_ptr()

@@ -18,7 +18,7 @@ for rep in range(2):
     ops.abmil_fused_forward(x, sd["feature.0.weight"], sd["feature.0.bias"], "relu", sd["attention.0.weight"], sd["attention.0.bias"],
                             sd["attention.2.weight"], sd["attention.2.bias"], "tanh", precision=prec)
 torch.cuda.synchronize()
-ws, _ = ops._fused_workspace(sd["feature.0.weight"], sd["attention.0.weight"], prec, ops._pipeline(None))
+ws, _ = ops._fused_workspace(sd["feature.0.weight"], sd["attention.0.weight"], prec, ops._pipeline(None, prec))
 base = ws.data_ptr()
 a = (base + 255) & ~255
 err = a + 512 * 1024 * 4 + 128 * 512 * 4
