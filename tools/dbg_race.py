@@ -7,8 +7,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cases  # noqa: E402
 import mhimk  # noqa: E402
-if os.environ.get("MHIMK_OLD"):          # A/B against an older build of the library (same entry point, no pipeline bits)
-    mhimk._lib.LIB_PATH = os.path.join(ROOT, "tools", "_old", "libmhimk_old.so")
+if os.environ.get("MHIMK_OLD_LIB"):      # A/B against another build of the library (path to its libmhimk.so; no pipeline bits)
+    mhimk._lib.LIB_PATH = os.environ["MHIMK_OLD_LIB"]
     mhimk.ops.PIPELINES = {"single": 0, "pair": 0}
 
 pipe = os.environ.get("PIPE", "single")

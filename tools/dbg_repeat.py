@@ -1,9 +1,11 @@
+"""Launch the fused forward REPS times on the same bag and report every launch that is not bit-identical to the last one
+(pipeline-synchronisation regression probe; PIPE=single|pair PREC=bf16x3|fp16|bf16 N=... REPS=...)."""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cases, mhimk
-if os.environ.get('MHIMK_OLD'):
-    mhimk._lib.LIB_PATH = os.path.join(ROOT, 'tools', '_old', 'libmhimk_old.so'); mhimk.ops.PIPELINES = {'single': 0, 'pair': 0}
+if os.environ.get('MHIMK_OLD_LIB'):      # A/B against another build of the library
+    mhimk._lib.LIB_PATH = os.environ['MHIMK_OLD_LIB']; mhimk.ops.PIPELINES = {'single': 0, 'pair': 0}
 pipe = os.environ.get("PIPE", "single"); prec = os.environ.get("PREC", "bf16x3"); N = int(os.environ.get("N", 50000))
 c = {k: v.cuda() for k, v in cases.abmil_state(5).items()}
 x = cases.make_bag(9, N, 1024)[0].cuda()
