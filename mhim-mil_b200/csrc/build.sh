@@ -10,7 +10,7 @@ mkdir -p "$HERE/build"
 pids=()
 for f in mil_api mil_simt mil_topk mil_fused_sm100 mil_fused2_sm100; do
   if [ ! -f "$HERE/build/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/build/$f.o" ] || [ "$HERE/mil_common.cuh" -nt "$HERE/build/$f.o" ] || [ "$HERE/mil_umma.cuh" -nt "$HERE/build/$f.o" ] || [ "$ROOT/include/mhimk.h" -nt "$HERE/build/$f.o" ]; then
-    "$NVCC" "${FLAGS[@]}" ${PTXAS_V:+-Xptxas -v} -c "$HERE/$f.cu" -o "$HERE/build/$f.o" &
+    "$NVCC" "${FLAGS[@]}" ${PTXAS_V:+-Xptxas -v} ${KSTAMP:+-DMIL_KSTAMP} -c "$HERE/$f.cu" -o "$HERE/build/$f.o" &
     pids+=($!)
   fi
 done

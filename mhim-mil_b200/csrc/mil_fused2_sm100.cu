@@ -45,9 +45,12 @@ constexpr int CONV_WARP0 = 8;                 // warps 8..11 converters
 constexpr int W_X = 12, W_MMA1 = 13, W_W1 = 14, W_MMA2 = 15;   // bag TMA; GEMM1 issue; TMEM alloc + W1 TMA; Wa TMA + GEMM2 issue
 constexpr int MISC_BYTES = 512 + 1024 + 4096 + 16 + (HMAX + 256) * 4 + 8 * 128 * 4;
 
-// k-step stamps of CTA 0 (MHIMK_TRACE=1): series x first 64 k-steps, see tools/trace_ksteps.py
+// k-step stamps of CTA 0 (MHIMK_TRACE=1): series x first 64 k-steps, see tools/trace_ksteps.py.  Compiled in only with
+// -DMIL_KSTAMP (KSTAMP=1 csrc/build.sh): even a predicated-off stamp costs the control loops issue slots.
 __device__ __forceinline__ void kstamp(const FusedParams& p, int series, uint32_t it) {
+#ifdef MIL_KSTAMP
   if (p.trace && blockIdx.x == 0 && it < 64) p.trace[1024 + series * 64 + it] = clock64();
+#endif
 }
 
 template <int NPROD, bool FP16, int NST, int XS, int KSUB, int ACT, int ATT>
@@ -190,7 +193,8 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       // ===================== GEMM1 issuer (leader CTA) =====================
       const uint32_t idesc1 = make_idesc(FP16, 256, BMP);
       const uint32_t sa0 = smem_u32(sA), sb0 = smem_u32(sB);
-      uint32_t s = 0, ph = 0, tl = 0, iit = 0;
+      uint32_t s = 0, ph = 0, tl = 0, iit = 0, sq = 0, phq = 0, gi = 0;
+      const uint32_t qd = ((uint32_t)p.dbg >> 12) & 15u;
       for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs, ++tl) {
         const uint32_t b1 = tl & 1;
         mbar_wait(BAR(B_ACCEMPTY + b1), ((tl >> 1) & 1) ^ 1, p.err, 4);
@@ -199,6 +203,13 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const uint32_t d0 = tmem + b1 * 256;
         for (int kst = 0; kst < KST; ++kst) {
           if (lane == 0) kstamp(p, 2, iit);
+          // optional queue-depth limit (MHIMK_DEBUG bits 12..15 = qd): at most qd stages queued in the tensor pipe, so that GEMM2's
+          // short MMAs of the previous tile (other warp) do not wait behind a full ring of GEMM1 work
+          if (qd && gi >= qd) {
+            mbar_wait(BAR(B_EMPTY + sq), phq, p.err, 5);
+            if (++sq == (uint32_t)NST) { sq = 0; phq ^= 1; }
+          }
+          ++gi;
           mbar_wait(BAR(B_FULL + s), ph, p.err, 6);
           if (lane == 0) kstamp(p, 1, iit++);
           tc_fence_after();

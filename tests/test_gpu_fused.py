@@ -59,6 +59,27 @@ def test_fused_forward(K, pipe, prec, N, act, kind):
 
 
 @pytest.mark.parametrize("pipe", ["pair", "single"])
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16"])
+@pytest.mark.parametrize("N,D", [(777, 1536), (300, 96), (150, 32), (2000, 2048)])
+def test_fused_forward_other_feature_widths(K, pipe, prec, N, D):
+    """D = 1536 (GigaPath, BASELINE config 3), widths that are multiples of 32 but not of 64 (the pair pipeline's 32-wide stages),
+    a single k-step, and D = 2048."""
+    sd = cases.abmil_state(300 + D, D=D)
+    x = cases.make_bag(400 + D, N, D)
+    h_ref, s_ref, p_ref = run_oracle(sd, x, "gelu")
+    c = {k: v.cuda() for k, v in sd.items()}
+    out = K.abmil_fused_forward(x[0].cuda(), c["feature.0.weight"], c["feature.0.bias"], "gelu", c["attention.0.weight"], c["attention.0.bias"],
+                                c["attention.2.weight"], c["attention.2.bias"], "tanh", want_scores=True, want_h=True, precision=prec, pipeline=pipe,
+                                Wcls=c["classifier.weight"], bcls=c["classifier.bias"])
+    torch.cuda.synchronize()
+    assert cases.rel_err(out["h"], h_ref) < TOL[prec]
+    assert cases.rel_err(out["s"], s_ref) < TOL[prec] * 3
+    assert cases.rel_err(out["pooled"], p_ref) < TOL[prec]
+    ref_logits = p_ref @ sd["classifier.weight"].double().t() + sd["classifier.bias"].double()
+    assert cases.rel_err(out["logits"][0], ref_logits) < TOL[prec]
+
+
+@pytest.mark.parametrize("pipe", ["pair", "single"])
 def test_fused_forward_with_keep_mask(K, pipe):
     N = 3000
     sd = cases.abmil_state(7)

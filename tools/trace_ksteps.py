@@ -1,4 +1,5 @@
-"""Per-k-step stamps of CTA 0 of the pair pipeline (MHIMK_TRACE=1): who waits for whom in the operand ring."""
+"""Per-k-step stamps of CTA 0 of the pair pipeline (MHIMK_TRACE=1): who waits for whom in the operand ring.
+Needs a library built with the stamps compiled in:  KSTAMP=1 bash mhim-mil_b200/csrc/build.sh  (touch mil_fused2_sm100.cu first)."""
 import os
 import sys
 import torch
