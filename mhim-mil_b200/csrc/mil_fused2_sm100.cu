@@ -43,7 +43,7 @@ constexpr int NUM_THREADS = 512;
 constexpr int EPI_WARP0 = 0;                  // warps 0..7 epilogue
 constexpr int CONV_WARP0 = 8;                 // warps 8..11 converters
 constexpr int W_X = 12, W_MMA1 = 13, W_W1 = 14, W_MMA2 = 15;   // bag TMA; GEMM1 issue; TMEM alloc + W1 TMA; Wa TMA + GEMM2 issue
-constexpr int MISC_BYTES = 512 + 1024 + 4096 + 16 + (HMAX + 256) * 4 + 8 * 128 * 4;
+constexpr int MISC_BYTES = 512 + 1024 + 4096 + 16 + (HMAX + 256) * 4;
 
 // k-step stamps of CTA 0 (MHIMK_TRACE=1): series x first 64 k-steps, see tools/trace_ksteps.py.  Compiled in only with
 // -DMIL_KSTAMP (KSTAMP=1 csrc/build.sh): even a predicated-off stamp costs the control loops issue slots.
@@ -80,7 +80,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   float* c_b1 = reinterpret_cast<float*>(sMisc + 512 + 1024 + 4096 + 16);   // [512] feature bias
   float* c_ba = c_b1 + HMAX;                                                 // [128] attention bias
   float* c_wc = c_ba + 128;                                                  // [128] attention output weights
-  float* p_acc = c_wc + 128;                                                 // [8 warps][4 chunks][32 lanes] pooled partial sums
+  float* p_acc = reinterpret_cast<float*>(sX);                               // [8 warps][4 chunks][32 lanes]: hand-over buffer of the CTA tail (the staging ring is idle then)
 
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -316,6 +316,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           const uint32_t xs = it % XS, xph = (it / XS) & 1;
           const uint32_t st = it / KSUB, sub = it % KSUB, s = st % NST, ph = (st / NST) & 1;
           mbar_wait(BAR(B_XFULL + xs), xph, p.err, 10);
+          if (tid == 0) kstamp(p, 5, it);
           float x[16];
           const uint32_t src = smem_u32(sX + xs * X_SLOT) + (uint32_t)row * 128u;
 #pragma unroll
@@ -330,6 +331,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             lo[i] = pack_lo_bf16(x[2 * i], x[2 * i + 1], hi[i]);
           }
           mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 11);
+          if (tid == 0) kstamp(p, 3, it);
           const uint32_t a_hi = smem_u32(sA + s * A_STAGE + sub * A_SUB) + row_off;
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
@@ -340,6 +342,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) { ARRIVE_LEADER(B_FULL + s); mbar_arrive(BAR(B_XEMPTY + xs)); }
+          if (tid == 0) kstamp(p, 4, it);
         }
       }
     } else {
@@ -394,9 +397,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     named_bar_sync(1, 256);
 
     float m_run = -INFINITY, l_run = 0.f;
-    float* prun = p_acc + (warp - EPI_WARP0) * 128;          // prun[j * 32 + lane] = feature f0 + 32 j + lane
-#pragma unroll
-    for (int j = 0; j < 4; ++j) prun[j * 32 + lane] = 0.f;
+    float prun[4] = {0.f, 0.f, 0.f, 0.f};                  // registers: prun[j] (this lane) = pooled partial of feature f0 + 32 j + lane
     const float bc = p.bc ? p.bc[0] : 0.f;
     const uint32_t a2_hi = smem_u32(sA2 + strip * G2A_STAGE);
 
@@ -529,11 +530,12 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         for (int i = 0; i < 32; ++i) { keep_h[0][i] *= w; keep_h[1][i] *= w; }
         float r0, r1;
         warp_transpose_sum2(keep_h[0], keep_h[1], r0, r1);
-        prun[lane] = prun[lane] * scale + r0;
-        prun[32 + lane] = prun[32 + lane] * scale + r1;
+        prun[0] = prun[0] * scale + r0;
+        prun[1] = prun[1] * scale + r1;
       }
-#pragma unroll 1
-      for (int j = (half == 0 ? 2 : 0); j < 4; j += 2) {
+#pragma unroll
+      for (int j = 0; j < 4; j += 2) {
+        if (half == 0 && j == 0) continue;
         float ha[32], hb[32];
         uint32_t va[32], vb[32];
         tmem_ld32(tb + (uint32_t)(j * 32), va);
@@ -543,8 +545,8 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         for (int i = 0; i < 32; ++i) { ha[i] = __uint_as_float(va[i]) * w; hb[i] = __uint_as_float(vb[i]) * w; }
         float r0, r1;
         warp_transpose_sum2(ha, hb, r0, r1);
-        prun[j * 32 + lane] = prun[j * 32 + lane] * scale + r0;
-        prun[(j + 1) * 32 + lane] = prun[(j + 1) * 32 + lane] * scale + r1;
+        prun[j] = prun[j] * scale + r0;
+        prun[j + 1] = prun[j + 1] * scale + r1;
       }
       tc_fence_before();
       __syncwarp();
@@ -556,6 +558,8 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     float* red_m = s_part;                                  // [2]
     float* red_l = s_part + 2;                              // [2]
     named_bar_sync(1, 256);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p_acc[(warp - EPI_WARP0) * 128 + j * 32 + lane] = prun[j];   // every staged load was consumed: the ring is idle
     if (strip == 0 && lane == 0) { red_m[rg] = m_run; red_l[rg] = l_run; }
     named_bar_sync(1, 256);
     const float m_cta = fmaxf(red_m[0], red_m[1]);
@@ -662,7 +666,7 @@ static int launch_pair(const CUtensorMap& mx, const CUtensorMap& mw1, const CUte
 template <int ACT, int ATT>
 static int dispatch_prec(int precision, const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mwa, const FusedParams& p, int grid,
                          cudaStream_t stream) {
-  if (precision == MIL_PREC_BF16X3) return launch_pair<3, false, 3, 3, 1, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+  if (precision == MIL_PREC_BF16X3) return launch_pair<3, false, 3, 4, 1, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
   if (p.D % 64 == 0) {
     if (precision == MIL_PREC_FP16) return launch_pair<1, true, 3, 4, 2, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
     return launch_pair<1, false, 3, 4, 2, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
