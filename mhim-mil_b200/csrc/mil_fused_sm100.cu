@@ -315,7 +315,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
     uint32_t tl = 0;
 
     // per-column constants -> shared memory (broadcast reads in the hot loops)
-    for (int i = et; i < HMAX; i += 256) c_b1[i] = p.b1 ? p.b1[i] : 0.f;
+    for (int i = et; i < HMAX; i += 256) c_b1[i] = (p.b1 && i < p.nout) ? p.b1[i] : 0.f;   // the bias has nout entries (store mode: nout <= 512)
     if (MODE == MODE_FUSED) {
       for (int i = et; i < 128; i += 256) { c_ba[i] = p.ba ? p.ba[i] : 0.f; c_wc[i] = p.wc[i]; }
     } else {
