@@ -139,8 +139,8 @@ def main():
     model = DAttention(D_IN, N_CLASSES, dropout=0.0, act="relu").to(dev).eval()
     model.load_state_dict({k: v.to(dev) for k, v in cases.abmil_state(2021).items()}, strict=True)
     model.precision = args.precision
-    if args.pipeline == "auto":                    # the library's own default: pair for the 3-product parity mode, single otherwise
-        args.pipeline = "pair" if args.precision == "bf16x3" else "single"
+    if args.pipeline == "auto":                    # the library's own default
+        args.pipeline = "pair"
     os.environ["MHIMK_PIPELINE"] = {"single": "1", "pair": "2"}[args.pipeline]
     # 4 distinct bags (820 MB) visited round-robin: every step streams 205 MB that cannot be in the 126 MB L2
     n_bags = 4

@@ -35,7 +35,7 @@ enum {
   MIL_PREC_BF16   = 2  /* single bf16 product (fastest, ~2^-9 operand rounding) */
 };
 
-/* pipeline of the fused pass, OR-ed into `precision` as (pipeline << 8); 0 = library default */
+/* pipeline of the fused pass, OR-ed into `precision` as (pipeline << 8); 0 = library default (the pair pipeline) */
 enum {
   MIL_PIPE_DEFAULT = 0,
   MIL_PIPE_SINGLE  = 1, /* one CTA per 128-row tile (cta_group::1, M = 128): the accumulator fills TMEM, the epilogue of a tile

@@ -708,14 +708,13 @@ extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, 
                                        float* stats, float* pooled, const float* Wcls, const float* bcls, int n_cls, float* logits,
                                        void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  // bits 8..15 of `precision` select the pipeline: 0 = default (pair for the 3-product mode, single otherwise), MIL_PIPE_SINGLE,
-  // MIL_PIPE_PAIR; MHIMK_PIPELINE=1|2 overrides the default
+  // bits 8..15 of `precision` select the pipeline: 0 = default (pair), MIL_PIPE_SINGLE, MIL_PIPE_PAIR; MHIMK_PIPELINE=1|2 overrides the default
   int pipeline = (precision >> 8) & 0xFF;
   precision &= 0xFF;
   if (pipeline == 0) {
     const char* e = getenv("MHIMK_PIPELINE");
     pipeline = e ? atoi(e) : 0;
-    if (pipeline != 1 && pipeline != 2) pipeline = precision == MIL_PREC_BF16X3 ? 2 : 1;
+    if (pipeline != 1 && pipeline != 2) pipeline = 2;
   }
   MIL_CHECK_ARG(pipeline == 1 || pipeline == 2, "mil_abmil_fused_fwd_f32: bad pipeline %d", pipeline);
   MIL_CHECK_ARG(mil_device_supported(), "mil_abmil_fused_fwd_f32: needs a compute-capability 10.x device (tcgen05/TMEM/TMA)");

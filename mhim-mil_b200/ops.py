@@ -276,11 +276,11 @@ PIPELINES = {"single": 1, "pair": 2}
 
 def _pipeline(name, precision=None):
     """'single' (one CTA per 128-row tile) or 'pair' (two CTAs share every MMA, double-buffered TMEM accumulators, the epilogue
-    overlaps the next tile's GEMM1).  Default: 'pair' for the 3-product parity arithmetic (measured ~5 % faster), 'single' for the
-    1-product modes (on par); MHIMK_PIPELINE=1|2 overrides the default."""
+    overlaps the next tile's GEMM1).  Default: 'pair' (measured 5-7 % faster in the 3-product parity arithmetic, 3-4 % in the 1-product
+    modes); MHIMK_PIPELINE=1|2 overrides the default."""
     import os
     if name in (None, "auto"):
-        name = {"1": "single", "2": "pair"}.get(os.environ.get("MHIMK_PIPELINE", ""), "pair" if precision in (None, "bf16x3") else "single")
+        name = {"1": "single", "2": "pair"}.get(os.environ.get("MHIMK_PIPELINE", ""), "pair")
     if name not in PIPELINES:
         raise ValueError(f"mhimk: unknown fused pipeline {name!r}")
     return name
