@@ -44,3 +44,18 @@ def test_cpu_tensors_are_rejected_loudly():
     import mhimk
     with pytest.raises(RuntimeError, match="no CPU path"):
         mhimk.ops.linear_act(torch.zeros(4, 8), torch.zeros(2, 8), None, "relu")
+
+
+def test_fused_pipeline_selection(monkeypatch):
+    """Host logic of the pipeline switch (no GPU): default, environment override, explicit names, bad names."""
+    import mhimk
+    monkeypatch.delenv("MHIMK_PIPELINE", raising=False)
+    assert mhimk.ops._pipeline(None, "bf16x3") == "pair" and mhimk.ops._pipeline("auto", "fp16") == "pair"
+    monkeypatch.setenv("MHIMK_PIPELINE", "1")
+    assert mhimk.ops._pipeline(None, "bf16x3") == "single"
+    assert mhimk.ops._pipeline("pair", "bf16x3") == "pair"          # an explicit choice wins over the environment
+    with pytest.raises(ValueError):
+        mhimk.ops._pipeline("triple")
+    assert mhimk.ops.PIPELINES == {"single": 1, "pair": 2}          # = MIL_PIPE_SINGLE / MIL_PIPE_PAIR of include/mhimk.h
+    hdr = open(HEADER).read()
+    assert "MIL_PIPE_SINGLE  = 1" in hdr and "MIL_PIPE_PAIR    = 2" in hdr
