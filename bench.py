@@ -177,23 +177,37 @@ def main():
     mhimk.ops.profile_fused(False)
     kernel_ms = k_total / max(n_timed, 1)
 
-    # end to end through the public module call: pinned host bag -> H2D -> forward -> logits D2H, every step
+    # end to end through the public module call: pinned host bag -> H2D -> forward -> logits D2H, every step.  Two device buffers:
+    # the copy of bag i+1 (copy stream) overlaps the forward of bag i (compute stream); every step still moves its own 204.8 MB
+    # and reads its own logits back inside the timed region.
     host = [torch.randn(1, N_INST, D_IN).pin_memory() for _ in range(2)]
-    dbuf = torch.empty(1, N_INST, D_IN, device=dev)
-    hout = torch.empty(1, N_CLASSES).pin_memory()
+    dbufs = [torch.empty(1, N_INST, D_IN, device=dev) for _ in range(2)]
+    houts = [torch.empty(1, N_CLASSES).pin_memory() for _ in range(2)]
     e2e_steps = max(3, min(args.steps, 10))
-    for i in range(2):
-        dbuf.copy_(host[i % 2], non_blocking=True)
-        with torch.no_grad():
-            hout.copy_(model(dbuf), non_blocking=True)
+    copy_stream, main_stream = torch.cuda.Stream(device=dev), torch.cuda.current_stream(dev)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_loop(n):
+        for b in range(2):
+            consumed[b].record(main_stream)
+        for i in range(n):
+            b = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[b])            # the forward that read this buffer two steps ago is done
+                dbufs[b].copy_(host[b], non_blocking=True)
+                copied[b].record(copy_stream)
+            main_stream.wait_event(copied[b])
+            with torch.no_grad():
+                houts[b].copy_(model(dbufs[b]), non_blocking=True)
+            consumed[b].record(main_stream)
+
+    e2e_loop(2)
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for i in range(e2e_steps):
-        dbuf.copy_(host[i % 2], non_blocking=True)
-        with torch.no_grad():
-            hout.copy_(model(dbuf), non_blocking=True)
-    e3.record()
+    e2.record(main_stream)
+    e2e_loop(e2e_steps)
+    e3.record(main_stream)
     sync_all()
     sampler.stop_flag = True
     sampler.join(timeout=2)
