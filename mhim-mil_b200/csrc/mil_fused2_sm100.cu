@@ -6,9 +6,9 @@
 //   per CTA (rank r of the pair), per 128-row pair tile (its rows: tile * 128 + r * 64 .. + 64):
 //   HBM --TMA(SW128)--> fp32 staging [64 x 32] --converter warps--> 16-bit hi(/lo) A tiles (UMMA K-major SW64, 4 KB)
 //   L2  --TMA---------> W1 image tiles: this CTA's half (128 rows) of each 256-row N block; Wa image tiles (64 rows)
-//   leader CTA, one thread: tcgen05.mma.cta_group::2  pre[128 x 256] x 2 N blocks -> TMEM buffer (tile & 1)   (GEMM1)
+//   leader CTA, warp 13 (converged, one elected lane): tcgen05.mma.cta_group::2  pre[128 x 256] x 2 N blocks -> TMEM buffer (tile & 1)   (GEMM1)
 //   epilogue warps (both CTAs): h = act(pre + b1) -> 16-bit A2 tiles; h kept in TMEM / registers
-//   leader: tcgen05.mma.cta_group::2  u[128 x 128] = h Wa^T -> the first 64 columns of the same buffer          (GEMM2)
+//   leader CTA, warp 15: tcgen05.mma.cta_group::2  u[128 x 128] = h Wa^T -> the first 64 columns of the same buffer          (GEMM2)
 //   epilogue warps: s = wc . f(u + ba) + bc, online softmax over rows, p += e^{s-m} h (warp-shuffle transposes)
 //
 // TMEM layout of a pair MMA with M = 128 ("2x2", cute::UMMA::tmem_frg_2sm): rows 0..63 of the CTA on lanes 0..63 for
@@ -36,10 +36,10 @@ constexpr int G2S = 4;                        // GEMM2 A2 slots (one per epilogu
 constexpr int G2B_BUF = 16384;                // one Wa load group (GS chunks x NOP x 4 KB); two buffers
 
 constexpr int NUM_THREADS = 512;
-// Warp roles.  The SM's warp arbiter favours the highest warp id among eligible warps, and here the epilogue of tile t runs
-// concurrently with the operand pipeline of tile t+1: the short latency-critical loops (producers, MMA issue, converters) get the
-// high ids, the ALU-heavy epilogue warps the low ones.  (The other way round the control warps were starved of issue slots: ~1000
-// cycles per 64-wide stage with every TMA and MMA switched off.)
+// Warp roles.  The epilogue of tile t runs concurrently with the operand pipeline of tile t+1.  The short latency-critical loops
+// (producers, MMA issue, converters) have the high warp ids and the ALU-heavy epilogue warps the low ones because the SM's warp
+// arbiter is reported to favour the highest id among eligible warps; measured here the order made no difference (the control
+// loops are bound by their own issue latency, ~300-450 cycles per iteration, not by lost arbitration).
 constexpr int EPI_WARP0 = 0;                  // warps 0..7 epilogue
 constexpr int CONV_WARP0 = 8;                 // warps 8..11 converters
 constexpr int W_X = 12, W_MMA1 = 13, W_W1 = 14, W_MMA2 = 15;   // bag TMA; GEMM1 issue; TMEM alloc + W1 TMA; Wa TMA + GEMM2 issue
