@@ -143,6 +143,10 @@ int mil_pool_merge_f32(const float* part, int n_part, int H, float* stats, float
  * score_n = max_c softmax_c( a_n * t_{n,c} + bias0 ), a_n = exp(s_n - m)/l, t = h Wp^T given as float[L,C]. */
 int mil_cam_score_f32(const float* s, const float* t, int64_t L, int C, const float* stats, float bias0,
                       float* score, mil_stream_t stream);
+/* Same, with bias0 = bias_dev[0] read on the device (the predictor's bias parameter, scoring.py:54 `classifier bias[0]`):
+ * the caller needs no device->host read of the parameter, so the teacher pass enqueues without a host sync. */
+int mil_cam_score_dev_f32(const float* s, const float* t, int64_t L, int C, const float* stats, const float* bias_dev,
+                          float* score, mil_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Masked hard-instance selection.  Replaces torch.topk + the python-set complement of

@@ -339,9 +339,10 @@ __global__ void __launch_bounds__(256) softmax_pool_bwd_kernel(const float* __re
 }
 
 __global__ void cam_score_kernel(const float* __restrict__ s, const float* __restrict__ t, int64_t L, int C, const float* __restrict__ stats,
-                                 float bias0, float* __restrict__ score) {
+                                 float bias0, const float* __restrict__ bias_dev, float* __restrict__ score) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L) return;
+  if (bias_dev) bias0 = bias_dev[0];
   const float a = expf(s[i] - stats[0]) / stats[1];
   float mx = -INFINITY;
   for (int c = 0; c < C; ++c) mx = fmaxf(mx, fmaf(a, t[i * C + c], bias0));
@@ -468,7 +469,15 @@ extern "C" int mil_softmax_pool_bwd_f32(const float* s, int64_t s_stride, const 
 
 extern "C" int mil_cam_score_f32(const float* s, const float* t, int64_t L, int C, const float* stats, float bias0, float* score, mil_stream_t stream) {
   MIL_CHECK_ARG(s && t && stats && score && L > 0 && C > 0, "mil_cam_score_f32: bad arguments");
-  cam_score_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s, t, L, C, stats, bias0, score);
+  cam_score_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s, t, L, C, stats, bias0, nullptr, score);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mil_cam_score_dev_f32(const float* s, const float* t, int64_t L, int C, const float* stats, const float* bias_dev, float* score,
+                                     mil_stream_t stream) {
+  MIL_CHECK_ARG(s && t && stats && score && bias_dev && L > 0 && C > 0, "mil_cam_score_dev_f32: bad arguments");
+  cam_score_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s, t, L, C, stats, 0.f, bias_dev, score);
   MIL_LAUNCH_CHECK();
   return 0;
 }

@@ -114,7 +114,7 @@ def sharded_abmil_forward(model, x_local: torch.Tensor, group=None, want_scores:
     H = f0.out_features
     if x_local.shape[0] > 0:
         out = ops.abmil_fused_forward(x_local, f0.weight, f0.bias, model.act, a0.weight, a0.bias, a2.weight, a2.bias, "tanh",
-                                      want_scores=want_scores, precision=model.precision)
+                                      want_scores=want_scores, precision=model.precision, volatile=model.training)
         partial, s = make_partial(out["stats"], out["pooled"]), out["s"]
     else:
         partial, s = torch.zeros(2 + H, device=x_local.device), None

@@ -33,8 +33,20 @@ def grad_needed(module: nn.Module, *tensors) -> bool:
 
 
 def lin(layer: nn.Linear, x: torch.Tensor, act: str = "none") -> torch.Tensor:
-    """act(layer(x)) through the CUDA GEMM of libmhimk (x is [M, in])."""
-    return ops.linear_act(x, layer.weight, layer.bias, act)
+    """act(layer(x)) through the CUDA GEMM of libmhimk (x is [M, in]).  In train mode the cached weight image is not trusted
+    (`volatile`): the reference's EMA teacher update writes through `.data` (engines/base_engine.py:166-167), which autograd's
+    version counter does not see."""
+    return ops.linear_act(x, layer.weight, layer.bias, act, volatile=layer.training)
+
+
+class MilModule(nn.Module):
+    """Base of the drop-in modules.  Behaves exactly like nn.Module (no parameters, no state_dict keys, no hooks); it only tells
+    the weight-image caches of `ops` that a train()/eval() switch happened, so the first forward after the switch rebuilds its
+    images: the last `.data` update of a training epoch happens after the last train-mode forward."""
+
+    def train(self, mode: bool = True):
+        ops.weights_touched()
+        return super().train(mode)
 
 
 def require_cuda(x: torch.Tensor, who: str) -> None:

@@ -11,10 +11,10 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
-from ._common import act_module, grad_needed, init_linear_layers, lin, require_cuda
+from ._common import MilModule, act_module, grad_needed, init_linear_layers, lin, require_cuda
 
 
-class DAttention(nn.Module):
+class DAttention(MilModule):
     def __init__(self, input_dim, n_classes, dropout, act, mil_norm=None, mil_bias=True, mil_cls_bias=True, inner_dim=512,
                  embed_feat=True, embed_norm_pos=0, pos=None, **kwargs):
         super().__init__()
@@ -58,7 +58,7 @@ class DAttention(nn.Module):
             f0 = self.feature[0]
             out = ops.abmil_fused_forward(x2, f0.weight, f0.bias, self.act, att0.weight, att0.bias, att2.weight, att2.bias, "tanh",
                                           want_scores=return_attn, want_h=return_attn and return_act, precision=self.precision,
-                                          Wcls=self.classifier.weight, bcls=self.classifier.bias)
+                                          Wcls=self.classifier.weight, bcls=self.classifier.bias, volatile=self.training)
             pooled, fused_logits = out["pooled"], out["logits"]
             attn = torch.exp(out["s"] - out["stats"][0]) / out["stats"][1] if return_attn else None
             h = out["h"]
@@ -82,7 +82,7 @@ class DAttention(nn.Module):
         return logits
 
 
-class AttentionGated(nn.Module):
+class AttentionGated(MilModule):
     def __init__(self, input_dim, n_classes, act="relu", dropout=0.0, mil_norm=None, mil_bias=True, mil_cls_bias=True, inner_dim=512,
                  embed_feat=True, embed_norm_pos=0, pos=None, **kwargs):
         super().__init__()

@@ -10,7 +10,7 @@ from .. import ops
 from . import _common as C
 
 
-class BClassifier(nn.Module):
+class BClassifier(C.MilModule):
     def __init__(self, input_size, output_class, dropout_v=0.0, nonlinear=True, passing_v=True, bias=True, norm=False):
         super().__init__()
         self.q = (nn.Sequential(nn.Linear(input_size, 128, bias=bias), nn.ReLU(), nn.Linear(128, 128), nn.Tanh()) if nonlinear
@@ -45,7 +45,7 @@ class BClassifier(nn.Module):
         return pred, torch.stack(As, dim=1)[None], B
 
 
-class MILNet(nn.Module):
+class MILNet(C.MilModule):
     def __init__(self, n_classes, dropout, act, input_dim=1024, mil_norm=None, mil_bias=True, inner_dim=512, **kwargs):
         super().__init__()
         if mil_norm not in (None, "none"):

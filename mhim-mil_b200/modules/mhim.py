@@ -22,7 +22,7 @@ from .mhim_modules.merge import Merge
 from .mhim_modules.scoring import get_pseudo_score, get_pseudo_score_trans
 
 
-class MHIM(nn.Module):
+class MHIM(C.MilModule):
     def __init__(self, input_dim=1024, mlp_dim=512, mask_ratio=0, n_classes=2, temp_t=1.0, dropout=0.25, act="relu", mask_ratio_h=0.0,
                  mrh_sche=None, mask_ratio_hr=0.0, mask_ratio_l=0.0, da_act="gelu", baseline="selfattn", head=8, attn2score=True,
                  merge_enable=True, merge_k=1, merge_mm=0.9998, merge_ratio=0.0, merge_test=False):
@@ -72,7 +72,7 @@ class MHIM(nn.Module):
         return ops.abmil_fused_forward(x[0], f0.weight, f0.bias, self.act, att.attention[0].weight, None, att.attention[-1].weight, None,
                                        att.act, Wp=self.predictor.weight if with_pred else None, want_scores=want_scores, want_h=want_h,
                                        precision=self.precision, Wcls=self.predictor.weight if with_logits else None,
-                                       bcls=self.predictor.bias if with_logits else None)
+                                       bcls=self.predictor.bias if with_logits else None, volatile=self.training)
 
     # ------------------------------------------------------------------ masking
     def get_mask(self, ps, i, attn, mrh=None):
@@ -110,7 +110,7 @@ class MHIM(nn.Module):
         """-> (cls_feat, score) (mhim.py:181-227)"""
         if self._fusable(x) and not self.merge_test and self.attn2score:
             out = self._fused(x, want_scores=True, with_pred=True)
-            score = ops.cam_score(out["s"], out["t"], out["stats"], float(self.predictor.bias.data[0]))
+            score = ops.cam_score(out["s"], out["t"], out["stats"], self.predictor.bias)     # bias[0] read on the device: no host sync
             return out["pooled"][None], score[None]
         h = self._embed(x)
         p = h.size(1)

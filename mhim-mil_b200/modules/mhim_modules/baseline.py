@@ -20,7 +20,7 @@ def _act_name(act):
     return act if act in ("gelu", "relu", "tanh") else "none"
 
 
-class Attention(nn.Module):
+class Attention(C.MilModule):
     def __init__(self, input_dim=512, act="relu", bias=False, dropout=False):
         super().__init__()
         self.L, self.D, self.K = input_dim, 128, 1
@@ -46,7 +46,7 @@ class Attention(nn.Module):
         return pooled[None, None], (s if no_norm else attn)[None, None]
 
 
-class AttentionGated(nn.Module):
+class AttentionGated(C.MilModule):
     def __init__(self, input_dim=512, act="relu", bias=False, dropout=False):
         super().__init__()
         self.L, self.D, self.K = input_dim, 128, 1
@@ -69,7 +69,7 @@ class AttentionGated(nn.Module):
         return pooled[None, None], (s if no_norm else attn)[None, None]
 
 
-class DAttention(nn.Module):
+class DAttention(C.MilModule):
     def __init__(self, input_dim=512, act="relu", gated=False, bias=False, dropout=False):
         super().__init__()
         self.gated = gated
@@ -86,7 +86,7 @@ class DAttention(nn.Module):
         return pooled.squeeze(1)
 
 
-class BClassifier(nn.Module):
+class BClassifier(C.MilModule):
     def __init__(self, input_size, output_class, dropout_v=0.0, nonlinear=True, passing_v=True):
         super().__init__()
         self.q = (nn.Sequential(nn.Linear(input_size, 128), nn.ReLU(), nn.Linear(128, 128), nn.Tanh()) if nonlinear
@@ -120,7 +120,7 @@ class BClassifier(nn.Module):
         return pred, A, B
 
 
-class DSMIL(nn.Module):
+class DSMIL(C.MilModule):
     def __init__(self, n_classes=2, mask_ratio=0.0, mlp_dim=512, cls_attn=True, attn_index="max"):
         super().__init__()
         self.i_classifier = nn.Sequential(nn.Linear(mlp_dim, n_classes))
@@ -146,7 +146,7 @@ class DSMIL(nn.Module):
         return ([logits, inst], B, attn) if return_attn else ([logits, inst], B)
 
 
-class TransLayer(nn.Module):
+class TransLayer(C.MilModule):
     def __init__(self, norm_layer=nn.LayerNorm, dim=512, head=8):
         super().__init__()
         self.norm = norm_layer(dim)
@@ -159,7 +159,7 @@ class TransLayer(nn.Module):
         return x + self.attn(self.norm(x))
 
 
-class SAttention(nn.Module):
+class SAttention(C.MilModule):
     def __init__(self, mlp_dim=512, pos_pos=0, pos="ppeg", peg_k=7, head=8):
         super().__init__()
         self.norm = nn.LayerNorm(mlp_dim)

@@ -12,7 +12,7 @@ from .. import _common as C
 from .masking import select_mask_fn
 
 
-class MCA(nn.Module):
+class MCA(C.MilModule):
     def __init__(self, dim, heads=8, dim_head=64, dropout=0.0):
         super().__init__()
         inner = dim_head * heads
@@ -36,7 +36,7 @@ class MCA(nn.Module):
         return self.to_out[1](C.lin(self.to_out[0], out))[None]
 
 
-class Merge(nn.Module):
+class Merge(C.MilModule):
     def __init__(self, dim, heads=8, merge_h_dim=64, dropout=0.1, k=10, g_q_mm=1.0, merge_ratio=0.2, global_q_enable=True, no_merge=False,
                  g_q_grad=False, mask_type="random", **kwargs):
         super().__init__()

@@ -24,7 +24,7 @@ def moore_penrose_iter_pinv(x, iters=6):
     return z
 
 
-class NystromAttention(nn.Module):
+class NystromAttention(C.MilModule):
     def __init__(self, dim, dim_head=64, heads=8, num_landmarks=256, pinv_iterations=6, residual=True, residual_conv_kernel=33, eps=1e-8,
                  dropout=0.0):
         super().__init__()

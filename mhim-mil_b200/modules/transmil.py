@@ -8,7 +8,7 @@ from . import _common as C
 from .nystrom_attention import NystromAttention
 
 
-class TransLayer(nn.Module):
+class TransLayer(C.MilModule):
     def __init__(self, norm_layer=nn.LayerNorm, dim=512, n_heads=8):
         super().__init__()
         self.norm = norm_layer(dim)
@@ -22,7 +22,7 @@ class TransLayer(nn.Module):
         return x + self.attn(self.norm(x))
 
 
-class PPEG(nn.Module):
+class PPEG(C.MilModule):
     def __init__(self, dim=512):
         super().__init__()
         self.proj = nn.Conv2d(dim, dim, 7, 1, 7 // 2, groups=dim)
@@ -49,7 +49,7 @@ def _init_transmil(module):
                 nn.init.zeros_(m.bias)
 
 
-class TransMIL(nn.Module):
+class TransMIL(C.MilModule):
     def __init__(self, input_dim, n_classes, dropout, act, mil_norm=None, mil_bias=True, inner_dim=512, embed_feat=True, pos="ppeg", n_heads=8,
                  **kwargs):
         super().__init__()

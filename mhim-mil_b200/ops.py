@@ -60,27 +60,75 @@ def _tc_supported(M, N, K, W):
             and _lib.lib().mil_device_supported())
 
 
-def _tc_block(x, Wb, bb, act, pre_b, y_b, key_obj, blk, precision):
+def _drop_dead(cache, limit):
+    """Forget the entries whose owner tensor is gone (their workspaces would otherwise pin HBM until the cache is cleared)."""
+    dead = [k for k, v in cache.items() if v[0]() is None]
+    for k in dead:
+        del cache[k]
+    if len(cache) > limit:
+        cache.clear()
+
+
+# Validity of the cached 16-bit weight images.  An image is reused only while (a) the weight is the very same live tensor at the
+# same address and shape, (b) its autograd version counter is unchanged (optimizer.step / load_state_dict / copy_ bump it), (c) no
+# one has called weights_touched() since, and (d) the caller does not say `volatile`.  (d) exists because writes through `.data` --
+# the reference's EMA teacher update, engines/base_engine.py:166-167 -- do NOT bump the version counter: the drop-in modules pass
+# volatile=self.training, so in train mode every forward rebuilds its images (a few microseconds into the same buffer), and
+# MilModule.train()/eval() call weights_touched() so that the first eval-mode forward after training rebuilds once.
+_EPOCH = 0
+
+
+def weights_touched() -> None:
+    """Declare that weights may have been modified behind autograd's back (e.g. through `.data` while in eval mode):
+    every cached weight image is rebuilt at its next use."""
+    global _EPOCH
+    _EPOCH += 1
+
+
+# W^T copies for the tensor-core dX (the NT kernel wants [K, N] rows).  One persistent buffer per live weight: refreshed in place
+# (copy_ bumps the buffer's version, which in turn refreshes the image _tc_block keys on it).
+_WT_CACHE = {}
+
+
+def _transposed(W, volatile=False):
+    import weakref
+    ver = (W._version, _EPOCH)
+    hit = _WT_CACHE.get(id(W))
+    if hit is not None and hit[0]() is W and hit[2].shape == (W.shape[1], W.shape[0]) and hit[2].device == W.device:
+        if volatile or hit[1] != ver:
+            hit[2].copy_(W.detach().t())
+            _WT_CACHE[id(W)] = (hit[0], ver, hit[2])
+        return hit[2]
+    Wt = W.detach().t().contiguous()
+    _drop_dead(_WT_CACHE, 256)
+    _WT_CACHE[id(W)] = (weakref.ref(W), ver, Wt)
+    return Wt
+
+
+def _tc_block(x, Wb, bb, act, pre_b, y_b, key_obj, blk, precision, volatile=False):
     """One column block (<= 512 wide, contiguous rows of the weight) through mil_linear_act_tc_f32."""
     import weakref
     L = _lib.lib()
     M, K = x.shape
     N = Wb.shape[0]
     key = (id(key_obj), blk, N, precision)
-    ver = (key_obj._version, key_obj.data_ptr(), tuple(key_obj.shape))
+    ver = (key_obj._version, _EPOCH)
+    where = (key_obj.data_ptr(), tuple(key_obj.shape))
     hit = _TC_CACHE.get(key)
-    if hit is not None and hit[0]() is key_obj and hit[1] == ver:
-        ws, ready = hit[2], 1
+    if hit is not None and hit[0]() is key_obj and hit[3] == where:
+        ws = hit[2]                                   # same live weight: keep the buffer, rebuild the image in place if stale
+        ready = 0 if (volatile or hit[1] != ver) else 1
+        if not ready:
+            _TC_CACHE[key] = (hit[0], ver, ws, where)
     else:
         ws, ready = _ws(L.mil_linear_tc_workspace_bytes(N, K), x.device), 0
-        if len(_TC_CACHE) > 256:
-            _TC_CACHE.clear()
-        _TC_CACHE[key] = (weakref.ref(key_obj), ver, ws)
+        _drop_dead(_TC_CACHE, 256)
+        _TC_CACHE[key] = (weakref.ref(key_obj), ver, ws, where)
     check(L.mil_linear_act_tc_f32(ptr(x), M, K, ptr(Wb), ptr(bb), N, ACT[act], ptr(pre_b), ptr(y_b), ptr(ws), ws.numel(), ready,
                                   PREC[precision], stream_ptr()), "mil_linear_act_tc_f32")
 
 
-def linear_forward(x, W, b, act, pre=None, precision=None):
+def linear_forward(x, W, b, act, pre=None, precision=None, volatile=False):
     """y = act(x W^T + b): tcgen05 path when the shape allows (column blocks of <= 512), else the fp32 CUDA-core GEMM."""
     M, K = x.shape
     N = W.shape[0]
@@ -94,14 +142,14 @@ def linear_forward(x, W, b, act, pre=None, precision=None):
         left -= wdt
     if len(widths) == 1:
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
-        _tc_block(x, W, b, act, pre, y, W, 0, precision)
+        _tc_block(x, W, b, act, pre, y, W, 0, precision, volatile)
         return y
     ys, o = [], 0
     pres = []
     for i, wdt in enumerate(widths):
         y_b = torch.empty((M, wdt), dtype=torch.float32, device=x.device)
         p_b = torch.empty((M, wdt), dtype=torch.float32, device=x.device) if pre is not None else None
-        _tc_block(x, W[o:o + wdt], None if b is None else b[o:o + wdt], act, p_b, y_b, W, i, precision)
+        _tc_block(x, W[o:o + wdt], None if b is None else b[o:o + wdt], act, p_b, y_b, W, i, precision, volatile)
         ys.append(y_b)
         pres.append(p_b)
         o += wdt
@@ -112,15 +160,16 @@ def linear_forward(x, W, b, act, pre=None, precision=None):
 
 class _LinearAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, W, b, act):
+    def forward(ctx, x, W, b, act, volatile=False):
         x, W = _need(x, "x"), _need(W, "weight")
         b = _need(b, "bias") if b is not None else None
         M, K = x.shape
         N = W.shape[0]
         need_pre = act == "gelu" and (x.requires_grad or W.requires_grad)
         pre = torch.empty((M, N), dtype=torch.float32, device=x.device) if need_pre else None
-        y = linear_forward(x, W, b, act, pre)
+        y = linear_forward(x, W, b, act, pre, volatile=volatile)
         ctx.act = act
+        ctx.volatile = volatile
         ctx.has_bias = b is not None
         ctx.save_for_backward(x, W, pre if need_pre else y)
         return y
@@ -149,15 +198,17 @@ class _LinearAct(torch.autograd.Function):
             # gx[m,k] = sum_n g_pre[m,n] W[n,k].  With W^T materialised ([K,N], a few hundred KB) this is the NT form again and
             # runs on the tensor cores; otherwise A(m,n) = g_pre[m*N + n], B(k,n) = W[n*K + k] on the CUDA cores.
             if _tc_supported(M, K, N, W) and N % 32 == 0 and K % 64 == 0:
-                gx = linear_forward(g_pre.contiguous(), W.t().contiguous(), None, "none")
+                gx = linear_forward(g_pre.contiguous(), _transposed(W, ctx.volatile), None, "none")
             else:
                 gx = sgemm(g_pre, N, 1, W, 1, K, M, K, N)
-        return gx, gW, gb, None
+        return gx, gW, gb, None, None
 
 
-def linear_act(x: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor] = None, act: str = "none") -> torch.Tensor:
-    """act(x @ W.T + b) for x [M,K]; differentiable (CUDA backward)."""
-    return _LinearAct.apply(x, W, b, act)
+def linear_act(x: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor] = None, act: str = "none",
+               volatile: bool = False) -> torch.Tensor:
+    """act(x @ W.T + b) for x [M,K]; differentiable (CUDA backward).  volatile=True: do not trust a cached weight image
+    (see weights_touched)."""
+    return _LinearAct.apply(x, W, b, act, volatile)
 
 
 def linear_act_rows(x, W, b, act, row_ids):
@@ -225,13 +276,18 @@ def pool_merge(part: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return stats, pooled
 
 
-def cam_score(s, t, stats, bias0: float):
-    """score_n = max_c softmax_c(a_n t_nc + bias0) with a_n = exp(s_n - m)/l  (scoring.py:49-58)."""
+def cam_score(s, t, stats, bias0):
+    """score_n = max_c softmax_c(a_n t_nc + bias0) with a_n = exp(s_n - m)/l  (scoring.py:49-58).
+    bias0: a python float, or a CUDA fp32 tensor whose first element is read on the device (no host sync)."""
     L = _lib.lib()
     s, t = _need(s, "s"), _need(t, "t")
     n, C = t.shape
     out = torch.empty(n, dtype=torch.float32, device=s.device)
-    check(L.mil_cam_score_f32(ptr(s), ptr(t), n, C, ptr(stats), c_float(bias0), ptr(out), stream_ptr()), "mil_cam_score_f32")
+    if isinstance(bias0, torch.Tensor):
+        b = _need(bias0.detach().reshape(-1), "bias0")
+        check(L.mil_cam_score_dev_f32(ptr(s), ptr(t), n, C, ptr(stats), ptr(b), ptr(out), stream_ptr()), "mil_cam_score_dev_f32")
+    else:
+        check(L.mil_cam_score_f32(ptr(s), ptr(t), n, C, ptr(stats), c_float(bias0), ptr(out), stream_ptr()), "mil_cam_score_f32")
     return out
 
 
@@ -286,24 +342,29 @@ def _pipeline(name, precision=None):
     return name
 
 
-def _fused_workspace(W1, Wa, precision, pipeline="pair"):
+def _fused_workspace(W1, Wa, precision, pipeline="pair", volatile=False):
+    """(workspace, ready): the caller-owned buffer holding the 16-bit images of W1 / Wa, and whether the kernel may use them as
+    they are (1) or must rebuild them first (0)."""
     import weakref
     L = _lib.lib()
     key = (id(W1), id(Wa), precision, pipeline)
-    ver = (W1._version, Wa._version, W1.data_ptr(), Wa.data_ptr(), tuple(W1.shape), tuple(Wa.shape))
+    ver = (W1._version, Wa._version, _EPOCH)
+    where = (W1.data_ptr(), Wa.data_ptr(), tuple(W1.shape), tuple(Wa.shape))
     hit = _WS_CACHE.get(key)
-    if hit is not None and hit[0]() is W1 and hit[1]() is Wa and hit[2] == ver:
-        return hit[3], 1
+    if hit is not None and hit[0]() is W1 and hit[1]() is Wa and hit[4] == where:
+        ready = 0 if (volatile or hit[2] != ver) else 1
+        if not ready:
+            _WS_CACHE[key] = (hit[0], hit[1], ver, hit[3], where)
+        return hit[3], ready
     ws = _ws(L.mil_fused_workspace_bytes(W1.shape[1], W1.shape[0], Wa.shape[0], 0), W1.device)
-    if len(_WS_CACHE) > 64:
-        _WS_CACHE.clear()
-    _WS_CACHE[key] = (weakref.ref(W1), weakref.ref(Wa), ver, ws)
+    _drop_dead(_WS_CACHE, 64)
+    _WS_CACHE[key] = (weakref.ref(W1), weakref.ref(Wa), ver, ws, where)
     return ws, 0
 
 
 @torch.no_grad()
 def abmil_fused_forward(x, W1, b1, act, Wa, ba, wc, bc, att_act="tanh", keep=None, Wp=None, want_scores=False, want_h=False,
-                        precision: str = DEFAULT_PRECISION, Wcls=None, bcls=None, pipeline=None):
+                        precision: str = DEFAULT_PRECISION, Wcls=None, bcls=None, pipeline=None, volatile: bool = False):
     """One streaming pass over x [N,D]: returns dict(pooled[H], stats[2] = (m, l), s[N]?, t[N,C]?, h[N,H]?, part).
 
     h = act(x W1^T + b1); s = wc . att_act(Wa h + ba) + bc; pooled = softmax_N(s) @ h; logits = Wcls pooled + bcls when a
@@ -325,7 +386,7 @@ def abmil_fused_forward(x, W1, b1, act, Wa, ba, wc, bc, att_act="tanh", keep=Non
     ncls = Wcls.shape[0] if Wcls is not None else 0
     logits = torch.empty((1, ncls), dtype=torch.float32, device=dev) if Wcls is not None else None
     pipeline = _pipeline(pipeline, precision)
-    ws, ready = _fused_workspace(W1, Wa, precision, pipeline)
+    ws, ready = _fused_workspace(W1, Wa, precision, pipeline, volatile)
     check(L.mil_abmil_fused_fwd_f32(ptr(x), N, D, H, ptr(W1), ptr(b1), ACT[act], ptr(Wa), ptr(ba), None, None, Da, ACT[att_act], ptr(wc),
                                     ptr(bc), ptr(keep), ptr(Wp), C, ptr(s), ptr(t), ptr(h), ptr(part), ptr(stats), ptr(pooled),
                                     ptr(Wcls), ptr(bcls), ncls, ptr(logits), ptr(ws), ws.numel(), ready, PREC[precision] | (PIPELINES[pipeline] << 8),

@@ -59,3 +59,54 @@ def test_fused_pipeline_selection(monkeypatch):
     assert mhimk.ops.PIPELINES == {"single": 1, "pair": 2}          # = MIL_PIPE_SINGLE / MIL_PIPE_PAIR of include/mhimk.h
     hdr = open(HEADER).read()
     assert "MIL_PIPE_SINGLE  = 1" in hdr and "MIL_PIPE_PAIR    = 2" in hdr
+
+
+def test_weight_image_cache_policy(monkeypatch):
+    """Host logic of the cached 16-bit weight images (no GPU): reuse while the weight is the same live tensor with an unchanged
+    version counter; rebuild IN THE SAME BUFFER after an optimizer-style in-place update, when the caller says `volatile`
+    (train mode), and after weights_touched() / a train()-eval() switch.  A write through `.data` -- the reference's EMA update,
+    engines/base_engine.py:166-167 -- does not bump the version counter, which is why the last three exist."""
+    import gc
+    import torch
+    import mhimk
+    from mhimk import ops
+    from mhimk.modules._common import MilModule
+
+    class FakeLib:
+        def mil_fused_workspace_bytes(self, *a):
+            return 64
+
+    monkeypatch.setattr(ops, "_ws", lambda nbytes, device: torch.empty(max(int(nbytes), 16), dtype=torch.uint8))
+    monkeypatch.setattr(ops._lib, "lib", lambda: FakeLib())
+    W1, Wa = torch.nn.Parameter(torch.randn(8, 4)), torch.nn.Parameter(torch.randn(2, 8))
+    ws, ready = ops._fused_workspace(W1, Wa, "bf16x3", "pair")
+    assert ready == 0
+    ws2, ready = ops._fused_workspace(W1, Wa, "bf16x3", "pair")
+    assert ready == 1 and ws2 is ws
+    ws3, ready = ops._fused_workspace(W1, Wa, "bf16x3", "pair", volatile=True)
+    assert ready == 0 and ws3 is ws
+    assert ops._fused_workspace(W1, Wa, "bf16x3", "pair")[1] == 1
+    W1.data.mul_(0.5)                                               # invisible to the version counter ...
+    assert ops._fused_workspace(W1, Wa, "bf16x3", "pair")[1] == 1
+    ops.weights_touched()                                           # ... hence the explicit notification
+    assert ops._fused_workspace(W1, Wa, "bf16x3", "pair")[1] == 0
+    assert ops._fused_workspace(W1, Wa, "bf16x3", "pair")[1] == 1
+    MilModule().eval()                                              # a train()/eval() switch is such a notification
+    assert ops._fused_workspace(W1, Wa, "bf16x3", "pair")[1] == 0
+    with torch.no_grad():
+        W1.mul_(2)                                                  # what optimizer.step() / load_state_dict do
+    ws4, ready = ops._fused_workspace(W1, Wa, "bf16x3", "pair")
+    assert ready == 0 and ws4 is ws                                 # rebuilt in place, no new allocation per step
+    # W^T copy for the tensor-core dX: one persistent buffer per live weight, refreshed in place
+    Wt = ops._transposed(W1)
+    assert torch.equal(Wt, W1.detach().t())
+    v = Wt._version
+    assert ops._transposed(W1) is Wt and Wt._version == v
+    W1.data.mul_(3.0)
+    assert ops._transposed(W1, volatile=True) is Wt and Wt._version > v and torch.equal(Wt, W1.detach().t())
+    n_ws, n_wt = len(ops._WS_CACHE), len(ops._WT_CACHE)
+    del W1, Wa
+    gc.collect()
+    ops._drop_dead(ops._WS_CACHE, 64)
+    ops._drop_dead(ops._WT_CACHE, 256)
+    assert len(ops._WS_CACHE) == n_ws - 1 and len(ops._WT_CACHE) == n_wt - 1      # dead owners release their buffers

@@ -208,3 +208,57 @@ def test_fused_refuses_stale_weight_images(M):
         sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     assert cases.rel_err(b, O.abmil_dattention(sd, x.cpu(), "relu")) < TOL
     assert cases.rel_err(a, b) > 1e-3
+
+
+def _ema_through_data(student, teacher, mm):
+    """The reference's teacher update, verbatim in effect (engines/base_engine.py:166-167): in-place writes through `.data`,
+    which autograd's version counter does not see."""
+    for param_q, param_k in zip(student.parameters(), teacher.parameters()):
+        param_k.data.mul_(mm).add_(param_q.data, alpha=1. - mm)
+
+
+@pytest.mark.parametrize("base", ["attn", "dsmil"])
+def test_teacher_follows_ema_updates_written_through_data(M, base):
+    """Cached 16-bit weight images must not survive the EMA update: train-mode forwards rebuild them, and the train->eval switch
+    invalidates them (the last EMA update of an epoch comes after the last train-mode forward)."""
+    _, n, d, seed = MHIM_CASES["attn_2000" if base == "attn" else "dsmil_1000"]
+    cfg = O.MHIMConfig(**dict(cases.MHIM_KW, baseline=base, input_dim=d))
+    stu, tea = build_mhim(M, base, d, seed).train(), build_mhim(M, base, d, seed + 1).train()
+    x = cases.make_bag(seed + 1000, n, d).cuda()
+
+    def oracle_teacher():
+        sd = {k: v.detach().cpu() for k, v in tea.state_dict().items()}
+        with torch.no_grad():
+            return O.mhim_forward_teacher(cfg, sd, x.cpu()), O.mhim_forward_test(cfg, sd, x.cpu())
+
+    before, _ = tea.forward_teacher(x)
+    before = before.clone()
+    _ema_through_data(stu, tea, 0.5)                                   # a large step so that stale images would be far off
+    (cls_ref, score_ref), _ = oracle_teacher()
+    cls_tea, score = tea.forward_teacher(x)                            # train mode: images rebuilt
+    assert cases.rel_err(cls_tea, cls_ref) < TOL and cases.rel_err(score, score_ref) < TOL
+    assert cases.rel_err(before, cls_ref) > 1e-2
+    _ema_through_data(stu, tea, 0.5)                                   # the epoch's last update, then validation with the teacher
+    _, test_ref = oracle_teacher()
+    tea.eval()
+    got = tea.forward_test(x)
+    if base == "dsmil":
+        for a, b in zip(got[0], test_ref[0]):
+            assert cases.rel_err(a, b) < TOL
+    else:
+        assert cases.rel_err(got, test_ref) < TOL
+
+
+def test_eval_mode_data_write_needs_weights_touched(M):
+    """In eval mode the images are cached across calls (the headline path); a write through `.data` there is invisible until
+    ops.weights_touched() (documented in INTEGRATION.md)."""
+    import mhimk
+    m = M.DAttention(1024, 2, dropout=0.0, act="relu").cuda().eval()
+    x = cases.make_bag(3, 300, 1024).cuda()
+    with torch.no_grad():
+        m(x)
+        m.feature[0].weight.data.mul_(0.5)
+        mhimk.ops.weights_touched()
+        b = m(x)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    assert cases.rel_err(b, O.abmil_dattention(sd, x.cpu(), "relu")) < TOL

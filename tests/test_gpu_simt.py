@@ -161,3 +161,5 @@ def test_cam_score(K):
     stats = torch.stack([m, torch.exp(s - m).sum()])
     got = K.cam_score(dev(s), dev(h @ Wp.t()), dev(stats), float(bp[0]))
     assert cases.rel_err(got, ref) < 1e-6
+    got_dev = K.cam_score(dev(s), dev(h @ Wp.t()), dev(stats), dev(bp))      # bias read on the device (no host sync): same bits
+    assert torch.equal(got_dev, got)
