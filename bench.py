@@ -251,7 +251,7 @@ def main():
                "gpu_launches": args.steps,                # per step: ONE fused kernel (merge + classifier in its tail; weight images cached)
                "clocks": sampler.summary()}
         if not args.no_cpu_baseline:
-            n_cpu = 60                                     # bounded sample: ~3-5 s of CPU work on the box's host cores
+            n_cpu = 250                                    # bounded sample: ~10 s of CPU work on the box's host cores
             med = time_cpu(n_cpu, N_INST)
             out["cpu_baseline"] = {"value": N_INST / med, "unit": "instances/s", "cores": os.cpu_count(), "kind": "port",
                                    "sample": f"{n_cpu} full bags of N={N_INST} (median {med * 1e3:.1f} ms), oracle port of abmil.DAttention.forward, torch CPU fp32, all host threads"}
