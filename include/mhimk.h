@@ -163,6 +163,15 @@ int    mil_mask_from_indices(const int64_t* idx, int64_t k, int64_t N, int64_t* 
                              int64_t* len_keep_out, void* ws, size_t ws_bytes, mil_stream_t stream);
 size_t mil_topk_workspace_bytes(int64_t N);
 
+/* ---------------------------------------------------------------------------------------------
+ * EMA teacher update as ONE launch over all parameters.  Replaces the per-parameter loop
+ * `param_k.data.mul_(mm).add_(param_q.data, alpha=1 - mm)` of engines/base_engine.py:166-167 (and :488-489).
+ * segs_dev: device array of n_seg records; the caller cuts every parameter into segments of a few 10^4 elements (one CTA
+ * each).  dst <- fma(one_minus_mm, src, dst * mm), i.e. the same two roundings as the reference's mul_ + add_(alpha).
+ * mm outside [0, 1] is an argument error (the reference asserts the same, base_engine.py:164). */
+typedef struct { float* dst; const float* src; int64_t n; } mil_ema_seg_t;
+int mil_ema_update_f32(const mil_ema_seg_t* segs_dev, int n_seg, float mm, float one_minus_mm, mil_stream_t stream);
+
 /* Self-test hook for the tcgen05/TMA plumbing: C[M,N] = A[M,K] B[N,K]^T with the fused pass's operand pipeline
  * (fp32 in HBM -> TMA -> bf16/fp16 split in shared memory -> tcgen05.mma -> TMEM -> registers).  M % 128 == 0,
  * N in {64,128,256,512}, K % 32 == 0.  Used by tests/ only. */

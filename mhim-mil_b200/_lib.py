@@ -41,6 +41,7 @@ _SIGS = {
     "mil_pool_merge_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mil_cam_score_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_float, c_void_p, c_void_p]),
     "mil_cam_score_dev_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mil_ema_update_f32": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p]),
     "mil_topk_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mil_mask_from_indices": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mil_topk_workspace_bytes": (c_size_t, [c_int64]),

@@ -351,6 +351,32 @@ __global__ void cam_score_kernel(const float* __restrict__ s, const float* __res
   score[i] = 1.f / den;     // max_c softmax_c = exp(0) / den
 }
 
+// Multi-tensor EMA: block b owns segment b (<= a few 10^4 elements of one parameter).  k = fma(1 - mm, q, k * mm) -- the two roundings of
+// `param_k.mul_(mm).add_(param_q, alpha=1 - mm)`: the product k * mm is rounded on its own, alpha * q + that is fused.
+__global__ void ema_update_kernel(const mil_ema_seg_t* __restrict__ segs, float mm, float alpha) {
+  const mil_ema_seg_t sg = segs[blockIdx.x];
+  float* __restrict__ k = sg.dst;
+  const float* __restrict__ q = sg.src;
+  const int64_t n = sg.n;
+  if ((((uintptr_t)k | (uintptr_t)q) & 15) == 0) {
+    const int64_t n4 = n >> 2;
+    float4* k4 = reinterpret_cast<float4*>(k);
+    const float4* q4 = reinterpret_cast<const float4*>(q);
+    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 a = k4[i];
+      const float4 b = q4[i];
+      a.x = fmaf(alpha, b.x, __fmul_rn(a.x, mm));
+      a.y = fmaf(alpha, b.y, __fmul_rn(a.y, mm));
+      a.z = fmaf(alpha, b.z, __fmul_rn(a.z, mm));
+      a.w = fmaf(alpha, b.w, __fmul_rn(a.w, mm));
+      k4[i] = a;
+    }
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) k[i] = fmaf(alpha, q[i], __fmul_rn(k[i], mm));
+  } else {
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) k[i] = fmaf(alpha, q[i], __fmul_rn(k[i], mm));
+  }
+}
+
 }  // namespace mil
 
 using namespace mil;
@@ -478,6 +504,15 @@ extern "C" int mil_cam_score_dev_f32(const float* s, const float* t, int64_t L, 
                                      mil_stream_t stream) {
   MIL_CHECK_ARG(s && t && stats && score && bias_dev && L > 0 && C > 0, "mil_cam_score_dev_f32: bad arguments");
   cam_score_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s, t, L, C, stats, 0.f, bias_dev, score);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mil_ema_update_f32(const mil_ema_seg_t* segs_dev, int n_seg, float mm, float one_minus_mm, mil_stream_t stream) {
+  MIL_CHECK_ARG(n_seg >= 0 && (segs_dev || n_seg == 0), "mil_ema_update_f32: bad segment table");
+  MIL_CHECK_ARG(mm >= 0.f && mm <= 1.f, "mil_ema_update_f32: momentum %f outside [0, 1]", (double)mm);
+  if (n_seg == 0) return 0;
+  ema_update_kernel<<<(unsigned)n_seg, 256, 0, (cudaStream_t)stream>>>(segs_dev, mm, one_minus_mm);
   MIL_LAUNCH_CHECK();
   return 0;
 }

@@ -651,3 +651,24 @@ def abmil_backward_analytic(x: Tensor, W1: Tensor, b1: Tensor, Wa: Tensor, ba: O
         out["Wb"] = g_v.t() @ h
         out["bb"] = g_v.sum(0)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# f-1 : EMA teacher update
+# ----------------------------------------------------------------------------------------------
+def ema_update(params_q, params_k, mm: float):
+    """engines/base_engine.py:155-167 (:478-489 for survival): `param_k.data.mul_(mm).add_(param_q.data, alpha=1. - mm)` over
+    `zip(model.parameters(), model_ema.parameters())`.  Returns the new teacher tensors (inputs untouched).
+
+    Arithmetic as torch executes it on fp32 tensors: the python doubles `mm` and `1 - mm` are each rounded to fp32; `k * mm` is
+    rounded to fp32; `alpha * q + that` is one fused multiply-add (checked bit for bit against the literal loop in
+    tests/test_oracle_golden.py)."""
+    import numpy as np
+    assert 0.0 <= mm <= 1.0, "Momentum needs to be between 0.0 and 1.0, got %.5f" % mm          # base_engine.py:164
+    mm32, alpha32 = np.float32(mm), np.float32(1.0 - mm)
+    out = []
+    for q, k in zip(params_q, params_k):
+        k1 = (k.detach().cpu().numpy() * mm32).astype(np.float32)
+        fused = k1.astype(np.float64) + np.float64(alpha32) * q.detach().cpu().numpy().astype(np.float64)   # exact product, one rounding
+        out.append(torch.from_numpy(fused.astype(np.float32)).reshape(k.shape))
+    return out

@@ -46,6 +46,15 @@ def test_cpu_tensors_are_rejected_loudly():
         mhimk.ops.linear_act(torch.zeros(4, 8), torch.zeros(2, 8), None, "relu")
 
 
+def test_ema_update_rejects_cpu_models_loudly():
+    import torch
+    from mhimk.engines import ema_update
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ema_update(torch.nn.Linear(2, 2), torch.nn.Linear(2, 2), 0.5)
+    with pytest.raises(AssertionError, match="Momentum"):
+        ema_update(torch.nn.Linear(2, 2), torch.nn.Linear(2, 2), -0.1)
+
+
 def test_fused_pipeline_selection(monkeypatch):
     """Host logic of the pipeline switch (no GPU): default, environment override, explicit names, bad names."""
     import mhimk

@@ -262,3 +262,51 @@ def test_eval_mode_data_write_needs_weights_touched(M):
         b = m(x)
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     assert cases.rel_err(b, O.abmil_dattention(sd, x.cpu(), "relu")) < TOL
+
+
+def same_fma_result(got, want):
+    """Bit-equal, except that the oracle's fused multiply-add goes through a double (two roundings): allow a couple of 1-ulp cases."""
+    return int((got != want).sum()) <= 2 and torch.allclose(got, want, rtol=2.5e-7, atol=1e-37)
+
+
+@pytest.mark.parametrize("mm", [0.9999, 0.5])
+def test_ema_update_one_launch(M, mm):
+    """mhimk.engines.ema_update == the reference's per-parameter loop (oracle, bit for bit), and the teacher's next forward sees
+    the new weights even in eval mode (the helper notifies the weight-image caches)."""
+    from mhimk.engines import ema_update
+    _, n, d, seed = MHIM_CASES["attn_2000"]
+    stu, tea = build_mhim(M, "attn", d, seed), build_mhim(M, "attn", d, seed + 1).eval()
+    x = cases.make_bag(seed + 1000, n, d).cuda()
+    tea.forward_test(x)                                                  # fills the image cache with the old weights
+    want = O.ema_update(list(stu.parameters()), list(tea.parameters()), mm)
+    ema_update(stu, tea, mm)
+    for p, w in zip(tea.parameters(), want):
+        assert same_fma_result(p.detach().cpu(), w)
+    cfg = O.MHIMConfig(**dict(cases.MHIM_KW, baseline="attn", input_dim=d))
+    sd = {k: v.detach().cpu() for k, v in tea.state_dict().items()}
+    with torch.no_grad():
+        ref = O.mhim_forward_test(cfg, sd, x.cpu())
+    assert cases.rel_err(tea.forward_test(x), ref) < TOL
+    with pytest.raises(AssertionError):
+        ema_update(stu, tea, 1.5)
+
+
+def test_ema_update_odd_sizes_and_alignment(M):
+    """Segments that are not multiples of 4 elements or not 16-byte aligned take the scalar path; > 32768 elements span CTAs."""
+    from mhimk.engines import ema_update
+
+    class Bag(torch.nn.Module):
+        def __init__(self, seed):
+            super().__init__()
+            g = torch.Generator().manual_seed(seed)
+            self.a = torch.nn.Parameter(torch.randn(70001, generator=g))
+            self.b = torch.nn.Parameter(torch.randn(3, generator=g))
+            self.c = torch.nn.Parameter(torch.randn(1, generator=g))
+            self.d = torch.nn.Parameter(torch.randn(257, 129, generator=g))
+
+    q, k = Bag(1).cuda(), Bag(2).cuda()
+    k.a.data = torch.randn(70002, generator=torch.Generator().manual_seed(3)).cuda()[1:]      # 4-byte aligned only
+    want = O.ema_update(list(q.parameters()), list(k.parameters()), 0.99)
+    ema_update(q, k, 0.99)
+    for p, w in zip(k.parameters(), want):
+        assert same_fma_result(p.detach().cpu(), w)

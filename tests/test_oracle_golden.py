@@ -174,3 +174,19 @@ def test_shard_merge_is_associative():
             o += c
         _, _, p = O.merge_partials(*zip(*parts))
         assert cases.rel_err(p, p_ref) < 1e-12
+
+
+@pytest.mark.parametrize("mm", [0.9999, 0.99, 0.5, 0.0, 1.0])
+def test_ema_update_matches_the_literal_reference_loop(mm):
+    """Pins O.ema_update bit for bit to the reference's own statement (engines/base_engine.py:166-167) executed here on CPU
+    tensors: same zip order, same two roundings per element."""
+    sd_q, sd_k = cases.mhim_state(1, "attn"), cases.mhim_state(2, "attn")
+    q = [torch.nn.Parameter(v.clone()) for v in sd_q.values()]
+    k = [torch.nn.Parameter(v.clone()) for v in sd_k.values()]
+    got = O.ema_update(q, k, mm)
+    for param_q, param_k in zip(q, k):                                  # the reference's loop, verbatim in effect
+        param_k.data.mul_(mm).add_(param_q.data, alpha=1. - mm)
+    for a, b in zip(got, k):
+        assert torch.equal(a, b.data)
+    with pytest.raises(AssertionError):
+        O.ema_update(q, k, 1.5)
