@@ -29,20 +29,21 @@ def _segments(pairs):
 def ema_update(model: torch.nn.Module, model_ema: torch.nn.Module, mm: float) -> None:
     """model_ema <- mm * model_ema + (1 - mm) * model, parameter by parameter, in place (buffers are not touched, as upstream)."""
     assert 0.0 <= mm <= 1.0, "Momentum needs to be between 0.0 and 1.0, got %.5f" % mm          # base_engine.py:164
-    pairs = [(k.data, q.data) for q, k in zip(model.parameters(), model_ema.parameters())]
+    pairs = list(zip(model_ema.parameters(), model.parameters()))       # (param_k, param_q), the reference's zip order
     if not pairs:
         return
-    dev = pairs[0][0].device
-    for k, q in pairs:
-        if not (k.is_cuda and q.is_cuda) or k.device != dev or q.device != dev:
-            raise RuntimeError("mhimk ema_update: every parameter of both models must live on the same CUDA device -- no CPU path")
-        if k.dtype != torch.float32 or q.dtype != torch.float32 or k.shape != q.shape:
-            raise RuntimeError("mhimk ema_update: parameters must be float32 and pairwise of equal shape")
-        if not (k.is_contiguous() and q.is_contiguous()):
-            raise RuntimeError("mhimk ema_update: parameters must be contiguous")
-    key = tuple((k.data_ptr(), q.data_ptr(), k.numel()) for k, q in pairs)
+    # the segment table depends only on addresses, sizes and dtypes: validate and build it once per such layout
+    key = tuple((k.data_ptr(), q.data_ptr(), k.numel(), k.dtype, q.dtype) for k, q in pairs)
     table = _TABLES.get(key)
     if table is None:
+        dev = pairs[0][0].device
+        for k, q in pairs:
+            if not (k.is_cuda and q.is_cuda) or k.device != dev or q.device != dev:
+                raise RuntimeError("mhimk ema_update: every parameter of both models must live on the same CUDA device -- no CPU path")
+            if k.dtype != torch.float32 or q.dtype != torch.float32 or k.shape != q.shape:
+                raise RuntimeError("mhimk ema_update: parameters must be float32 and pairwise of equal shape")
+            if not (k.is_contiguous() and q.is_contiguous()):
+                raise RuntimeError("mhimk ema_update: parameters must be contiguous")
         if len(_TABLES) > 16:
             _TABLES.clear()
         table = torch.tensor(_segments(pairs), dtype=torch.int64).reshape(-1, 3).to(dev)
