@@ -190,3 +190,46 @@ def test_ema_update_matches_the_literal_reference_loop(mm):
         assert torch.equal(a, b.data)
     with pytest.raises(AssertionError):
         O.ema_update(q, k, 1.5)
+
+
+GT = torch.load(os.path.join(os.path.dirname(__file__), "golden", "golden_trainer_v1.pt"), weights_only=False)
+
+
+def test_training_trajectory_matches_reference():
+    """Four iterations of the reference's own training loop (CommonMIL.forward_func -> CE + aux_alpha * aux -> SGD step -> EMA
+    teacher update through `.data`), recorded from the live reference by tests/golden/make_golden_trainer.py, replayed on the
+    oracle: per-iteration teacher scores / cls_tea / logits / losses / keep_num and the final eval logits and weight norms."""
+    T = GT["cfg"]
+    cfg = O.MHIMConfig(**dict(cases.MHIM_KW, baseline=T["base"], input_dim=T["D"]))
+    sd_s, sd_t = leaf(cases.mhim_state(T["seed"], T["base"], D=T["D"])), cases.mhim_state(T["seed"] + 1, T["base"], D=T["D"])
+    bags = [cases.make_bag(T["seed"] + 1000 + j, T["N"], T["D"]) for j in range(2)]
+    assert cases.fingerprint(cases.mhim_state(T["seed"], T["base"], D=T["D"]), bags[0]) == pytest.approx(GT["fp"], rel=1e-12)
+    tol = 2e-5                                   # fp32 vs fp32, a few optimiser steps apart
+    for it, g in enumerate(GT["steps"]):
+        x = bags[it % 2]
+        with torch.no_grad():
+            cls_tea, score = O.mhim_forward_teacher(cfg, sd_t, x)
+        assert cases.rel_err(cls_tea, g["cls_tea"]) <= tol and cases.rel_err(score, g["score"]) <= tol
+        torch.manual_seed(T["seed"] + 7 + it)
+        logits, aux, ps, keep, new_q, _ = O.mhim_forward(cfg, sd_s, x, g["score"], cls_tea, i=it, training=True)
+        assert (ps, keep) == (g["patch_num"], g["keep_num"])
+        loss = F.cross_entropy(logits, LABEL) + T["aux_alpha"] * aux
+        assert cases.rel_err(logits, g["logits"]) <= tol and cases.rel_err(aux, g["aux_loss"]) <= tol and cases.rel_err(loss, g["loss"]) <= tol
+        loss.backward()
+        with torch.no_grad():
+            sd_s["merge.global_q_mm"].copy_(new_q)                       # merge.py:127-129 (train-mode side effect; no gradient)
+            sd_s["merge.global_q"].copy_(new_q)                          # the same Parameter under its second name
+            for k, p in sd_s.items():                                    # SGD step + zero_grad
+                if p.grad is not None and not k.startswith("merge.global_q"):
+                    p -= T["lr"] * p.grad
+                p.grad = None
+            keys = list(sd_t)
+            new_t = O.ema_update([sd_s[k] for k in keys], [sd_t[k] for k in keys], T["mm"])      # base_engine.py:166-167
+            sd_t = dict(zip(keys, new_t))
+    with torch.no_grad():
+        assert cases.rel_err(O.mhim_forward_test(cfg, sd_s, bags[0]), GT["stu_eval"]) <= tol
+        assert cases.rel_err(O.mhim_forward_test(cfg, sd_t, bags[0]), GT["tea_eval"]) <= tol
+    for k, n in GT["stu_norms"].items():
+        assert abs(sd_s[k].double().norm().item() - n) <= tol * max(n, 1e-12), k
+    for k, n in GT["tea_norms"].items():
+        assert abs(sd_t[k].double().norm().item() - n) <= tol * max(n, 1e-12), k
