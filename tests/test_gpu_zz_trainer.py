@@ -14,7 +14,7 @@ import cases
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GT = torch.load(os.path.join(os.path.dirname(__file__), "golden", "golden_trainer_v1.pt"), weights_only=False)
-TOL_FIRST, TOL_LATER = 1e-4, 3e-4        # the north-star gate on the first iteration; later ones sit a few optimiser steps downstream
+TOL_FIRST, TOL_LATER = 1e-4, 1e-4        # the north-star gate on every iteration (measured on B200: <= 6e-6, profiles/round1e_trainer_trajectory_errs.json)
 
 
 def test_training_trajectory_matches_reference():
