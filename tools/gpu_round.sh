@@ -20,4 +20,9 @@ timeout 300 env PROF_REPS=10 python tools/prof_fused.py > gpurun_out/prof_fused.
 timeout 300 python tools/trace_fused.py > gpurun_out/trace_fused.log 2>&1; tail -30 gpurun_out/trace_fused.log
 MHIMK_PIPELINE=2 PROF_PREC=fp16 timeout 300 python tools/trace_fused.py > gpurun_out/trace_fused_pair.log 2>&1; tail -12 gpurun_out/trace_fused_pair.log
 MHIMK_PIPELINE=1 PROF_PREC=bf16x3 timeout 300 python tools/trace_fused.py > gpurun_out/trace_fused_single_bf16x3.log 2>&1; tail -8 gpurun_out/trace_fused_single_bf16x3.log
+# the other BASELINE.json configs, the training-step profile and the EMA update (round 1, run E)
+CFG_REPS=5 timeout 200 python tools/bench_configs.py > gpurun_out/configs.json 2> gpurun_out/configs.err; tail -c 1500 gpurun_out/configs.json
+timeout 60 python tools/prof_train_step.py > gpurun_out/train_prof_attn.txt 2>&1; head -1 gpurun_out/train_prof_attn.txt
+T_BASE=dsmil T_D=1536 timeout 60 python tools/prof_train_step.py > gpurun_out/train_prof_dsmil.txt 2>&1; head -1 gpurun_out/train_prof_dsmil.txt
+timeout 40 python tools/time_ema.py > gpurun_out/time_ema.txt 2>&1; tail -2 gpurun_out/time_ema.txt
 ls -la gpurun_out
