@@ -119,3 +119,25 @@ def test_weight_image_cache_policy(monkeypatch):
     ops._drop_dead(ops._WS_CACHE, 64)
     ops._drop_dead(ops._WT_CACHE, 256)
     assert len(ops._WS_CACHE) == n_ws - 1 and len(ops._WT_CACHE) == n_wt - 1      # dead owners release their buffers
+
+
+def test_modules_survive_the_plumbing_of_the_reference_main():
+    """What the reference's factory / main do to a model before training (modules/__init__.py:179-214, main.py:224-236):
+    deepcopy for the teacher, load_state_dict of the student's dict, .to(memory_format=channels_last), attribute pokes.
+    Pure host logic: no kernel is called."""
+    import copy
+    import torch
+    import cases
+    from mhimk import modules as M
+    for base, n_par in (("attn", 13), ("dsmil", 21), ("selfattn", 32)):
+        stu = M.MHIM(**dict(cases.MHIM_KW, baseline=base, input_dim=1024))
+        tea = copy.deepcopy(stu).to(memory_format=torch.channels_last)
+        assert tea.load_state_dict(stu.state_dict(), strict=True).missing_keys == []
+        assert len(list(tea.parameters())) == n_par == len(list(stu.parameters()))
+        assert all(a is not b for a, b in zip(stu.parameters(), tea.parameters()))
+        tea.merge_test = False
+        assert tea.training and isinstance(tea, torch.nn.Module)
+    for cls, args in ((M.DAttention, (1024, 2, 0.25, "relu")), (M.AttentionGated, (1024, 2)), (M.TransMIL, (1024, 2, 0.25, "relu")),
+                      (M.MILNet, (2, 0.25, "relu"))):
+        m = cls(*args)
+        assert copy.deepcopy(m).load_state_dict(m.state_dict(), strict=True).unexpected_keys == []
