@@ -65,7 +65,7 @@ def _worker(rank, world, port, n_rows, ret):
 @pytest.mark.parametrize("world,n_rows", [(2, 1000), (3, 300), (2, 100)])
 def test_protocol_over_gloo(world, n_rows):
     port = 29500 + (os.getpid() + world * 7 + n_rows) % 2000
-    with mp.Manager() as mgr:
+    with mp.get_context("spawn").Manager() as mgr:          # not fork(): the parent already runs torch threads
         ret = mgr.dict()
         mp.spawn(_worker, args=(world, port, n_rows, ret), nprocs=world, join=True)
         assert all(ret.get(r) == "ok" for r in range(world)), dict(ret)
