@@ -250,7 +250,7 @@ def main():
                        "d2h_bytes_per_step": N_CLASSES * 4, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
                "gpu_launches": args.steps,                # per step: ONE fused kernel (merge + classifier in its tail; weight images cached)
                "clocks": sampler.summary()}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:        # rank 0 at N=1 only: at N>1 the other ranks' host threads would distort it
             n_cpu = 250                                    # bounded sample: ~10 s of CPU work on the box's host cores
             med = time_cpu(n_cpu, N_INST)
             out["cpu_baseline"] = {"value": N_INST / med, "unit": "instances/s", "cores": os.cpu_count(), "kind": "port",
