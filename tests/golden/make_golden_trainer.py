@@ -23,11 +23,12 @@ import cases  # noqa: E402
 from _refload import load_reference, zero_dropout  # noqa: E402
 
 TRAINER = dict(base="attn", N=2000, D=1024, seed=81, iters=4, lr=0.02, mm=0.99, aux_alpha=0.5)
+# further trajectories (stored under "more"; replayed by the CPU oracle test): the other two MHIM baselines
+MORE = {"dsmil": dict(base="dsmil", N=600, D=1536, seed=83, iters=3, lr=0.02, mm=0.99, aux_alpha=0.5),
+        "selfattn": dict(base="selfattn", N=300, D=1024, seed=85, iters=3, lr=0.02, mm=0.99, aux_alpha=0.5)}
 
 
-def main():
-    R = load_reference()
-    T = TRAINER
+def run(R, T):
     kw = dict(cases.MHIM_KW, baseline=T["base"], input_dim=T["D"], dropout=0.0)
     stu, tea = zero_dropout(R.mhim.MHIM(**kw)), zero_dropout(R.mhim.MHIM(**kw))
     stu.load_state_dict(cases.mhim_state(T["seed"], T["base"], D=T["D"]), strict=True)
@@ -54,17 +55,28 @@ def main():
         opt.zero_grad()
         for param_q, param_k in zip(stu.parameters(), tea.parameters()):  # base_engine.py:166-167
             param_k.data.mul_(T["mm"]).add_(param_q.data, alpha=1. - T["mm"])
-        steps.append({"score": score.detach().clone(), "cls_tea": cls_tea.detach().clone(), "logits": logits.detach().clone(),
+        steps.append({"score": score.detach().clone(), "cls_tea": (cls_tea[0] if T["base"] == "dsmil" else cls_tea).detach().clone(),
+                      "logits": logits.detach().clone(),
                       "aux_loss": aux_loss.detach().clone(), "loss": loss.detach().clone(), "patch_num": patch_num, "keep_num": keep_num})
     stu.eval(), tea.eval()
+    val = R.common_mil.CommonMIL(None).validate_func                    # engines/common_mil.py:56-69 (dsmil: 0.5 bag + 0.5 instance logits)
     with torch.no_grad():
-        out = {"cfg": T, "steps": steps, "stu_eval": stu.forward_test(bags[0]).clone(), "tea_eval": tea.forward_test(bags[0]).clone(),
+        out = {"cfg": T, "steps": steps, "stu_eval": val(args, stu, bags[0], label, None, 1, 0, None)[0].clone(),
+               "tea_eval": val(args, tea, bags[0], label, None, 1, 0, None)[0].clone(),
                "stu_norms": {k: v.double().norm().item() for k, v in stu.state_dict().items()},
                "tea_norms": {k: v.double().norm().item() for k, v in tea.state_dict().items()},
                "fp": cases.fingerprint(cases.mhim_state(T["seed"], T["base"], D=T["D"]), bags[0])}
+    print(T["base"], [float(s["loss"]) for s in steps])
+    return out
+
+
+def main():
+    R = load_reference()
+    out = run(R, TRAINER)
+    out["more"] = {name: run(R, T) for name, T in MORE.items()}
     path = os.path.join(HERE, "golden_trainer_v1.pt")
     torch.save(out, path)
-    print("wrote", path, os.path.getsize(path), "bytes;", [float(s["loss"]) for s in steps])
+    print("wrote", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":
