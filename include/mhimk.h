@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MIL_ABI_VERSION 1
+#define MIL_ABI_VERSION 2
 
 /* activation codes used by every entry point */
 enum { MIL_ACT_NONE = 0, MIL_ACT_RELU = 1, MIL_ACT_GELU = 2, MIL_ACT_TANH = 3, MIL_ACT_SIGMOID = 4 };
@@ -46,6 +46,23 @@ enum {
 
 typedef void* mil_stream_t; /* cudaStream_t */
 
+/* Dropout on the embedding h inside the kernels (nn.Dropout after the feature layer: modules/mhim.py:193-194,331; abmil.py:188-189).
+ * A HOST struct passed by pointer (NULL or mode 0 = no dropout).  Kept values are scaled by 1/(1-p) like torch.nn.functional.dropout.
+ *   mode 1: keep_bits = device uint32[rows][ncols/32], bit i of word (r, c) = keep flag of column 32c+i (parity tests feed the
+ *           reference's own Bernoulli mask this way);
+ *   mode 2: in-kernel Philox4x32-10: counter = (row, column/8, offset_lo, offset_hi), key = (seed_lo, seed_hi); each call yields
+ *           eight 16-bit uniforms u (low half-word first), keep iff u < round((1-p)*65536).  Stateless in (row, column): the same
+ *           (seed, offset) regenerates the same mask in the backward pass or on the host (tests/philox_ref.py). */
+enum { MIL_DROP_NONE = 0, MIL_DROP_BITS = 1, MIL_DROP_PHILOX = 2 };
+typedef struct {
+  int             mode;
+  float           p;
+  uint64_t        seed, offset;
+  const uint32_t* keep_bits;
+} mil_dropout_t;
+/* keep_bits_out[rows][ncols/32] = the mask mode 2 would apply (ncols % 32 == 0). */
+int mil_dropout_bits(int64_t rows, int ncols, const mil_dropout_t* drop, uint32_t* keep_bits_out, mil_stream_t stream);
+
 int         mil_abi_version(void);
 const char* mil_last_error(void);
 /* 1 if the current device is compute capability 10.x (tcgen05/TMEM/TMA available), else 0. */
@@ -58,11 +75,14 @@ int         mil_device_supported(void);
  * Replaces: modules/abmil.py:213-234 (DAttention.forward), :121-139 (AttentionGated.forward),
  *           modules/mhim.py:193 + modules/mhim_modules/baseline.py:31-41,97-110 (feature + DAttention),
  *           and with `keep` the gather of modules/mhim_modules/masking.py:91-110.
- * X [N,D] row-major, 16-byte aligned, D % 32 == 0, H == 512, Da in {128, 256, 384} (Da*(gated?2:1) <= 768).
+ * X [N,D] row-major, 16-byte aligned, D % 32 == 0, H == 512, Da == 128; Wb / bb (the gated branch) must be NULL here: the gated
+ * heads run through mil_gated_attn_pool_f32 below.
  * keep      nullable uint8[N]: rows with keep[n]==0 are skipped (masked instances).
  * s_out     nullable float[N]: raw attention logits (-inf for skipped rows).
  * t_out     nullable float[N,C]: t_{n,c} = h_n . Wp_c (needs Wp [C,H], C <= 4) -- input of mil_cam_score_f32.
  * h_out     nullable float[N,H]: materialised embedding (training / return_act).
+ * drop      nullable: dropout applied to h right after the activation (everything downstream -- attention logits, pooling,
+ *           t_out, h_out -- sees the dropped embedding, as in the reference).
  * part      float[n_part,(2+H)] scratch for the per-CTA partials, n_part = mil_fused_num_partials() (one record more than
  *           CTAs are launched: the bulk copies of the in-kernel merge round up to 16 bytes).
  * stats     float[2] = (m, l); pooled float[H]: written by the last CTA to finish (in-kernel log-sum-exp merge of the partials).
@@ -80,7 +100,7 @@ int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H,
                             const uint8_t* keep, const float* Wp, int C,
                             float* s_out, float* t_out, float* h_out,
                             float* part, float* stats, float* pooled,
-                            const float* Wcls, const float* bcls, int n_cls, float* logits,
+                            const float* Wcls, const float* bcls, int n_cls, float* logits, const mil_dropout_t* drop,
                             void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream);
 int    mil_fused_num_partials(void);
 /* Kernel-only timing of the fused pass for the roofline line of bench.py: while enabled, every fused launch is bracketed
@@ -109,12 +129,18 @@ int mil_sgemm_f32(const float* A, int64_t sAm, int64_t sAk, const int64_t* row_i
  * (pre-activation, ld = N).  ws >= mil_linear_tc_workspace_bytes(N, K) holds the weight image; ws_ready as above.
  * Replaces the forward of the N-row projections (mhim.py:69, dsmil.py:62-70, nystrom_attention.py:52-57, merge.py:35-41). */
 int    mil_linear_act_tc_f32(const float* X, int64_t M, int K, const float* W, const float* bias, int N, int act, float* pre_out,
-                             float* Y, void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream);
+                             float* Y, const mil_dropout_t* drop /* nullable: dropout on Y (N % 32 == 0) */,
+                             void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream);
 size_t mil_linear_tc_workspace_bytes(int N, int K);
 
 /* g_pre = g_y * act'(.) elementwise; `y_or_pre` is the activation OUTPUT for relu/tanh/sigmoid and the
  * PRE-activation for gelu.  n elements.  (autograd of nn.ReLU/GELU/Tanh/Sigmoid on the path) */
 int mil_act_bwd_f32(const float* g_y, const float* y_or_pre, int64_t n, int act, float* g_pre, mil_stream_t stream);
+/* The same through a dropout that followed the activation: g_pre = g_y * keep/(1-p) * act'(.) over a [rows, ncols] tensor (ncols % 32 == 0);
+ * the mask is regenerated from `drop` (mode 1 or 2).  `y_or_pre`: for relu the activation output (dropped or not: y_dropped > 0 <=> kept
+ * and pre > 0); for gelu / tanh / sigmoid the PRE-activation. */
+int mil_act_bwd_drop_f32(const float* g_y, const float* y_or_pre, int64_t rows, int ncols, int act, const mil_dropout_t* drop, float* g_pre,
+                         mil_stream_t stream);
 
 /* out[n] = sum_m A[m,n]  (bias gradients), deterministic. */
 int mil_colsum_f32(const float* A, int64_t M, int64_t N, float* out, void* ws, size_t ws_bytes, mil_stream_t stream);

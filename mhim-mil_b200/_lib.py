@@ -9,10 +9,17 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmhimk.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ACT = {"none": 0, None: 0, "relu": 1, "gelu": 2, "tanh": 3, "sigmoid": 4}
 PREC = {"bf16x3": 0, "fp16": 1, "bf16": 2}
+
+
+
+class DropoutT(ctypes.Structure):
+    """mil_dropout_t of include/mhimk.h (a HOST struct passed by pointer)."""
+    _fields_ = [("mode", c_int), ("p", c_float), ("seed", ctypes.c_uint64), ("offset", ctypes.c_uint64), ("keep_bits", c_void_p)]
+
 
 _lib = None
 
@@ -22,17 +29,19 @@ _SIGS = {
     "mil_device_supported": (c_int, []),
     "mil_abmil_fused_fwd_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "mil_dropout_bits": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "mil_profile_enable": (None, [c_int]),
     "mil_profile_collect": (c_int, [ctypes.POINTER(ctypes.c_double)]),
     "mil_fused_num_partials": (c_int, []),
     "mil_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mil_sgemm_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                               c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    "mil_linear_act_tc_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
-                                      c_int, c_void_p]),
+    "mil_linear_act_tc_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                      c_int, c_int, c_void_p]),
     "mil_linear_tc_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mil_act_bwd_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "mil_act_bwd_drop_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mil_colsum_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mil_softmax_pool_fwd_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mil_pool_num_partials": (c_int, [c_int64]),

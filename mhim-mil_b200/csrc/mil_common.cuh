@@ -67,6 +67,31 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Philox4x32-10 keep words of the in-kernel dropout (see mil_umma.cuh / mhimk.h mil_dropout_t)
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    c[0] = n0; c[1] = (uint32_t)p1; c[2] = n2; c[3] = (uint32_t)p0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__host__ __device__ __forceinline__ uint32_t philox_keep_word(uint32_t row, uint32_t chunk, uint32_t thresh, const uint32_t (&seed)[2], const uint32_t (&off)[2]) {
+  uint32_t m = 0;
+#pragma unroll
+  for (uint32_t q4 = 0; q4 < 4; ++q4) {
+    uint32_t c[4] = {row, chunk * 4u + q4, off[0], off[1]};
+    philox4x32_10(c, seed[0], seed[1]);
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+      m |= ((c[j] & 0xFFFFu) < thresh ? 1u : 0u) << (q4 * 8u + 2u * j);
+      m |= ((c[j] >> 16) < thresh ? 1u : 0u) << (q4 * 8u + 2u * j + 1u);
+    }
+  }
+  return m;
+}
+
 int num_sms();
 
 }  // namespace mil

@@ -429,6 +429,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         for (int j = 0; j < 2; ++j) {
           tmem_ld32f(tb + (uint32_t)(j * 32), keep_h[j]);
           bias_act32<ACT>(keep_h[j], c_b1 + f0 + j * 32, p.act);
+          if (p.drop_mode) drop_apply32(keep_h[j], drop_keep_word(p, grow, (f0 >> 5) + j, HMAX / 32), p.drop_scale);
         }
         tc_fence_before();
         __syncwarp();
@@ -474,6 +475,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         float hv[32];
         tmem_ld32f(tb + (uint32_t)(j * 32), hv);
         bias_act32<ACT>(hv, c_b1 + f0 + j * 32, p.act);
+        if (p.drop_mode) drop_apply32(hv, drop_keep_word(p, grow, (f0 >> 5) + j, HMAX / 32), p.drop_scale);
         tmem_st32f(tb + (uint32_t)(j * 32), hv);
         emit_chunk(j, hv);
       }

@@ -345,6 +345,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
           } else {
             bias_act32<-1>(hv, c_b1 + c * 32, p.act);
           }
+          if (p.drop_mode) drop_apply32(hv, drop_keep_word(p, grow, c, nch), p.drop_scale);
           if (grow < p.N) {
             float* dst = p.c_out + grow * p.ldc + c * 32;
 #pragma unroll
@@ -375,6 +376,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
           const int c = 2 * j + half;
           tmem_ld32f(tq + (uint32_t)(c * 32), keep_h[j]);
           bias_act32<ACT>(keep_h[j], c_b1 + c * 32, p.act);
+          if (p.drop_mode) drop_apply32(keep_h[j], drop_keep_word(p, grow, c, HMAX / 32), p.drop_scale);
         }
         tc_fence_before();
         __syncwarp();
@@ -417,6 +419,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
           float hv[32];
           tmem_ld32f(tq + (uint32_t)(c * 32), hv);
           bias_act32<ACT>(hv, c_b1 + c * 32, p.act);
+          if (p.drop_mode) drop_apply32(hv, drop_keep_word(p, grow, c, HMAX / 32), p.drop_scale);
           tmem_st32f(tq + (uint32_t)(c * 32), hv);
           emit_chunk(c, hv);
         }
@@ -665,6 +668,31 @@ static int dispatch_fused(int precision, int mode, const CUtensorMap& mx, const 
   return -1;
 }
 
+int set_dropout(FusedParams& p, const mil_dropout_t* drop, int ncols) {
+  p.drop_mode = 0; p.drop_bits = nullptr; p.drop_thresh = 65536u; p.drop_scale = 1.f;
+  p.drop_seed[0] = p.drop_seed[1] = p.drop_off[0] = p.drop_off[1] = 0u;
+  if (!drop || drop->mode == MIL_DROP_NONE || drop->p == 0.f) return 0;
+  MIL_CHECK_ARG(drop->mode == MIL_DROP_BITS || drop->mode == MIL_DROP_PHILOX, "dropout: bad mode %d", drop->mode);
+  MIL_CHECK_ARG(drop->p > 0.f && drop->p < 1.f, "dropout: p=%g must be in [0, 1)", (double)drop->p);
+  MIL_CHECK_ARG(ncols % 32 == 0, "dropout: the dropped tensor must have a multiple of 32 columns (got %d)", ncols);
+  MIL_CHECK_ARG(drop->mode != MIL_DROP_BITS || drop->keep_bits, "dropout: mode 1 needs keep_bits");
+  p.drop_mode = drop->mode;
+  p.drop_bits = drop->keep_bits;
+  p.drop_scale = 1.f / (1.f - drop->p);
+  p.drop_thresh = (uint32_t)lrint((1.0 - (double)drop->p) * 65536.0);
+  p.drop_seed[0] = (uint32_t)drop->seed; p.drop_seed[1] = (uint32_t)(drop->seed >> 32);
+  p.drop_off[0] = (uint32_t)drop->offset; p.drop_off[1] = (uint32_t)(drop->offset >> 32);
+  return 0;
+}
+
+__global__ void dropout_bits_kernel(int64_t words, int words_per_row, uint32_t thresh, uint32_t s0, uint32_t s1, uint32_t o0, uint32_t o1,
+                                    uint32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= words) return;
+  const uint32_t seed[2] = {s0, s1}, off[2] = {o0, o1};
+  out[i] = philox_keep_word((uint32_t)(i / words_per_row), (uint32_t)(i % words_per_row), thresh, seed, off);
+}
+
 static int split_weights(const float* w, int R, int K, uint8_t* img, int precision, cudaStream_t stream) {
   const int64_t items = (int64_t)R * (K / 8);
   const unsigned blocks = (unsigned)((items + 255) / 256);
@@ -697,6 +725,19 @@ extern "C" int mil_profile_collect(double* total_ms) {
   return n;
 }
 
+extern "C" int mil_dropout_bits(int64_t rows, int ncols, const mil_dropout_t* drop, uint32_t* keep_bits_out, mil_stream_t stream_) {
+  MIL_CHECK_ARG(rows > 0 && rows < (1ll << 31) && ncols > 0 && ncols % 32 == 0 && drop && keep_bits_out, "mil_dropout_bits: bad argument");
+  MIL_CHECK_ARG(drop->mode == MIL_DROP_PHILOX && drop->p > 0.f && drop->p < 1.f, "mil_dropout_bits: needs mode 2 and 0 < p < 1");
+  FusedParams p;
+  int rc;
+  if ((rc = set_dropout(p, drop, ncols))) return rc;
+  const int64_t words = rows * (ncols / 32);
+  dropout_bits_kernel<<<(unsigned)((words + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(words, ncols / 32, p.drop_thresh, p.drop_seed[0], p.drop_seed[1],
+                                                                                         p.drop_off[0], p.drop_off[1], keep_bits_out);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" size_t mil_fused_workspace_bytes(int D, int H, int Da, int gated) {
   (void)gated;
   return ((size_t)H * D + (size_t)Da * H) * 2 /*hi+lo*/ * sizeof(uint16_t) + 1024 + sizeof(int) * 4 + 64 + (16 * 16 + 2 * 1024) * sizeof(long long);
@@ -706,7 +747,7 @@ extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, 
                                        const float* ba, const float* Wb, const float* bb, int Da, int att_act, const float* wc, const float* bc,
                                        const uint8_t* keep, const float* Wp, int C, float* s_out, float* t_out, float* h_out, float* part,
                                        float* stats, float* pooled, const float* Wcls, const float* bcls, int n_cls, float* logits,
-                                       void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream_) {
+                                       const mil_dropout_t* drop, void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   // bits 8..15 of `precision` select the pipeline: 0 = default (pair), MIL_PIPE_SINGLE, MIL_PIPE_PAIR; MHIMK_PIPELINE=1|2 overrides the default
   int pipeline = (precision >> 8) & 0xFF;
@@ -754,6 +795,7 @@ extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, 
   p.s_out = s_out; p.t_out = t_out; p.h_out = h_out; p.part = part; p.c_out = nullptr; p.ldc = 0; p.err = err; p.dbg = debug_mask(); p.w1_img = w1_img; p.wa_img = wa_img;
   p.stats = stats; p.pooled = pooled; p.counter = (unsigned int*)(err + 1); p.Wcls = Wcls; p.bcls = bcls; p.n_cls = n_cls; p.logits = logits;
   p.trace = getenv("MHIMK_TRACE") ? (long long*)(((uintptr_t)(err + 4) + 63) & ~(uintptr_t)63) : nullptr;
+  if ((rc = set_dropout(p, drop, H))) return rc;
   if (pipeline == 2) return pair_fused_launch(X, p, precision, stream);
   const int64_t n_tiles = (N + BM - 1) / BM;
   const int grid = grid_override((int)(n_tiles < num_sms() ? n_tiles : num_sms()));
@@ -782,6 +824,7 @@ extern "C" int mil_umma_selftest_f32(const float* A, const float* B, float* C, i
   p.b1 = nullptr; p.ba = nullptr; p.wc = nullptr; p.bc = nullptr; p.keep = nullptr; p.Wp = nullptr; p.C = 0;
   p.s_out = nullptr; p.t_out = nullptr; p.h_out = nullptr; p.part = nullptr; p.c_out = C; p.ldc = N; p.err = err; p.dbg = debug_mask(); p.w1_img = b_img; p.wa_img = b_img; p.trace = nullptr;
   p.stats = nullptr; p.pooled = nullptr; p.counter = nullptr; p.Wcls = nullptr; p.bcls = nullptr; p.n_cls = 0; p.logits = nullptr;
+  set_dropout(p, nullptr, N);
   const int64_t n_tiles = ((int64_t)M + BM - 1) / BM;
   const int grid = grid_override((int)(n_tiles < num_sms() ? n_tiles : num_sms()));
   return dispatch_fused(precision, MODE_STORE, mx, p, grid, stream);
@@ -790,7 +833,8 @@ extern "C" int mil_umma_selftest_f32(const float* A, const float* B, float* C, i
 extern "C" size_t mil_linear_tc_workspace_bytes(int N, int K) { return (size_t)N * K * 4 + 1024 + 64; }
 
 extern "C" int mil_linear_act_tc_f32(const float* X, int64_t M, int K, const float* W, const float* bias, int N, int act, float* pre_out,
-                                     float* Y, void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream_) {
+                                     float* Y, const mil_dropout_t* drop, void* ws, size_t ws_bytes, int ws_ready, int precision,
+                                     mil_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MIL_CHECK_ARG(mil_device_supported(), "mil_linear_act_tc_f32: needs a compute-capability 10.x device");
   MIL_CHECK_ARG(X && W && Y && ws && M > 0 && M < (1ll << 31) - 256, "mil_linear_act_tc_f32: bad argument");
@@ -815,6 +859,7 @@ extern "C" int mil_linear_act_tc_f32(const float* X, int64_t M, int K, const flo
   p.s_out = nullptr; p.t_out = nullptr; p.h_out = pre_out; p.part = nullptr; p.c_out = Y; p.ldc = N; p.err = err; p.dbg = 0;
   p.w1_img = w_img; p.wa_img = w_img; p.trace = nullptr;
   p.stats = nullptr; p.pooled = nullptr; p.counter = nullptr; p.Wcls = nullptr; p.bcls = nullptr; p.n_cls = 0; p.logits = nullptr;
+  if ((rc = set_dropout(p, drop, N))) return rc;
   const int64_t n_tiles = (M + BM - 1) / BM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   return dispatch_fused(precision, MODE_STORE, mx, p, grid, stream);

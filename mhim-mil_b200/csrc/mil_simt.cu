@@ -170,6 +170,39 @@ __global__ void act_bwd_kernel(const float* __restrict__ g, const float* __restr
   out[i] = g[i] * d;
 }
 
+// the same through a dropout that followed the activation: one thread per (row, 32-column chunk)
+__global__ void act_bwd_drop_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t rows, int words_per_row, int act,
+                                    int mode, const uint32_t* __restrict__ bits, uint32_t thresh, float scale, uint32_t s0, uint32_t s1,
+                                    uint32_t o0, uint32_t o1, float* __restrict__ out) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= rows * words_per_row) return;
+  const uint32_t seed[2] = {s0, s1}, off[2] = {o0, o1};
+  const uint32_t word = mode == 1 ? bits[w] : mil::philox_keep_word((uint32_t)(w / words_per_row), (uint32_t)(w % words_per_row), thresh, seed, off);
+  const float4* g4 = reinterpret_cast<const float4*>(g + w * 32);
+  const float4* y4 = reinterpret_cast<const float4*>(y + w * 32);
+  float4* o4 = reinterpret_cast<float4*>(out + w * 32);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 gv = g4[q], yv = y4[q];
+    const float gg[4] = {gv.x, gv.y, gv.z, gv.w}, vv[4] = {yv.x, yv.y, yv.z, yv.w};
+    float r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v = vv[e];
+      float d;
+      switch (act) {   // v: relu -> the (dropped or undropped) output; every other activation -> the PRE-activation
+        case MIL_ACT_RELU: d = v > 0.f ? 1.f : 0.f; break;
+        case MIL_ACT_TANH: { const float t = tanhf(v); d = 1.f - t * t; break; }
+        case MIL_ACT_SIGMOID: { const float t = 1.f / (1.f + expf(-v)); d = t * (1.f - t); break; }
+        case MIL_ACT_GELU: d = 0.5f * (1.f + erff(v * 0.70710678118654752440f)) + v * 0.39894228040143267794f * expf(-0.5f * v * v); break;
+        default: d = 1.f;
+      }
+      r[e] = ((word >> (q * 4 + e)) & 1u) ? gg[e] * scale * d : 0.f;
+    }
+    o4[q] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
 __global__ void colsum_partial_kernel(const float* __restrict__ A, int64_t M, int64_t N, int64_t rows_per_slice, float* __restrict__ ws) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
@@ -429,6 +462,23 @@ extern "C" int mil_act_bwd_f32(const float* g_y, const float* y_or_pre, int64_t 
   MIL_CHECK_ARG(g_y && y_or_pre && g_pre && n >= 0, "mil_act_bwd_f32: bad arguments");
   if (n == 0) return 0;
   act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g_y, y_or_pre, n, act, g_pre);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mil_act_bwd_drop_f32(const float* g_y, const float* y_or_pre, int64_t rows, int ncols, int act, const mil_dropout_t* drop,
+                                    float* g_pre, mil_stream_t stream) {
+  MIL_CHECK_ARG(g_y && y_or_pre && g_pre && rows >= 0 && rows < (1ll << 31) && ncols > 0 && ncols % 32 == 0, "mil_act_bwd_drop_f32: bad arguments");
+  MIL_CHECK_ARG(drop && (drop->mode == MIL_DROP_BITS || drop->mode == MIL_DROP_PHILOX) && drop->p > 0.f && drop->p < 1.f,
+                "mil_act_bwd_drop_f32: needs a dropout description (mode 1 or 2, 0 < p < 1)");
+  MIL_CHECK_ARG(drop->mode != MIL_DROP_BITS || drop->keep_bits, "mil_act_bwd_drop_f32: mode 1 needs keep_bits");
+  MIL_CHECK_ARG((uintptr_t)g_y % 16 == 0 && (uintptr_t)y_or_pre % 16 == 0 && (uintptr_t)g_pre % 16 == 0, "mil_act_bwd_drop_f32: pointers must be 16-byte aligned");
+  if (rows == 0) return 0;
+  const int64_t words = rows * (ncols / 32);
+  const uint32_t thresh = (uint32_t)lrint((1.0 - (double)drop->p) * 65536.0);
+  act_bwd_drop_kernel<<<(unsigned)((words + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      g_y, y_or_pre, rows, ncols / 32, act, drop->mode, drop->keep_bits, thresh, 1.f / (1.f - drop->p), (uint32_t)drop->seed,
+      (uint32_t)(drop->seed >> 32), (uint32_t)drop->offset, (uint32_t)(drop->offset >> 32), g_pre);
   MIL_LAUNCH_CHECK();
   return 0;
 }

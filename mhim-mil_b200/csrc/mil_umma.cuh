@@ -27,6 +27,8 @@ struct FusedParams {
   const float* Wcls; const float* bcls; int n_cls; float* logits;
   int* err;
   long long* trace;     // optional [16 tiles][16 slots] clock64 stamps of CTA 0 (MHIMK_TRACE=1), see tools/trace_fused.py
+  // dropout on h (mhim.py:193-194, abmil.py:188-189): 0 = none, 1 = caller-supplied keep bits, 2 = in-kernel Philox4x32-10
+  int drop_mode; const uint32_t* drop_bits; uint32_t drop_thresh; float drop_scale; uint32_t drop_seed[2]; uint32_t drop_off[2];
   int dbg;              // MHIMK_DEBUG bitmask (timing attribution only): 1 skip W1 TMA, 2 skip X TMA, 4 skip GEMM1 MMA, 8 skip convert, 16 skip Wa TMA, 32 skip pooling, 64 skip GEMM2 MMA
 };
 
@@ -327,6 +329,23 @@ __device__ __forceinline__ void bias_act32(float (&v)[32], const float* bias, in
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Dropout keep-mask of h.  One 32-bit word per (row, 32-column chunk): bit i = keep flag of column 32 * chunk + i.
+//   mode 1: the caller's words (uint32 [rows][ncols/32]) -- parity tests feed the reference's own mask;
+//   mode 2: Philox4x32-10, counter = (row, 4 * chunk + quarter, offset_lo, offset_hi), key = seed: every call yields eight
+//           16-bit uniforms, one per column; keep iff u16 < thresh, thresh = round((1 - p) * 65536).  Stateless in (row, column),
+//           so a backward pass (or a host-side check, tests/philox_ref.py) regenerates the identical mask.
+// ------------------------------------------------------------------------------------------------------------
+// words_per_row = ncols / 32 of the tensor the mask belongs to
+__device__ __forceinline__ uint32_t drop_keep_word(const FusedParams& p, int64_t row, int chunk, int words_per_row) {
+  if (p.drop_mode == 1) return row < p.N ? __ldg(p.drop_bits + row * words_per_row + chunk) : 0u;
+  return philox_keep_word((uint32_t)row, (uint32_t)chunk, p.drop_thresh, p.drop_seed, p.drop_off);
+}
+__device__ __forceinline__ void drop_apply32(float (&v)[32], uint32_t word, float scale) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = ((word >> i) & 1u) ? v[i] * scale : 0.f;
+}
+
 // column sums over the 32 lanes of a warp of v[0..31] (one value per column per lane): afterwards lane j holds sum_rows v_row[j].
 __device__ __forceinline__ float warp_transpose_sum(float (&v)[32]) {
   const int lane = threadIdx.x & 31;
@@ -468,5 +487,7 @@ int debug_mask();
 size_t pair_weight_image_bytes(int D, int H, int Da);
 int pair_build_images(const float* W1, int H, int D, const float* Wa, int Da, uint8_t* w1_img, uint8_t* wa_img, int precision, cudaStream_t stream);
 int pair_fused_launch(const float* X, FusedParams p, int precision, cudaStream_t stream);
+// fills the dropout fields of p from the ABI struct (nullptr / mode 0 = no dropout); <0 on a bad argument
+int set_dropout(FusedParams& p, const mil_dropout_t* drop, int ncols);
 
 }  // namespace mil

@@ -44,7 +44,12 @@ class DAttention(MilModule):
 
     def _fused_ok(self, x):
         return (self.embed_feat and self.feature[0].bias is not None and self.L == 512 and x.shape[-1] % 32 == 0
-                and not (self.training and self.p_drop > 0))
+                and self.classifier.out_features <= 64)
+
+    def _dropout(self, rows, device):
+        if self.training and self.p_drop > 0 and self.embed_feat:
+            return ops.next_dropout(self.p_drop, rows, self.L, device)
+        return None
 
     def forward(self, x, return_attn=False, no_norm=False, return_act=False, pos=None, return_img_feat=False, **kwargs):
         require_cuda(x, "DAttention")
@@ -58,14 +63,17 @@ class DAttention(MilModule):
             f0 = self.feature[0]
             out = ops.abmil_fused_forward(x2, f0.weight, f0.bias, self.act, att0.weight, att0.bias, att2.weight, att2.bias, "tanh",
                                           want_scores=return_attn, want_h=return_attn and return_act, precision=self.precision,
-                                          Wcls=self.classifier.weight, bcls=self.classifier.bias, volatile=self.training)
+                                          Wcls=self.classifier.weight, bcls=self.classifier.bias, volatile=self.training,
+                                          dropout=self._dropout(x2.shape[0], x2.device))
             pooled, fused_logits = out["pooled"], out["logits"]
             attn = torch.exp(out["s"] - out["stats"][0]) / out["stats"][1] if return_attn else None
             h = out["h"]
         else:
-            h = lin(self.feature[0], x2, self.act) if self.embed_feat else x2
-            if self.training and self.p_drop > 0 and self.embed_feat:
-                h = F.dropout(h, self.p_drop, True)
+            if self.embed_feat:                                            # dropout inside the GEMM's epilogue (abmil.py:188-189)
+                f0 = self.feature[0]
+                h = ops.linear_act(x2, f0.weight, f0.bias, self.act, volatile=f0.training, dropout=self._dropout(x2.shape[0], x2.device))
+            else:
+                h = x2
             u = lin(att0, h, "tanh")
             s = lin(att2, u)[:, 0]
             pooled, attn = ops.softmax_pool(s, h)

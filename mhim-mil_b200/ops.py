@@ -19,6 +19,67 @@ from ._lib import ACT, PREC, check, ptr, stream_ptr
 DEFAULT_PRECISION = "bf16x3"
 
 
+# --------------------------------------------------------------------------------------------------------------
+# dropout inside the kernels (mil_dropout_t)
+# --------------------------------------------------------------------------------------------------------------
+class DropSpec:
+    """Host description of a dropout fused into a kernel: probability `p` and either the in-kernel Philox stream (seed, offset)
+    or caller-supplied keep bits (int32 [rows, ncols/32], bit i of word (r, c) = keep flag of column 32c+i)."""
+    __slots__ = ("p", "seed", "offset", "keep_bits", "_c")
+
+    def __init__(self, p, seed=0, offset=0, keep_bits=None):
+        if not 0.0 <= p < 1.0:
+            raise ValueError(f"mhimk: dropout p={p} must be in [0, 1)")
+        if keep_bits is not None:
+            keep_bits = _need(keep_bits, "keep_bits", torch.int32)
+        self.p, self.seed, self.offset, self.keep_bits = float(p), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), keep_bits
+        self._c = _lib.DropoutT(1 if keep_bits is not None else 2, self.p, self.seed, self.offset, None if keep_bits is None else keep_bits.data_ptr())
+
+    def c(self):
+        import ctypes
+        return ctypes.byref(self._c)
+
+
+_DROP_STATE = {"seed": None, "offset": 0}
+DROPOUT_HOOK = None          # tests: callable (rows, ncols, p, device) -> DropSpec, e.g. keep bits packed from the reference's own mask
+
+
+def next_dropout(p, rows=None, ncols=None, device=None):
+    """A fresh DropSpec: seed = torch's global seed (torch.manual_seed makes runs reproducible), offset = a per-process call counter
+    that restarts whenever the seed changes.  DROPOUT_HOOK, when set, supplies the spec instead (mask-in parity tests)."""
+    if p <= 0.0:
+        return None
+    if DROPOUT_HOOK is not None:
+        return DROPOUT_HOOK(rows, ncols, p, device)
+    seed = torch.initial_seed()
+    if _DROP_STATE["seed"] != seed:
+        _DROP_STATE["seed"], _DROP_STATE["offset"] = seed, 0
+    _DROP_STATE["offset"] += 1
+    return DropSpec(p, seed, _DROP_STATE["offset"])
+
+
+def pack_keep_bits(keep: torch.Tensor) -> torch.Tensor:
+    """bool/0-1 mask [rows, ncols] -> int32 keep words [rows, ncols/32] (torch ops on the mask's device; test / integration helper)."""
+    rows, ncols = keep.shape
+    w = (keep.reshape(rows, ncols // 32, 32) != 0).to(torch.int64) << torch.arange(32, device=keep.device, dtype=torch.int64)
+    w = w.sum(-1)
+    return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32).contiguous()
+
+
+def dropout_bits(rows: int, ncols: int, spec: DropSpec, device) -> torch.Tensor:
+    """The keep words the in-kernel Philox stream of `spec` yields for a [rows, ncols] tensor (mil_dropout_bits)."""
+    out = torch.empty((rows, ncols // 32), dtype=torch.int32, device=device)
+    check(_lib.lib().mil_dropout_bits(rows, ncols, spec.c(), ptr(out), stream_ptr()), "mil_dropout_bits")
+    return out
+
+
+def apply_dropout(y: torch.Tensor, spec: DropSpec) -> torch.Tensor:
+    """y * keep / (1 - p) for a contiguous [rows, ncols] tensor (no autograd; the primitive under linear_act's non-tensor-core path)."""
+    out = torch.empty_like(y)
+    check(_lib.lib().mil_act_bwd_drop_f32(ptr(y), ptr(y), y.shape[0], y.shape[1], ACT["none"], spec.c(), ptr(out), stream_ptr()), "mil_act_bwd_drop_f32")
+    return out
+
+
 def _need(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise RuntimeError(f"mhimk: `{name}` must be a CUDA tensor -- there is no CPU path (got {getattr(t, 'device', type(t))})")
@@ -105,7 +166,7 @@ def _transposed(W, volatile=False):
     return Wt
 
 
-def _tc_block(x, Wb, bb, act, pre_b, y_b, key_obj, blk, precision, volatile=False):
+def _tc_block(x, Wb, bb, act, pre_b, y_b, key_obj, blk, precision, volatile=False, dropout=None):
     """One column block (<= 512 wide, contiguous rows of the weight) through mil_linear_act_tc_f32."""
     import weakref
     L = _lib.lib()
@@ -118,23 +179,25 @@ def _tc_block(x, Wb, bb, act, pre_b, y_b, key_obj, blk, precision, volatile=Fals
     if hit is not None and hit[0]() is key_obj and hit[3] == where:
         ws = hit[2]                                   # same live weight: keep the buffer, rebuild the image in place if stale
         ready = 0 if (volatile or hit[1] != ver) else 1
-        if not ready:
-            _TC_CACHE[key] = (hit[0], ver, ws, where)
     else:
         ws, ready = _ws(L.mil_linear_tc_workspace_bytes(N, K), x.device), 0
         _drop_dead(_TC_CACHE, 256)
+    if not ready:                                     # not valid until the call below has rebuilt the image (a failed
+        _TC_CACHE[key] = (weakref.ref(key_obj), None, ws, where)   # call must not leave a "ready" entry behind)
+    check(L.mil_linear_act_tc_f32(ptr(x), M, K, ptr(Wb), ptr(bb), N, ACT[act], ptr(pre_b), ptr(y_b), dropout.c() if dropout else None,
+                                  ptr(ws), ws.numel(), ready, PREC[precision], stream_ptr()), "mil_linear_act_tc_f32")
+    if not ready:
         _TC_CACHE[key] = (weakref.ref(key_obj), ver, ws, where)
-    check(L.mil_linear_act_tc_f32(ptr(x), M, K, ptr(Wb), ptr(bb), N, ACT[act], ptr(pre_b), ptr(y_b), ptr(ws), ws.numel(), ready,
-                                  PREC[precision], stream_ptr()), "mil_linear_act_tc_f32")
 
 
-def linear_forward(x, W, b, act, pre=None, precision=None, volatile=False):
-    """y = act(x W^T + b): tcgen05 path when the shape allows (column blocks of <= 512), else the fp32 CUDA-core GEMM."""
+def linear_forward(x, W, b, act, pre=None, precision=None, volatile=False, dropout=None):
+    """y = drop(act(x W^T + b)): tcgen05 path when the shape allows (column blocks of <= 512), else the fp32 CUDA-core GEMM."""
     M, K = x.shape
     N = W.shape[0]
     precision = precision or DEFAULT_PRECISION
     if not _tc_supported(M, N, K, W):
-        return sgemm(x, K, 1, W, K, 1, M, N, K, bias=b, act=act, pre_out=pre)
+        y = sgemm(x, K, 1, W, K, 1, M, N, K, bias=b, act=act, pre_out=pre)
+        return apply_dropout(y, dropout) if dropout else y
     widths, left = [], N
     while left > 0:                                   # 512-wide blocks, then one of 256 / 192 / 128 / 64
         wdt = 512 if left >= 512 else (256 if left >= 256 else left)
@@ -142,8 +205,10 @@ def linear_forward(x, W, b, act, pre=None, precision=None, volatile=False):
         left -= wdt
     if len(widths) == 1:
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
-        _tc_block(x, W, b, act, pre, y, W, 0, precision, volatile)
+        _tc_block(x, W, b, act, pre, y, W, 0, precision, volatile, dropout)
         return y
+    if dropout:
+        raise RuntimeError("mhimk: fused dropout on a Linear wider than 512 columns is not provided")
     ys, o = [], 0
     pres = []
     for i, wdt in enumerate(widths):
@@ -160,16 +225,20 @@ def linear_forward(x, W, b, act, pre=None, precision=None, volatile=False):
 
 class _LinearAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, W, b, act, volatile=False):
+    def forward(ctx, x, W, b, act, volatile=False, dropout=None):
         x, W = _need(x, "x"), _need(W, "weight")
         b = _need(b, "bias") if b is not None else None
         M, K = x.shape
         N = W.shape[0]
-        need_pre = act == "gelu" and (x.requires_grad or W.requires_grad)
+        grad = x.requires_grad or W.requires_grad
+        # saved for the backward: relu -> the output (dropped or not); gelu -> the pre-activation; through a dropout tanh / sigmoid
+        # also keep the pre-activation (their derivative needs the undropped value)
+        need_pre = grad and (act == "gelu" or (dropout is not None and act in ("tanh", "sigmoid")))
         pre = torch.empty((M, N), dtype=torch.float32, device=x.device) if need_pre else None
-        y = linear_forward(x, W, b, act, pre, volatile=volatile)
+        y = linear_forward(x, W, b, act, pre, volatile=volatile, dropout=dropout)
         ctx.act = act
         ctx.volatile = volatile
+        ctx.dropout = dropout
         ctx.has_bias = b is not None
         ctx.save_for_backward(x, W, pre if need_pre else y)
         return y
@@ -181,15 +250,17 @@ class _LinearAct(torch.autograd.Function):
         g_y = _need(g_y, "grad")
         M, K = x.shape
         N = W.shape[0]
-        if ctx.act in ("none", None):
+        if ctx.dropout is not None:
+            g_pre = torch.empty_like(g_y)
+            check(L.mil_act_bwd_drop_f32(ptr(g_y), ptr(saved), M, N, ACT[ctx.act], ctx.dropout.c(), ptr(g_pre), stream_ptr()), "mil_act_bwd_drop_f32")
+        elif ctx.act in ("none", None):
             g_pre = g_y
         else:
             g_pre = torch.empty_like(g_y)
             check(L.mil_act_bwd_f32(ptr(g_y), ptr(saved), g_y.numel(), ACT[ctx.act], ptr(g_pre), stream_ptr()), "mil_act_bwd_f32")
         gx = gW = gb = None
         if ctx.needs_input_grad[1]:
-            # gW[n,k] = sum_m g_pre[m,n] x[m,k]:  A(n,m) = g_pre[m*N + n] (row-contiguous), B(k,m) = x[m*K + k]
-            gW = sgemm(g_pre, 1, N, x, 1, K, N, K, M, splitk=_splitk_for(N, K, M))
+            gW = weight_grad(g_pre, x)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = torch.empty(N, dtype=torch.float32, device=x.device)
             ws = _ws(64 * N * 4, x.device)
@@ -201,14 +272,23 @@ class _LinearAct(torch.autograd.Function):
                 gx = linear_forward(g_pre.contiguous(), _transposed(W, ctx.volatile), None, "none")
             else:
                 gx = sgemm(g_pre, N, 1, W, 1, K, M, K, N)
-        return gx, gW, gb, None, None
+        return gx, gW, gb, None, None, None
+
+
+def weight_grad(g_pre, x):
+    """gW[n,k] = sum_m g_pre[m,n] x[m,k] (the contraction over the instances).  fp32 CUDA-core split-K GEMM:
+    A(n,m) = g_pre[m*N + n], B(k,m) = x[m*K + k]."""
+    M, K = x.shape
+    N = g_pre.shape[1]
+    return sgemm(g_pre, 1, N, x, 1, K, N, K, M, splitk=_splitk_for(N, K, M))
 
 
 def linear_act(x: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor] = None, act: str = "none",
-               volatile: bool = False) -> torch.Tensor:
-    """act(x @ W.T + b) for x [M,K]; differentiable (CUDA backward).  volatile=True: do not trust a cached weight image
-    (see weights_touched)."""
-    return _LinearAct.apply(x, W, b, act, volatile)
+               volatile: bool = False, dropout: Optional[DropSpec] = None) -> torch.Tensor:
+    """drop(act(x @ W.T + b)) for x [M,K]; differentiable (CUDA backward).  volatile=True: do not trust a cached weight image
+    (see weights_touched).  dropout: a DropSpec (next_dropout(p)) applied inside the GEMM's epilogue; the backward regenerates
+    the same mask."""
+    return _LinearAct.apply(x, W, b, act, volatile, dropout)
 
 
 def linear_act_rows(x, W, b, act, row_ids):
@@ -343,8 +423,9 @@ def _pipeline(name, precision=None):
 
 
 def _fused_workspace(W1, Wa, precision, pipeline="pair", volatile=False):
-    """(workspace, ready): the caller-owned buffer holding the 16-bit images of W1 / Wa, and whether the kernel may use them as
-    they are (1) or must rebuild them first (0)."""
+    """(workspace, ready, commit): the caller-owned buffer holding the 16-bit images of W1 / Wa, whether the kernel may use them
+    as they are (1) or must rebuild them first (0), and the callback that marks the rebuilt images valid -- called only after
+    the C call has returned 0 (a failed call must not leave a "ready" entry behind)."""
     import weakref
     L = _lib.lib()
     key = (id(W1), id(Wa), precision, pipeline)
@@ -352,23 +433,30 @@ def _fused_workspace(W1, Wa, precision, pipeline="pair", volatile=False):
     where = (W1.data_ptr(), Wa.data_ptr(), tuple(W1.shape), tuple(Wa.shape))
     hit = _WS_CACHE.get(key)
     if hit is not None and hit[0]() is W1 and hit[1]() is Wa and hit[4] == where:
+        ws = hit[3]
         ready = 0 if (volatile or hit[2] != ver) else 1
-        if not ready:
-            _WS_CACHE[key] = (hit[0], hit[1], ver, hit[3], where)
-        return hit[3], ready
-    ws = _ws(L.mil_fused_workspace_bytes(W1.shape[1], W1.shape[0], Wa.shape[0], 0), W1.device)
-    _drop_dead(_WS_CACHE, 64)
-    _WS_CACHE[key] = (weakref.ref(W1), weakref.ref(Wa), ver, ws, where)
-    return ws, 0
+    else:
+        ws, ready = _ws(L.mil_fused_workspace_bytes(W1.shape[1], W1.shape[0], Wa.shape[0], 0), W1.device), 0
+        _drop_dead(_WS_CACHE, 64)
+    if ready:
+        return ws, 1, lambda: None
+    refs = (weakref.ref(W1), weakref.ref(Wa))
+    _WS_CACHE[key] = (refs[0], refs[1], None, ws, where)
+
+    def commit():
+        _WS_CACHE[key] = (refs[0], refs[1], ver, ws, where)
+    return ws, 0, commit
 
 
 @torch.no_grad()
 def abmil_fused_forward(x, W1, b1, act, Wa, ba, wc, bc, att_act="tanh", keep=None, Wp=None, want_scores=False, want_h=False,
-                        precision: str = DEFAULT_PRECISION, Wcls=None, bcls=None, pipeline=None, volatile: bool = False):
+                        precision: str = DEFAULT_PRECISION, Wcls=None, bcls=None, pipeline=None, volatile: bool = False,
+                        dropout: Optional[DropSpec] = None):
     """One streaming pass over x [N,D]: returns dict(pooled[H], stats[2] = (m, l), s[N]?, t[N,C]?, h[N,H]?, part).
 
     h = act(x W1^T + b1); s = wc . att_act(Wa h + ba) + bc; pooled = softmax_N(s) @ h; logits = Wcls pooled + bcls when a
-    classifier is given (same kernel).  (mil_abmil_fused_fwd_f32)
+    classifier is given (same kernel).  dropout: a DropSpec applied to h right after the activation (train-mode teacher,
+    mhim.py:193-194).  (mil_abmil_fused_fwd_f32)
     """
     L = _lib.lib()
     x, W1, b1, Wa, wc = _need(x, "x"), _need(W1, "W1"), _need(b1, "b1"), _need(Wa, "Wa"), _need(wc.reshape(-1), "wc")
@@ -386,12 +474,13 @@ def abmil_fused_forward(x, W1, b1, act, Wa, ba, wc, bc, att_act="tanh", keep=Non
     ncls = Wcls.shape[0] if Wcls is not None else 0
     logits = torch.empty((1, ncls), dtype=torch.float32, device=dev) if Wcls is not None else None
     pipeline = _pipeline(pipeline, precision)
-    ws, ready = _fused_workspace(W1, Wa, precision, pipeline, volatile)
+    ws, ready, commit = _fused_workspace(W1, Wa, precision, pipeline, volatile)
     check(L.mil_abmil_fused_fwd_f32(ptr(x), N, D, H, ptr(W1), ptr(b1), ACT[act], ptr(Wa), ptr(ba), None, None, Da, ACT[att_act], ptr(wc),
                                     ptr(bc), ptr(keep), ptr(Wp), C, ptr(s), ptr(t), ptr(h), ptr(part), ptr(stats), ptr(pooled),
-                                    ptr(Wcls), ptr(bcls), ncls, ptr(logits), ptr(ws), ws.numel(), ready, PREC[precision] | (PIPELINES[pipeline] << 8),
-                                    stream_ptr()),
+                                    ptr(Wcls), ptr(bcls), ncls, ptr(logits), dropout.c() if dropout else None, ptr(ws), ws.numel(), ready,
+                                    PREC[precision] | (PIPELINES[pipeline] << 8), stream_ptr()),
           "mil_abmil_fused_fwd_f32")
+    commit()
     return {"pooled": pooled, "stats": stats, "s": s, "t": t, "h": h, "part": part, "logits": logits}
 
 

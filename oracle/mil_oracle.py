@@ -87,8 +87,9 @@ def merge_partials(ms: Sequence[Tensor], ls: Sequence[Tensor], Ps: Sequence[Tens
 # a1 / a2 : plain ABMIL heads
 # ----------------------------------------------------------------------------------------------
 def abmil_dattention(sd: SD, x: Tensor, act: str = "relu", return_attn: bool = False,
-                     return_act: bool = False, return_img_feat: bool = False):
-    """modules/abmil.py:203-251 (DAttention.forward), mil_norm=None, pos=None, dropout off.
+                     return_act: bool = False, return_img_feat: bool = False, drop_mask: Optional[Tensor] = None):
+    """modules/abmil.py:203-251 (DAttention.forward), mil_norm=None, pos=None.  drop_mask [N,512] (keep/(1-p), i.e. what
+    nn.Dropout(0.25) of `feature` (:188-189) multiplies by in train mode) or None for dropout off.
 
     feature (:213) -> attention Linear/Tanh/Linear (:229) -> softmax over N (:231-232) ->
     weighted sum (:234) -> classifier (:238).
@@ -98,6 +99,8 @@ def abmil_dattention(sd: SD, x: Tensor, act: str = "relu", return_attn: bool = F
     h = x[0]
     if "feature.0.weight" in sd:
         h = apply_act(affine(h, sd["feature.0.weight"], sd.get("feature.0.bias")), act)
+        if drop_mask is not None:
+            h = h * drop_mask.to(h.dtype)
     u = torch.tanh(affine(h, sd["attention.0.weight"], sd.get("attention.0.bias")))
     s = affine(u, sd["attention.2.weight"], sd.get("attention.2.bias"))[:, 0]
     p, a = softmax_pool(s, h)
@@ -527,9 +530,12 @@ def soft_target_ce(student: Tensor, teacher: Tensor, temp_t: float, temp_s: floa
     return (-(torch.softmax(teacher / temp_t, -1) * torch.log_softmax(student / temp_s, -1)).sum(-1)).mean()
 
 
-def mhim_embed(sd: SD, x: Tensor, act: str) -> Tensor:
-    """mhim.py:193/244/285/335: feature = Linear(D->512)+act on every row (dropout off)."""
-    return apply_act(affine(x[0], sd["feature.0.weight"], sd["feature.0.bias"]), act)
+def mhim_embed(sd: SD, x: Tensor, act: str, drop_mask: Optional[Tensor] = None) -> Tensor:
+    """mhim.py:193-194/244-245/285-286/335-336: feature = Linear(D->512)+act on every row, then `self.dp`: drop_mask [N,512]
+    holds keep/(1-p) (what nn.Dropout multiplies by in train mode; pinned against the live reference under a fixed torch seed in
+    tests/test_oracle_vs_reference.py), None = dropout off / eval."""
+    h = apply_act(affine(x[0], sd["feature.0.weight"], sd["feature.0.bias"]), act)
+    return h if drop_mask is None else h * drop_mask.to(h.dtype)
 
 
 def _encode(cfg: MHIMConfig, sd: SD, h: Tensor, return_attn=False, return_act=False, no_norm=False):
@@ -549,9 +555,9 @@ def _encode(cfg: MHIMConfig, sd: SD, h: Tensor, return_attn=False, return_act=Fa
     raise ValueError(cfg.baseline)
 
 
-def mhim_forward_teacher(cfg: MHIMConfig, sd: SD, x: Tensor):
+def mhim_forward_teacher(cfg: MHIMConfig, sd: SD, x: Tensor, drop_mask: Optional[Tensor] = None):
     """mhim.py:181-227 (merge_test=False): returns (cls_feat, score)."""
-    h = mhim_embed(sd, x, cfg.act)
+    h = mhim_embed(sd, x, cfg.act, drop_mask)
     if cfg.baseline == "dsmil":                                              # :202-205
         _, B, attn = _encode(cfg, sd, h, return_attn=True)
         return B, attn
@@ -588,9 +594,9 @@ def mhim_pure(cfg: MHIMConfig, sd: SD, x: Tensor):
 
 
 def mhim_forward(cfg: MHIMConfig, sd: SD, x: Tensor, attn: Tensor, teacher_cls_feat: Optional[Tensor],
-                 i: Optional[int] = None, training: bool = True):
+                 i: Optional[int] = None, training: bool = True, drop_mask: Optional[Tensor] = None):
     """mhim.py:318-378: the student pass.  Returns (logits, cls_loss, ps, len_keep, new_global_q, mask_ids)."""
-    h = mhim_embed(sd, x, cfg.act)
+    h = mhim_embed(sd, x, cfg.act, drop_mask)
     ps = h.shape[0]
     len_keep, ids = mhim_get_mask(cfg, ps, i, attn)                          # :341
     h = h[ids[0, :len_keep]]                                                 # :342

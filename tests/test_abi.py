@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(h, s), f"{s} declared in mhimk.h but not exported"
     h.mil_abi_version.restype = ctypes.c_int
-    assert h.mil_abi_version() == 1
+    assert h.mil_abi_version() == int(re.search(r"#define MIL_ABI_VERSION (\d+)", open(HEADER).read()).group(1)) == 2
 
 
 def test_python_binding_covers_the_header():
@@ -88,23 +88,32 @@ def test_weight_image_cache_policy(monkeypatch):
     monkeypatch.setattr(ops, "_ws", lambda nbytes, device: torch.empty(max(int(nbytes), 16), dtype=torch.uint8))
     monkeypatch.setattr(ops._lib, "lib", lambda: FakeLib())
     W1, Wa = torch.nn.Parameter(torch.randn(8, 4)), torch.nn.Parameter(torch.randn(2, 8))
-    ws, ready = ops._fused_workspace(W1, Wa, "bf16x3", "pair")
+    def use(**kw):                                                  # a successful kernel call: (ws, ready), images marked valid
+        ws, ready, commit = ops._fused_workspace(W1, Wa, "bf16x3", "pair", **kw)
+        commit()
+        return ws, ready
+
+    ws, ready, commit = ops._fused_workspace(W1, Wa, "bf16x3", "pair")
     assert ready == 0
-    ws2, ready = ops._fused_workspace(W1, Wa, "bf16x3", "pair")
+    # the C call failed (commit never ran): the next call must rebuild, not trust the unbuilt buffer
+    ws1, ready, commit = ops._fused_workspace(W1, Wa, "bf16x3", "pair")
+    assert ready == 0 and ws1 is ws
+    commit()
+    ws2, ready = use()
     assert ready == 1 and ws2 is ws
-    ws3, ready = ops._fused_workspace(W1, Wa, "bf16x3", "pair", volatile=True)
+    ws3, ready = use(volatile=True)
     assert ready == 0 and ws3 is ws
-    assert ops._fused_workspace(W1, Wa, "bf16x3", "pair")[1] == 1
+    assert use()[1] == 1
     W1.data.mul_(0.5)                                               # invisible to the version counter ...
-    assert ops._fused_workspace(W1, Wa, "bf16x3", "pair")[1] == 1
+    assert use()[1] == 1
     ops.weights_touched()                                           # ... hence the explicit notification
-    assert ops._fused_workspace(W1, Wa, "bf16x3", "pair")[1] == 0
-    assert ops._fused_workspace(W1, Wa, "bf16x3", "pair")[1] == 1
+    assert use()[1] == 0
+    assert use()[1] == 1
     MilModule().eval()                                              # a train()/eval() switch is such a notification
-    assert ops._fused_workspace(W1, Wa, "bf16x3", "pair")[1] == 0
+    assert use()[1] == 0
     with torch.no_grad():
         W1.mul_(2)                                                  # what optimizer.step() / load_state_dict do
-    ws4, ready = ops._fused_workspace(W1, Wa, "bf16x3", "pair")
+    ws4, ready = use()
     assert ready == 0 and ws4 is ws                                 # rebuilt in place, no new allocation per step
     # W^T copy for the tensor-core dX: one persistent buffer per live weight, refreshed in place
     Wt = ops._transposed(W1)

@@ -102,3 +102,40 @@ def test_transmil_and_milnet(R):
     rp, rc = d(x)
     op, oc, _, _ = O.milnet_forward(sd, x, "gelu")
     assert cases.rel_err(op, rp) <= 1e-6 and cases.rel_err(oc, rc) <= 1e-6
+
+
+@pytest.mark.parametrize("base,N", [("attn", 257), ("dsmil", 129)])
+def test_feature_dropout_mask_semantics(R, base, N):
+    """The reference's own training configuration (dropout=0.25, teacher kept in train(), engines/base_engine.py:36-37): with the
+    global torch seed fixed, `self.dp` draws exactly F.dropout(ones(1,N,512)) -- the oracle's `drop_mask` argument reproduces the
+    train-mode teacher and student passes of the live classes."""
+    d = 1536 if base == "dsmil" else 1024
+    kw = dict(cases.MHIM_KW, baseline=base, input_dim=d, dropout=0.25)
+    cfg = O.MHIMConfig(**dict(cases.MHIM_KW, baseline=base, input_dim=d))
+    sd_s, sd_t = cases.mhim_state(N, base, D=d), cases.mhim_state(N + 1, base, D=d)
+    stu, tea = R.mhim.MHIM(**kw), R.mhim.MHIM(**kw)
+    for m in (stu, tea):                                               # keep the feature dropout, neutralise the others (merge / attention)
+        for name, mod in m.named_modules():
+            if isinstance(mod, torch.nn.Dropout) and name != "dp":
+                mod.p = 0.0
+    stu.load_state_dict(sd_s, strict=True)
+    tea.load_state_dict(sd_t, strict=True)
+    stu.train(), tea.train()
+    x = cases.make_bag(N + 5, N, d)
+    torch.manual_seed(123)
+    ct, sc = tea.forward_teacher(x)
+    torch.manual_seed(123)
+    mask = torch.nn.functional.dropout(torch.ones(1, N, 512), 0.25, True)[0]
+    oct_, osc = O.mhim_forward_teacher(cfg, sd_t, x, drop_mask=mask)
+    assert cases.rel_err(oct_, ct) <= 1e-6 and cases.rel_err(osc, sc) <= 1e-6
+    assert 0.70 < float((mask > 0).float().mean()) < 0.80 and torch.all((mask == 0) | ((mask - 1 / 0.75).abs() < 1e-6))
+    tcf = ct[0] if base == "dsmil" else ct
+    torch.manual_seed(9)
+    lg, loss, ps, lk = stu(x, sc, tcf, i=0)
+    torch.manual_seed(9)
+    mask_s = torch.nn.functional.dropout(torch.ones(1, N, 512), 0.25, True)[0]      # the student's dp draws first (mhim.py:331-336)
+    olg, oloss, ops, olk, newq, ids = O.mhim_forward(cfg, sd_s, x, sc, tcf, i=0, training=True, drop_mask=mask_s)
+    pairs = zip(olg, lg) if base == "dsmil" else [(olg, lg)]
+    for a, b in pairs:
+        assert cases.rel_err(a, b) <= 1e-6
+    assert cases.rel_err(oloss, loss) <= 1e-6
