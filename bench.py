@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- patch-instances/s through the MIL aggregator at N=50 000 x D=1024 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16x3|fp16|bf16] [--pipeline single|pair]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp16x3|bf16x3|fp16|bf16] [--pipeline single|pair]
 
 One "step" = one pass of the hot path (abmil.DAttention eval forward: projection -> gated tanh attention logit ->
 softmax over N -> weighted pool -> classifier) over one synthetic bag of N=50 000 x D=1024 fp32 (204.8 MB).
@@ -71,17 +71,30 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
+CONFIG = {"workload": WORKLOAD}            # identical in both arms (the driver compares the dicts)
+
+
 def cpu_forward_fn():
-    """The CPU arm: the oracle restatement of abmil.DAttention.forward (the reference tree does not travel to the GPU box)."""
+    """The CPU arm: the reference's OWN abmil.DAttention class (unmodified files under oracle/_ref/, shipped to the box by
+    oracle/make_ref.py) when present -- kind "reference"; else the oracle restatement of its forward -- kind "port"."""
     import torch
     import cases
-    from oracle import mil_oracle as O
     sd = cases.abmil_state(2021)
-    return (lambda x: O.abmil_dattention(sd, x, "relu")), torch
+    try:
+        import _refload
+        if _refload.have_reference():
+            R = _refload.load_reference()
+            m = R.abmil.DAttention(D_IN, N_CLASSES, dropout=0.0, act="relu").eval()
+            m.load_state_dict(sd, strict=True)
+            return (lambda x: m(x)), torch, "reference", f"reference class modules/abmil.py:DAttention ({_refload.REF_ROOT})"
+    except Exception as e:                                   # e.g. torchvision missing on the box: fall back to the port, say so
+        print(f"bench.py: reference classes unavailable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+    from oracle import mil_oracle as O
+    return (lambda x: O.abmil_dattention(sd, x, "relu")), torch, "port", "oracle port of abmil.DAttention.forward"
 
 
 def time_cpu(n_rep, n_inst):
-    fn, torch = cpu_forward_fn()
+    fn, torch, kind, what = cpu_forward_fn()
     import cases
     torch.set_num_threads(os.cpu_count())
     x = cases.make_bag(2021, n_inst, D_IN)
@@ -93,21 +106,81 @@ def time_cpu(n_rep, n_inst):
             fn(x)
             ts.append(time.perf_counter() - t0)
     ts.sort()
-    return ts[len(ts) // 2]
+    return ts[len(ts) // 2], kind, what
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port; torch CPU, all host threads)."""
+    """--impl reference: the reference's own CPU implementation of the path (torch CPU, all host threads)."""
     if rank != 0:
         return
-    med = time_cpu(max(args.steps, 20), N_INST)
+    n_rep = max(args.steps, 20)
+    med, kind, what = time_cpu(n_rep, N_INST)
     val = N_INST / med
-    cb = {"value": val, "unit": "instances/s", "cores": os.cpu_count(), "kind": "port",
-          "sample": f"{max(args.steps, 20)} full bags of N={N_INST} (median), oracle port of abmil.DAttention.forward, torch CPU fp32, {os.cpu_count()} threads"}
+    cb = {"value": val, "unit": "instances/s", "cores": os.cpu_count(), "kind": kind,
+          "sample": f"{n_rep} full bags of N={N_INST} (median), {what}, torch CPU fp32, {os.cpu_count()} threads"}
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "instances/s", "n_gpus": args.gpus, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                      "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD}, "cpu_baseline": cb,
+                      "dtype": "f32", "data": "synthetic", "config": CONFIG, "cpu_baseline": cb,
                       "e2e": {"value": val, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def sharded_giant_bag(args, model, dev, rank, world, dist, torch, mhimk):
+    """BASELINE config 5 beside the headline (N > 1 only): ONE giant bag N = 200 000 x 1024 instance-sharded along N over the ranks;
+    per rank the fused pass on its rows, ONE all-gather of the 2056-byte record its tail wrote, one merge + classifier kernel.
+    Strong scaling: ms per bag (max over ranks), the share of it that is not the local fused kernel (exchange + merge + host), and
+    on rank 0 the same bag on one GPU for the speed-up."""
+    from mhimk import dist as D
+    n_giant, steps = 200000, max(10, min(args.steps, 30))
+    lo, hi = D.row_slices(n_giant, world)[rank]
+    shards = [torch.randn(hi - lo, D_IN, device=dev, generator=torch.Generator(device=dev).manual_seed(99 + rank + 100 * i)) for i in range(3)]
+
+    def step(i):
+        return D.sharded_abmil_forward(model, shards[i % 3])[0]
+
+    for i in range(5):
+        step(i)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    mhimk.ops.profile_fused(True)
+    for i in range(steps):
+        step(i)
+    torch.cuda.synchronize()
+    n_t, k_tot = mhimk.ops.profile_collect()
+    mhimk.ops.profile_fused(False)
+    t = torch.tensor([ms, k_tot / max(n_t, 1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, kernel_ms = (float(v) for v in t.tolist())
+    del shards
+    single_ms = None
+    if rank == 0:                                            # the same giant bag on ONE GPU (819 MB), for the strong-scaling ratio
+        full = torch.randn(1, n_giant, D_IN, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+        with torch.no_grad():
+            for _ in range(3):
+                model(full)
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(10):
+                model(full)
+            s1.record()
+            torch.cuda.synchronize()
+        single_ms = s0.elapsed_time(s1) / 10
+        del full
+    dist.barrier()
+    return {"workload": f"abmil.DAttention eval forward, ONE giant bag N={n_giant} x D={D_IN}, instance-sharded along N x{world}",
+            "scaling": "strong", "ms_per_bag": ms, "instances_per_s": n_giant / (ms * 1e-3), "steps": steps,
+            "local_fused_kernel_ms": kernel_ms, "exchange_overhead_us": (ms - kernel_ms) * 1e3,
+            "single_gpu_ms_per_bag": single_ms, "speedup_vs_single_gpu": (single_ms / ms) if single_ms else None,
+            "collective": "one ncclAllGather of (m, l, P[512]) = 2056 B per rank on the compute stream, then mil_shard_merge_cls_f32; latency-bound",
+            "launches_per_rank_per_bag": 3}
 
 
 def main():
@@ -116,7 +189,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp16", "bf16"])
+    ap.add_argument("--precision", default="bf16x3", choices=["fp16x3", "bf16x3", "fp16", "bf16"])
     ap.add_argument("--pipeline", default="auto", choices=["auto", "single", "pair"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -213,6 +286,11 @@ def main():
     sampler.join(timeout=2)
     e2e_ms = e2.elapsed_time(e3)
 
+    # free the headline buffers, then the instance-sharded giant bag (N > 1 only)
+    del bags, host, dbufs
+    torch.cuda.empty_cache()
+    sharded = sharded_giant_bag(args, model, dev, rank, world, dist, torch, mhimk) if world > 1 else None
+
     t = torch.tensor([total_ms, e2e_ms, kernel_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -229,15 +307,16 @@ def main():
         if os.path.isfile(tp):
             traffic = json.load(open(tp)).get(args.precision)
         # the binding bound of the pass: the two contractions run on the tensor cores, x3 in the hi/lo-split parity arithmetic
-        nprod = 3 if args.precision == "bf16x3" else 1
+        nprod = 3 if args.precision in ("bf16x3", "fp16x3") else 1
         flops = (2.0 * D_IN * 512 + 2.0 * 512 * 128) * N_INST * nprod
         tpeak, tsus, tsrc = tensor_peaks()
         tflops = flops / (kernel_ms * 1e-3) / 1e12
         out = {"metric": METRIC, "value": value, "unit": "instances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "precision": args.precision, "pipeline": args.pipeline,
-               "config": {"workload": WORKLOAD, "parallelism": f"bag-parallel x{world}", "l2": "4 distinct 205 MB bags round-robin (> 126 MB L2)",
-                          "operand_arithmetic": {"bf16x3": "bf16 hi+lo split, 3 tcgen05 products, fp32 accumulate", "fp16": "single fp16 product",
+               "config": CONFIG,
+               "detail": {"parallelism": f"bag-parallel x{world}", "l2": "4 distinct 205 MB bags round-robin (> 126 MB L2)",
+                          "operand_arithmetic": {"fp16x3": "fp16 hi+lo split, 3 tcgen05 products, fp32 accumulate", "bf16x3": "bf16 hi+lo split, 3 tcgen05 products, fp32 accumulate", "fp16": "single fp16 product",
                                                  "bf16": "single bf16 product"}[args.precision]},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                             "peak_source": peak_src, "kernel_ms": kernel_ms, "alg_bytes": alg_bytes,
@@ -247,14 +326,18 @@ def main():
                                    "note": "issued tensor-core FLOPs of the two contractions (D->512, 512->128) x products per operand pair; the 3-product "
                                            "parity arithmetic is tensor-bound (<= ~29 % of the HBM roofline at the measured peaks), see DESIGN.md 4.1"},
                "e2e": {"value": world * N_INST / (e2e_ms / e2e_steps * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": alg_bytes,
-                       "d2h_bytes_per_step": N_CLASSES * 4, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
+                       "d2h_bytes_per_step": N_CLASSES * 4, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                       "h2d_gbs_per_rank": alg_bytes / (e2e_ms / e2e_steps * 1e-3) / 1e9, "h2d_gbs_aggregate": world * alg_bytes / (e2e_ms / e2e_steps * 1e-3) / 1e9,
+                       "note": "PCIe-bound: the pinned-host -> HBM copy of the 204.8 MB bag is the step; all ranks copy concurrently"},
                "gpu_launches": args.steps,                # per step: ONE fused kernel (merge + classifier in its tail; weight images cached)
                "clocks": sampler.summary()}
         if not args.no_cpu_baseline and world == 1:        # rank 0 at N=1 only: at N>1 the other ranks' host threads would distort it
             n_cpu = 250                                    # bounded sample: ~10 s of CPU work on the box's host cores
-            med = time_cpu(n_cpu, N_INST)
-            out["cpu_baseline"] = {"value": N_INST / med, "unit": "instances/s", "cores": os.cpu_count(), "kind": "port",
-                                   "sample": f"{n_cpu} full bags of N={N_INST} (median {med * 1e3:.1f} ms), oracle port of abmil.DAttention.forward, torch CPU fp32, all host threads"}
+            med, kind, what = time_cpu(n_cpu, N_INST)
+            out["cpu_baseline"] = {"value": N_INST / med, "unit": "instances/s", "cores": os.cpu_count(), "kind": kind,
+                                   "sample": f"{n_cpu} full bags of N={N_INST} (median {med * 1e3:.1f} ms), {what}, torch CPU fp32, all host threads"}
+        if sharded is not None:
+            out["sharded"] = sharded
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -32,7 +32,10 @@ enum {
   MIL_PREC_BF16X3 = 0, /* x = hi + lo (bf16), 3 tcgen05 products, fp32 accumulate: fp32-class (parity mode) */
   MIL_PREC_FP16   = 1, /* single fp16 product, fp32 accumulate: TF32-class (the reference's own GPU numerics,
                           main.py:435 enables TF32) */
-  MIL_PREC_BF16   = 2  /* single bf16 product (fastest, ~2^-9 operand rounding) */
+  MIL_PREC_BF16   = 2, /* single bf16 product (fastest, ~2^-9 operand rounding) */
+  MIL_PREC_FP16X3 = 3  /* x = hi + lo (fp16), 3 tcgen05 products, fp32 accumulate: unit roundoff ~2^-22 (bf16x3: 2^-17) at the same
+                          cost -- ReLU gates flip ~30x less often against an fp32 reference.  Operands must stay inside fp16's range:
+                          |x| <= 65504 (larger values saturate); weight images are built from 16 W (exact), undone in the epilogue. */
 };
 
 /* pipeline of the fused pass, OR-ed into `precision` as (pipeline << 8); 0 = library default (the pair pipeline) */
@@ -86,6 +89,8 @@ int         mil_device_supported(void);
  * part      float[n_part,(2+H)] scratch for the per-CTA partials, n_part = mil_fused_num_partials() (one record more than
  *           CTAs are launched: the bulk copies of the in-kernel merge round up to 16 bytes).
  * stats     float[2] = (m, l); pooled float[H]: written by the last CTA to finish (in-kernel log-sum-exp merge of the partials).
+ * rec_out   nullable float[2+H] = (m, l, P[H] = l * pooled): the record an instance-sharded bag exchanges (one all-gather, then
+ *           mil_shard_merge_cls_f32), written by the same tail -- no extra launch.
  * logits    nullable float[n_cls] = Wcls pooled + bcls (classifier fused into the same tail; replaces abmil.py:238 /
  *           mhim.py:267); Wcls [n_cls, H], bcls nullable.
  * ws / ws_bytes: scratch of at least mil_fused_workspace_bytes(D, H, Da, gated) bytes; it holds the 16-bit hi/lo images of
@@ -99,7 +104,7 @@ int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H,
                             const float* wc, const float* bc,
                             const uint8_t* keep, const float* Wp, int C,
                             float* s_out, float* t_out, float* h_out,
-                            float* part, float* stats, float* pooled,
+                            float* part, float* stats, float* pooled, float* rec_out,
                             const float* Wcls, const float* bcls, int n_cls, float* logits, const mil_dropout_t* drop,
                             void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream);
 int    mil_fused_num_partials(void);
@@ -133,6 +138,30 @@ int    mil_linear_act_tc_f32(const float* X, int64_t M, int K, const float* W, c
                              void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream);
 size_t mil_linear_tc_workspace_bytes(int N, int K);
 
+/* Skinny Linear layers (GEMV-shaped), forward and backward, exact fp32 streaming kernels: Y[M,N] = act(X[M,K] W[N,K]^T + b) with
+ * N <= 8 outputs over many rows (attention logit 128 -> 1: abmil.py:196, baseline.py:27; DSMIL instance classifier / critical-instance
+ * logits: dsmil.py:62,93) or M <= 8 rows (classifier / predictor on the pooled vector: abmil.py:238, mhim.py:267; Merge's to_q / to_out:
+ * merge.py:35-41; q(h_crit): dsmil.py:92).  K <= 1536.  mil_skinny_supported: 0 = no, 1 = "thin" (N <= 8), 2 = "short" (M <= 8).
+ * X has leading dimension ldx; pre_out nullable (pre-activation, for the gelu backward).
+ * Backward: G = dL/d(pre-activation) [M,N]; any of dW [N,K], db [N] (only together with dW), dX [M,K] may be NULL.
+ * ws >= mil_skinny_workspace_bytes(M, N, K) (row-slice partials of the thin weight gradient, reduced in a fixed order). */
+int    mil_skinny_supported(int64_t M, int N, int K);
+int    mil_skinny_fwd_f32(const float* X, int64_t ldx, int64_t M, int K, const float* W, const float* b, int N, int act,
+                          float* pre_out, float* Y, mil_stream_t stream);
+int    mil_skinny_bwd_f32(const float* G, const float* X, int64_t ldx, const float* W, int64_t M, int N, int K,
+                          float* dW, float* db, float* dX, void* ws, size_t ws_bytes, mil_stream_t stream);
+size_t mil_skinny_workspace_bytes(int64_t M, int N, int K);
+
+/* Weight (and bias) gradient of an N-row Linear on the tensor cores: dW[n,k] = sum_m G[m,n] X[m,k], db[n] = sum_m G[m,n]
+ * (db nullable).  G [M, Nn] (leading dimension ldg), X [M, K] (ldx), fp32 row-major, 16-byte aligned; Nn % 128 == 0, K % 256 == 0.
+ * bf16 hi+lo split, 3 tcgen05 products, fp32 accumulation (fp32-class); the instance range is cut into slices whose partial
+ * sums are added in a fixed order (deterministic).  ws >= mil_wgrad_tc_workspace_bytes(M, Nn, K).
+ * Replaces the autograd weight gradient of every N-row nn.Linear on the path (abmil.py:213, mhim.py:193/335, baseline.py:15,27,
+ * dsmil.py:62-70, nystrom_attention.py:52-57, merge.py:35-41) -- the dW1 = sum_n g_pre^T x reduction of SURVEY 9.2. */
+int    mil_wgrad_tc_f32(const float* G, int64_t ldg, const float* X, int64_t ldx, int64_t M, int Nn, int K, float* dW, float* db,
+                        void* ws, size_t ws_bytes, mil_stream_t stream);
+size_t mil_wgrad_tc_workspace_bytes(int64_t M, int Nn, int K);
+
 /* g_pre = g_y * act'(.) elementwise; `y_or_pre` is the activation OUTPUT for relu/tanh/sigmoid and the
  * PRE-activation for gelu.  n elements.  (autograd of nn.ReLU/GELU/Tanh/Sigmoid on the path) */
 int mil_act_bwd_f32(const float* g_y, const float* y_or_pre, int64_t n, int act, float* g_pre, mil_stream_t stream);
@@ -164,6 +193,12 @@ int mil_softmax_pool_bwd_f32(const float* s, int64_t s_stride, const float* h, i
  * Used for the per-CTA partials of one GPU and for the per-rank partials of an instance-sharded bag
  * (SURVEY.md §9.3); entries with l_i == 0 are ignored. */
 int mil_pool_merge_f32(const float* part, int n_part, int H, float* stats, float* pooled, mil_stream_t stream);
+
+/* Instance-sharded bag (BASELINE config 5): merge the n_rec gathered records (m_g, l_g, P_g[H]) of the ranks AND apply the classifier
+ * in ONE launch: stats = (m, l), pooled = sum_g P_g e^{m_g - m} / l, logits = Wcls pooled + bcls (nullable Wcls -> no logits).
+ * Records with l_g == 0 (ranks without rows) are ignored; n_rec <= 1024; fixed summation order -> identical on every rank. */
+int mil_shard_merge_cls_f32(const float* rec, int n_rec, int H, const float* Wcls, const float* bcls, int n_cls,
+                            float* stats, float* pooled, float* logits, mil_stream_t stream);
 
 /* Teacher attention -> score.  Replaces modules/mhim_modules/scoring.py:37-58 (get_pseudo_score):
  * score_n = max_c softmax_c( a_n * t_{n,c} + bias0 ), a_n = exp(s_n - m)/l, t = h Wp^T given as float[L,C]. */

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libmhimk.so")
 ABI_VERSION = 2
 
 ACT = {"none": 0, None: 0, "relu": 1, "gelu": 2, "tanh": 3, "sigmoid": 4}
-PREC = {"bf16x3": 0, "fp16": 1, "bf16": 2}
+PREC = {"bf16x3": 0, "fp16": 1, "bf16": 2, "fp16x3": 3}
 
 
 
@@ -29,7 +29,7 @@ _SIGS = {
     "mil_device_supported": (c_int, []),
     "mil_abmil_fused_fwd_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "mil_dropout_bits": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "mil_profile_enable": (None, [c_int]),
     "mil_profile_collect": (c_int, [ctypes.POINTER(ctypes.c_double)]),
@@ -40,6 +40,12 @@ _SIGS = {
     "mil_linear_act_tc_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                       c_int, c_int, c_void_p]),
     "mil_linear_tc_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "mil_skinny_supported": (c_int, [c_int64, c_int, c_int]),
+    "mil_skinny_fwd_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mil_skinny_bwd_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mil_skinny_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "mil_wgrad_tc_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mil_wgrad_tc_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "mil_act_bwd_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "mil_act_bwd_drop_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mil_colsum_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -48,6 +54,7 @@ _SIGS = {
     "mil_softmax_pool_bwd_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                          c_void_p, c_int, c_void_p]),
     "mil_pool_merge_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mil_shard_merge_cls_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mil_cam_score_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_float, c_void_p, c_void_p]),
     "mil_cam_score_dev_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mil_ema_update_f32": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p]),

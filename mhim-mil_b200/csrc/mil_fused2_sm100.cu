@@ -328,7 +328,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             hi[i] = pack_hi<FP16>(x[2 * i], x[2 * i + 1]);
-            lo[i] = pack_lo_bf16(x[2 * i], x[2 * i + 1], hi[i]);
+            lo[i] = pack_lo<FP16>(x[2 * i], x[2 * i + 1], hi[i]);
           }
           mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 11);
           if (tid == 0) kstamp(p, 3, it);
@@ -428,7 +428,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           tmem_ld32f(tb + (uint32_t)(j * 32), keep_h[j]);
-          bias_act32<ACT>(keep_h[j], c_b1 + f0 + j * 32, p.act);
+          bias_act32<ACT>(keep_h[j], c_b1 + f0 + j * 32, p.act, p.w1_inv);
           if (p.drop_mode) drop_apply32(keep_h[j], drop_keep_word(p, grow, (f0 >> 5) + j, HMAX / 32), p.drop_scale);
         }
         tc_fence_before();
@@ -474,7 +474,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       for (int j = (half == 0 ? 2 : 0); j < 4; ++j) {
         float hv[32];
         tmem_ld32f(tb + (uint32_t)(j * 32), hv);
-        bias_act32<ACT>(hv, c_b1 + f0 + j * 32, p.act);
+        bias_act32<ACT>(hv, c_b1 + f0 + j * 32, p.act, p.w1_inv);
         if (p.drop_mode) drop_apply32(hv, drop_keep_word(p, grow, (f0 >> 5) + j, HMAX / 32), p.drop_scale);
         tmem_st32f(tb + (uint32_t)(j * 32), hv);
         emit_chunk(j, hv);
@@ -491,7 +491,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const int da0 = g * 64 + half * 32;
         float uv[32];
         tmem_ld32f(tq + b * 256 + (uint32_t)(half * 32), uv);
-        bias_act32<ATT>(uv, c_ba + da0, p.att_act);
+        bias_act32<ATT>(uv, c_ba + da0, p.att_act, p.wa_inv);
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -601,15 +601,16 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 //           strips produce A2 tiles); for chunk c, CTA rank, operand op: the 64 rows rank*64 + [0,64) (4 KB); order (c, rank, op).
 // ------------------------------------------------------------------------------------------------------------
 template <bool FP16, bool LO>
-__global__ void pair_split_w1_kernel(const float* __restrict__ w, int H, int K, uint8_t* __restrict__ img, int ksub) {
+__global__ void pair_split_w1_kernel(const float* __restrict__ w, int H, int K, uint8_t* __restrict__ img, int ksub, float scale) {
   const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (row f, 16-byte chunk kc = k / 8)
   const int kchunks = K / 8;
   if (item >= (int64_t)H * kchunks) return;
   const int f = (int)(item / kchunks), kc = (int)(item % kchunks);
   const int ks = kc >> 2, c = kc & 3;
   const int blk = f >> 8, rank = (f >> 7) & 1, r = f & 127;
-  const float4 a = *reinterpret_cast<const float4*>(w + (int64_t)f * K + kc * 8);
-  const float4 b = *reinterpret_cast<const float4*>(w + (int64_t)f * K + kc * 8 + 4);
+  float4 a = *reinterpret_cast<const float4*>(w + (int64_t)f * K + kc * 8);
+  float4 b = *reinterpret_cast<const float4*>(w + (int64_t)f * K + kc * 8 + 4);
+  a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale; b.x *= scale; b.y *= scale; b.z *= scale; b.w *= scale;
   uint32_t h[4], l[4];
   h[0] = pack_hi<FP16>(a.x, a.y); h[1] = pack_hi<FP16>(a.z, a.w); h[2] = pack_hi<FP16>(b.x, b.y); h[3] = pack_hi<FP16>(b.z, b.w);
   constexpr int NOPK = LO ? 2 : 1;
@@ -617,13 +618,13 @@ __global__ void pair_split_w1_kernel(const float* __restrict__ w, int H, int K, 
   uint8_t* dst = img + ((size_t)(((ks / ksub) * 2 + rank) * ksub + ks % ksub) * NOPK) * 16384 + (size_t)blk * 8192 + off;
   *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
   if (LO) {
-    l[0] = pack_lo_bf16(a.x, a.y, h[0]); l[1] = pack_lo_bf16(a.z, a.w, h[1]); l[2] = pack_lo_bf16(b.x, b.y, h[2]); l[3] = pack_lo_bf16(b.z, b.w, h[3]);
+    l[0] = pack_lo<FP16>(a.x, a.y, h[0]); l[1] = pack_lo<FP16>(a.z, a.w, h[1]); l[2] = pack_lo<FP16>(b.x, b.y, h[2]); l[3] = pack_lo<FP16>(b.z, b.w, h[3]);
     *reinterpret_cast<uint4*>(dst + 16384) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
 template <bool FP16, bool LO>
-__global__ void pair_split_wa_kernel(const float* __restrict__ w, int Da, int K, uint8_t* __restrict__ img) {
+__global__ void pair_split_wa_kernel(const float* __restrict__ w, int Da, int K, uint8_t* __restrict__ img, float scale) {
   const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (row d, 16-byte chunk kc)
   const int kchunks = K / 8;
   if (item >= (int64_t)Da * kchunks) return;
@@ -632,8 +633,9 @@ __global__ void pair_split_wa_kernel(const float* __restrict__ w, int Da, int K,
   const int half = fi >> 3, g = (fi >> 2) & 1, j = fi & 3;
   const int chunk = 4 * j + half * 2 + g;
   const int rank = d >> 6, r = d & 63;
-  const float4 a = *reinterpret_cast<const float4*>(w + (int64_t)d * K + kc * 8);
-  const float4 b = *reinterpret_cast<const float4*>(w + (int64_t)d * K + kc * 8 + 4);
+  float4 a = *reinterpret_cast<const float4*>(w + (int64_t)d * K + kc * 8);
+  float4 b = *reinterpret_cast<const float4*>(w + (int64_t)d * K + kc * 8 + 4);
+  a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale; b.x *= scale; b.y *= scale; b.z *= scale; b.w *= scale;
   uint32_t h[4], l[4];
   h[0] = pack_hi<FP16>(a.x, a.y); h[1] = pack_hi<FP16>(a.z, a.w); h[2] = pack_hi<FP16>(b.x, b.y); h[3] = pack_hi<FP16>(b.z, b.w);
   constexpr int NOPK = LO ? 2 : 1;
@@ -642,7 +644,7 @@ __global__ void pair_split_wa_kernel(const float* __restrict__ w, int Da, int K,
   uint8_t* dst = img + ((size_t)((chunk / GSK) * 2 + rank) * GSK + (size_t)(chunk % GSK)) * NOPK * 4096 + off;
   *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
   if (LO) {
-    l[0] = pack_lo_bf16(a.x, a.y, h[0]); l[1] = pack_lo_bf16(a.z, a.w, h[1]); l[2] = pack_lo_bf16(b.x, b.y, h[2]); l[3] = pack_lo_bf16(b.z, b.w, h[3]);
+    l[0] = pack_lo<FP16>(a.x, a.y, h[0]); l[1] = pack_lo<FP16>(a.z, a.w, h[1]); l[2] = pack_lo<FP16>(b.x, b.y, h[2]); l[3] = pack_lo<FP16>(b.z, b.w, h[3]);
     *reinterpret_cast<uint4*>(dst + 4096) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
@@ -669,6 +671,7 @@ template <int ACT, int ATT>
 static int dispatch_prec(int precision, const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mwa, const FusedParams& p, int grid,
                          cudaStream_t stream) {
   if (precision == MIL_PREC_BF16X3) return launch_pair<3, false, 3, 4, 1, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
+  if (precision == MIL_PREC_FP16X3) return launch_pair<3, true, 3, 4, 1, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
   if (p.D % 64 == 0) {
     if (precision == MIL_PREC_FP16) return launch_pair<1, true, 3, 4, 2, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
     return launch_pair<1, false, 3, 4, 2, ACT, ATT>(mx, mw1, mwa, p, grid, stream);
@@ -680,7 +683,7 @@ static int dispatch_prec(int precision, const CUtensorMap& mx, const CUtensorMap
 }  // namespace pairk
 
 // 64-wide stages (two 32-wide sub-steps) for the single-product modes when D allows; the 3-product mode has no room for them
-static int pair_ksub(int precision, int D) { return (precision != MIL_PREC_BF16X3 && D % 64 == 0) ? 2 : 1; }
+static int pair_ksub(int precision, int D) { return (!prec_split(precision) && D % 64 == 0) ? 2 : 1; }
 
 size_t pair_weight_image_bytes(int D, int H, int Da) { return ((size_t)H * D + (size_t)Da * H) * 2 * sizeof(uint16_t); }
 
@@ -688,15 +691,19 @@ int pair_build_images(const float* W1, int H, int D, const float* Wa, int Da, ui
   using namespace pairk;
   const int64_t i1 = (int64_t)H * (D / 8), i2 = (int64_t)Da * (H / 8);
   const unsigned b1 = (unsigned)((i1 + 255) / 256), b2 = (unsigned)((i2 + 255) / 256);
+  const float sc = prec_wscale(precision);
   if (precision == MIL_PREC_BF16X3) {
-    pair_split_w1_kernel<false, true><<<b1, 256, 0, stream>>>(W1, H, D, w1_img, pair_ksub(precision, D));
-    pair_split_wa_kernel<false, true><<<b2, 256, 0, stream>>>(Wa, Da, H, wa_img);
+    pair_split_w1_kernel<false, true><<<b1, 256, 0, stream>>>(W1, H, D, w1_img, pair_ksub(precision, D), sc);
+    pair_split_wa_kernel<false, true><<<b2, 256, 0, stream>>>(Wa, Da, H, wa_img, sc);
+  } else if (precision == MIL_PREC_FP16X3) {
+    pair_split_w1_kernel<true, true><<<b1, 256, 0, stream>>>(W1, H, D, w1_img, pair_ksub(precision, D), sc);
+    pair_split_wa_kernel<true, true><<<b2, 256, 0, stream>>>(Wa, Da, H, wa_img, sc);
   } else if (precision == MIL_PREC_FP16) {
-    pair_split_w1_kernel<true, false><<<b1, 256, 0, stream>>>(W1, H, D, w1_img, pair_ksub(precision, D));
-    pair_split_wa_kernel<true, false><<<b2, 256, 0, stream>>>(Wa, Da, H, wa_img);
+    pair_split_w1_kernel<true, false><<<b1, 256, 0, stream>>>(W1, H, D, w1_img, pair_ksub(precision, D), sc);
+    pair_split_wa_kernel<true, false><<<b2, 256, 0, stream>>>(Wa, Da, H, wa_img, sc);
   } else {
-    pair_split_w1_kernel<false, false><<<b1, 256, 0, stream>>>(W1, H, D, w1_img, pair_ksub(precision, D));
-    pair_split_wa_kernel<false, false><<<b2, 256, 0, stream>>>(Wa, Da, H, wa_img);
+    pair_split_w1_kernel<false, false><<<b1, 256, 0, stream>>>(W1, H, D, w1_img, pair_ksub(precision, D), sc);
+    pair_split_wa_kernel<false, false><<<b2, 256, 0, stream>>>(Wa, Da, H, wa_img, sc);
   }
   MIL_LAUNCH_CHECK();
   return 0;
@@ -705,7 +712,7 @@ int pair_build_images(const float* W1, int H, int D, const float* Wa, int Da, ui
 // p: every field of the fused pass filled in by the caller (mil_abmil_fused_fwd_f32), w1_img / wa_img in the pair layout.
 int pair_fused_launch(const float* X, FusedParams p, int precision, cudaStream_t stream) {
   using namespace pairk;
-  const int NOP = precision == MIL_PREC_BF16X3 ? 2 : 1;
+  const int NOP = prec_split(precision) ? 2 : 1;
   CUtensorMap mx, mw1, mwa;
   int rc;
   if ((rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)p.N, (uint64_t)p.D, BMC, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;

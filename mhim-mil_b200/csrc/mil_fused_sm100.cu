@@ -335,7 +335,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
           float hv[32];
           tmem_ld32f(tq + (uint32_t)(c * 32), hv);
           if (p.h_out) {                                      // pre-activation (needed by the GELU backward)
-            bias_act32<MIL_ACT_NONE>(hv, c_b1 + c * 32, 0);
+            bias_act32<MIL_ACT_NONE>(hv, c_b1 + c * 32, 0, p.w1_inv);
             if (grow < p.N) {
               float* dst = p.h_out + grow * p.ldc + c * 32;
 #pragma unroll
@@ -343,7 +343,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
             }
             bias_act32<-1>(hv, c_zero, p.act);
           } else {
-            bias_act32<-1>(hv, c_b1 + c * 32, p.act);
+            bias_act32<-1>(hv, c_b1 + c * 32, p.act, p.w1_inv);
           }
           if (p.drop_mode) drop_apply32(hv, drop_keep_word(p, grow, c, nch), p.drop_scale);
           if (grow < p.N) {
@@ -375,7 +375,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
         for (int j = 0; j < 2; ++j) {
           const int c = 2 * j + half;
           tmem_ld32f(tq + (uint32_t)(c * 32), keep_h[j]);
-          bias_act32<ACT>(keep_h[j], c_b1 + c * 32, p.act);
+          bias_act32<ACT>(keep_h[j], c_b1 + c * 32, p.act, p.w1_inv);
           if (p.drop_mode) drop_apply32(keep_h[j], drop_keep_word(p, grow, c, HMAX / 32), p.drop_scale);
         }
         tc_fence_before();
@@ -418,7 +418,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
           const int c = 2 * j + half;
           float hv[32];
           tmem_ld32f(tq + (uint32_t)(c * 32), hv);
-          bias_act32<ACT>(hv, c_b1 + c * 32, p.act);
+          bias_act32<ACT>(hv, c_b1 + c * 32, p.act, p.w1_inv);
           if (p.drop_mode) drop_apply32(hv, drop_keep_word(p, grow, c, HMAX / 32), p.drop_scale);
           tmem_st32f(tq + (uint32_t)(c * 32), hv);
           emit_chunk(c, hv);
@@ -436,7 +436,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
           const int c0 = half * 64 + j * 32;
           float uv[32];
           tmem_ld32f(tq + (uint32_t)c0, uv);
-          bias_act32<ATT>(uv, c_ba + c0, p.att_act);
+          bias_act32<ATT>(uv, c_ba + c0, p.att_act, p.wa_inv);
           float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
@@ -549,14 +549,15 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
 //   c = 16-byte chunk (8 elements) inside the 64-byte row.  One thread converts one (row, chunk).
 // ------------------------------------------------------------------------------------------------------------
 template <bool FP16, bool LO>
-__global__ void split_weights_kernel(const float* __restrict__ w, int R, int K, uint8_t* __restrict__ img) {
+__global__ void split_weights_kernel(const float* __restrict__ w, int R, int K, uint8_t* __restrict__ img, float scale) {
   const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (r, kc): kc = k / 8
   const int kchunks = K / 8;
   if (item >= (int64_t)R * kchunks) return;
   const int r = (int)(item / kchunks), kc = (int)(item % kchunks);
   const int ks = kc >> 2, c = kc & 3;
-  const float4 a = *reinterpret_cast<const float4*>(w + (int64_t)r * K + kc * 8);
-  const float4 b = *reinterpret_cast<const float4*>(w + (int64_t)r * K + kc * 8 + 4);
+  float4 a = *reinterpret_cast<const float4*>(w + (int64_t)r * K + kc * 8);
+  float4 b = *reinterpret_cast<const float4*>(w + (int64_t)r * K + kc * 8 + 4);
+  a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale; b.x *= scale; b.y *= scale; b.z *= scale; b.w *= scale;
   uint32_t h[4], l[4];
   h[0] = pack_hi<FP16>(a.x, a.y); h[1] = pack_hi<FP16>(a.z, a.w); h[2] = pack_hi<FP16>(b.x, b.y); h[3] = pack_hi<FP16>(b.z, b.w);
   constexpr int NOPK = LO ? 2 : 1;
@@ -565,7 +566,7 @@ __global__ void split_weights_kernel(const float* __restrict__ w, int R, int K, 
   uint8_t* dst = img + (size_t)ks * NOPK * tile + off;
   *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
   if (LO) {
-    l[0] = pack_lo_bf16(a.x, a.y, h[0]); l[1] = pack_lo_bf16(a.z, a.w, h[1]); l[2] = pack_lo_bf16(b.x, b.y, h[2]); l[3] = pack_lo_bf16(b.z, b.w, h[3]);
+    l[0] = pack_lo<FP16>(a.x, a.y, h[0]); l[1] = pack_lo<FP16>(a.z, a.w, h[1]); l[2] = pack_lo<FP16>(b.x, b.y, h[2]); l[3] = pack_lo<FP16>(b.z, b.w, h[3]);
     *reinterpret_cast<uint4*>(dst + tile) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
@@ -587,18 +588,23 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                       uint32_t box_cols, CUtensorMapSwizzle sw) {
+int make_map_2d_ld(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                   uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle sw) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -2; }
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstr[1] = {cols * (uint64_t)elem_bytes};
+  cuuint64_t gstr[1] = {ld * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu box=%ux%u)", (int)r, (unsigned long long)rows, (unsigned long long)cols, box_rows, box_cols); return -3; }
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)", (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols); return -3; }
   return 0;
+}
+
+int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                       uint32_t box_cols, CUtensorMapSwizzle sw) {
+  return make_map_2d_ld(m, dt, elem_bytes, base, rows, cols, cols, box_rows, box_cols, sw);
 }
 
 // optional kernel-only timing (bench.py roofline): CUDA events recorded on the launching stream around the fused kernel
@@ -651,6 +657,7 @@ static int grid_override(int grid) {
 template <int MODE, int ACT, int ATT>
 static int dispatch_prec(int precision, const CUtensorMap& mx, const FusedParams& p, int grid, cudaStream_t stream) {
   if (precision == MIL_PREC_BF16X3) return launch_fused<3, false, 2, MODE, ACT, ATT>(mx, p, grid, stream);
+  if (precision == MIL_PREC_FP16X3) return launch_fused<3, true, 2, MODE, ACT, ATT>(mx, p, grid, stream);
   if (precision == MIL_PREC_FP16) return launch_fused<1, true, 4, MODE, ACT, ATT>(mx, p, grid, stream);
   return launch_fused<1, false, 4, MODE, ACT, ATT>(mx, p, grid, stream);
 }
@@ -696,9 +703,11 @@ __global__ void dropout_bits_kernel(int64_t words, int words_per_row, uint32_t t
 static int split_weights(const float* w, int R, int K, uint8_t* img, int precision, cudaStream_t stream) {
   const int64_t items = (int64_t)R * (K / 8);
   const unsigned blocks = (unsigned)((items + 255) / 256);
-  if (precision == MIL_PREC_BF16X3) split_weights_kernel<false, true><<<blocks, 256, 0, stream>>>(w, R, K, img);
-  else if (precision == MIL_PREC_FP16) split_weights_kernel<true, false><<<blocks, 256, 0, stream>>>(w, R, K, img);
-  else split_weights_kernel<false, false><<<blocks, 256, 0, stream>>>(w, R, K, img);
+  const float sc = prec_wscale(precision);
+  if (precision == MIL_PREC_BF16X3) split_weights_kernel<false, true><<<blocks, 256, 0, stream>>>(w, R, K, img, sc);
+  else if (precision == MIL_PREC_FP16X3) split_weights_kernel<true, true><<<blocks, 256, 0, stream>>>(w, R, K, img, sc);
+  else if (precision == MIL_PREC_FP16) split_weights_kernel<true, false><<<blocks, 256, 0, stream>>>(w, R, K, img, sc);
+  else split_weights_kernel<false, false><<<blocks, 256, 0, stream>>>(w, R, K, img, sc);
   MIL_LAUNCH_CHECK();
   return 0;
 }
@@ -746,7 +755,7 @@ extern "C" size_t mil_fused_workspace_bytes(int D, int H, int Da, int gated) {
 extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, const float* W1, const float* b1, int act, const float* Wa,
                                        const float* ba, const float* Wb, const float* bb, int Da, int att_act, const float* wc, const float* bc,
                                        const uint8_t* keep, const float* Wp, int C, float* s_out, float* t_out, float* h_out, float* part,
-                                       float* stats, float* pooled, const float* Wcls, const float* bcls, int n_cls, float* logits,
+                                       float* stats, float* pooled, float* rec_out, const float* Wcls, const float* bcls, int n_cls, float* logits,
                                        const mil_dropout_t* drop, void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   // bits 8..15 of `precision` select the pipeline: 0 = default (pair), MIL_PIPE_SINGLE, MIL_PIPE_PAIR; MHIMK_PIPELINE=1|2 overrides the default
@@ -765,7 +774,7 @@ extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, 
   MIL_CHECK_ARG(D >= BK && D % BK == 0, "mil_abmil_fused_fwd_f32: D=%d must be a positive multiple of %d", D, BK);
   MIL_CHECK_ARG(Wb == nullptr && bb == nullptr, "mil_abmil_fused_fwd_f32: the gated branch is not fused yet; use the composed path");
   MIL_CHECK_ARG(Da == 128, "mil_abmil_fused_fwd_f32: Da=%d (only 128 is fused)", Da);
-  MIL_CHECK_ARG(precision >= 0 && precision <= 2, "mil_abmil_fused_fwd_f32: bad precision %d", precision);
+  MIL_CHECK_ARG(precision >= 0 && precision <= 3, "mil_abmil_fused_fwd_f32: bad precision %d", precision);
   MIL_CHECK_ARG(!t_out || (Wp && C >= 1 && C <= 4), "mil_abmil_fused_fwd_f32: t_out needs Wp and 1 <= C <= 4");
   MIL_CHECK_ARG((uintptr_t)X % 16 == 0 && (!h_out || (uintptr_t)h_out % 16 == 0), "mil_abmil_fused_fwd_f32: X / h_out must be 16-byte aligned");
   MIL_CHECK_ARG(ws_bytes >= mil_fused_workspace_bytes(D, H, Da, 0), "mil_abmil_fused_fwd_f32: workspace needs %zu bytes", mil_fused_workspace_bytes(D, H, Da, 0));
@@ -793,8 +802,9 @@ extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, 
   p.N = N; p.D = D; p.nout = H; p.Da = Da; p.act = act; p.att_act = att_act;
   p.b1 = b1; p.ba = ba; p.wc = wc; p.bc = bc; p.keep = keep; p.Wp = Wp; p.C = t_out ? C : 0;
   p.s_out = s_out; p.t_out = t_out; p.h_out = h_out; p.part = part; p.c_out = nullptr; p.ldc = 0; p.err = err; p.dbg = debug_mask(); p.w1_img = w1_img; p.wa_img = wa_img;
-  p.stats = stats; p.pooled = pooled; p.counter = (unsigned int*)(err + 1); p.Wcls = Wcls; p.bcls = bcls; p.n_cls = n_cls; p.logits = logits;
+  p.stats = stats; p.pooled = pooled; p.rec_out = rec_out; p.counter = (unsigned int*)(err + 1); p.Wcls = Wcls; p.bcls = bcls; p.n_cls = n_cls; p.logits = logits;
   p.trace = getenv("MHIMK_TRACE") ? (long long*)(((uintptr_t)(err + 4) + 63) & ~(uintptr_t)63) : nullptr;
+  p.w1_inv = p.wa_inv = 1.f / prec_wscale(precision);
   if ((rc = set_dropout(p, drop, H))) return rc;
   if (pipeline == 2) return pair_fused_launch(X, p, precision, stream);
   const int64_t n_tiles = (N + BM - 1) / BM;
@@ -808,7 +818,7 @@ extern "C" int mil_umma_selftest_f32(const float* A, const float* B, float* C, i
   MIL_CHECK_ARG(mil_device_supported(), "mil_umma_selftest_f32: needs a compute-capability 10.x device");
   MIL_CHECK_ARG(A && B && C && ws && M > 0, "mil_umma_selftest_f32: null argument");
   MIL_CHECK_ARG((N == 64 || N == 128 || N == 256 || N == 512) && K >= BK && K % BK == 0, "mil_umma_selftest_f32: unsupported N=%d K=%d", N, K);
-  MIL_CHECK_ARG(precision >= 0 && precision <= 2, "mil_umma_selftest_f32: bad precision");
+  MIL_CHECK_ARG(precision >= 0 && precision <= 3, "mil_umma_selftest_f32: bad precision");
   MIL_CHECK_ARG(ws_bytes >= (size_t)N * K * 4 + 1024, "mil_umma_selftest_f32: workspace needs %zu bytes", (size_t)N * K * 4 + 1024);
   MIL_CHECK_ARG(K % 32 == 0, "mil_umma_selftest_f32: K must be a multiple of 32");
   uint8_t* b_img = (uint8_t*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
@@ -823,8 +833,9 @@ extern "C" int mil_umma_selftest_f32(const float* A, const float* B, float* C, i
   p.N = M; p.D = K; p.nout = N; p.Da = 128; p.act = MIL_ACT_NONE; p.att_act = MIL_ACT_NONE;
   p.b1 = nullptr; p.ba = nullptr; p.wc = nullptr; p.bc = nullptr; p.keep = nullptr; p.Wp = nullptr; p.C = 0;
   p.s_out = nullptr; p.t_out = nullptr; p.h_out = nullptr; p.part = nullptr; p.c_out = C; p.ldc = N; p.err = err; p.dbg = debug_mask(); p.w1_img = b_img; p.wa_img = b_img; p.trace = nullptr;
-  p.stats = nullptr; p.pooled = nullptr; p.counter = nullptr; p.Wcls = nullptr; p.bcls = nullptr; p.n_cls = 0; p.logits = nullptr;
+  p.stats = nullptr; p.pooled = nullptr; p.rec_out = nullptr; p.counter = nullptr; p.Wcls = nullptr; p.bcls = nullptr; p.n_cls = 0; p.logits = nullptr;
   set_dropout(p, nullptr, N);
+  p.w1_inv = p.wa_inv = 1.f / prec_wscale(precision);
   const int64_t n_tiles = ((int64_t)M + BM - 1) / BM;
   const int grid = grid_override((int)(n_tiles < num_sms() ? n_tiles : num_sms()));
   return dispatch_fused(precision, MODE_STORE, mx, p, grid, stream);
@@ -840,7 +851,7 @@ extern "C" int mil_linear_act_tc_f32(const float* X, int64_t M, int K, const flo
   MIL_CHECK_ARG(X && W && Y && ws && M > 0 && M < (1ll << 31) - 256, "mil_linear_act_tc_f32: bad argument");
   MIL_CHECK_ARG(N >= 64 && N <= 512 && N % 64 == 0 && (N <= 256 || N == 512), "mil_linear_act_tc_f32: N=%d must be 64,128,192,256 or 512", N);
   MIL_CHECK_ARG(K >= BK && K % BK == 0, "mil_linear_act_tc_f32: K=%d must be a positive multiple of %d", K, BK);
-  MIL_CHECK_ARG(precision >= 0 && precision <= 2, "mil_linear_act_tc_f32: bad precision");
+  MIL_CHECK_ARG(precision >= 0 && precision <= 3, "mil_linear_act_tc_f32: bad precision");
   MIL_CHECK_ARG((uintptr_t)X % 16 == 0 && (uintptr_t)W % 16 == 0 && (uintptr_t)Y % 16 == 0 && (!pre_out || (uintptr_t)pre_out % 16 == 0),
                 "mil_linear_act_tc_f32: pointers must be 16-byte aligned");
   MIL_CHECK_ARG(ws_bytes >= mil_linear_tc_workspace_bytes(N, K), "mil_linear_act_tc_f32: workspace needs %zu bytes", mil_linear_tc_workspace_bytes(N, K));
@@ -858,8 +869,9 @@ extern "C" int mil_linear_act_tc_f32(const float* X, int64_t M, int K, const flo
   p.b1 = bias; p.ba = nullptr; p.wc = nullptr; p.bc = nullptr; p.keep = nullptr; p.Wp = nullptr; p.C = 0;
   p.s_out = nullptr; p.t_out = nullptr; p.h_out = pre_out; p.part = nullptr; p.c_out = Y; p.ldc = N; p.err = err; p.dbg = 0;
   p.w1_img = w_img; p.wa_img = w_img; p.trace = nullptr;
-  p.stats = nullptr; p.pooled = nullptr; p.counter = nullptr; p.Wcls = nullptr; p.bcls = nullptr; p.n_cls = 0; p.logits = nullptr;
+  p.stats = nullptr; p.pooled = nullptr; p.rec_out = nullptr; p.counter = nullptr; p.Wcls = nullptr; p.bcls = nullptr; p.n_cls = 0; p.logits = nullptr;
   if ((rc = set_dropout(p, drop, N))) return rc;
+  p.w1_inv = p.wa_inv = 1.f / prec_wscale(precision);
   const int64_t n_tiles = (M + BM - 1) / BM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   return dispatch_fused(precision, MODE_STORE, mx, p, grid, stream);

@@ -327,6 +327,52 @@ __global__ void __launch_bounds__(MERGE_COLS * MERGE_GROUPS) pool_merge_kernel(c
   if (blockIdx.x == 0 && tid == 0) { stats[0] = m; stats[1] = l; }
 }
 
+// One CTA: log-sum-exp merge of the per-rank records + classifier (the tail of an instance-sharded forward).
+__global__ void __launch_bounds__(512) shard_merge_cls_kernel(const float* __restrict__ rec, int n_rec, int H, const float* __restrict__ Wcls,
+                                                              const float* __restrict__ bcls, int n_cls, float* __restrict__ stats,
+                                                              float* __restrict__ pooled, float* __restrict__ logits) {
+  extern __shared__ float sm[];                  // [n_rec] weights | [H] pooled
+  float* wgt = sm;
+  float* pl = sm + n_rec;
+  __shared__ float ml[2];
+  const int stride = 2 + H, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    float m = -INFINITY;
+    for (int i = lane; i < n_rec; i += 32)
+      if (rec[(int64_t)i * stride + 1] > 0.f) m = fmaxf(m, rec[(int64_t)i * stride]);
+    m = warp_max(m);
+    float l = 0.f;
+    for (int i0 = 0; i0 < n_rec; i0 += 32) {     // fixed order
+      const int i = i0 + lane;
+      float li = 0.f, w = 0.f;
+      if (i < n_rec) {
+        li = rec[(int64_t)i * stride + 1];
+        w = li > 0.f ? expf(rec[(int64_t)i * stride] - m) : 0.f;
+        wgt[i] = w;
+      }
+      l += warp_sum(li * w);
+    }
+    if (lane == 0) { ml[0] = m; ml[1] = l; stats[0] = m; stats[1] = l; }
+  }
+  __syncthreads();
+  const float l = ml[1];
+  for (int c = tid; c < H; c += blockDim.x) {
+    float v = 0.f;
+    for (int i = 0; i < n_rec; ++i) v = fmaf(rec[(int64_t)i * stride + 2 + c], wgt[i], v);
+    v /= l;
+    pl[c] = v;
+    pooled[c] = v;
+  }
+  __syncthreads();
+  if (logits)
+    for (int k = warp; k < n_cls; k += (int)(blockDim.x >> 5)) {
+      float a = 0.f;
+      for (int c = lane; c < H; c += 32) a = fmaf(pl[c], Wcls[(int64_t)k * H + c], a);
+      a = warp_sum(a);
+      if (lane == 0) logits[k] = a + (bcls ? bcls[k] : 0.f);
+    }
+}
+
 __global__ void attn_norm_kernel(const float* __restrict__ s, int64_t s_stride, int64_t L, const uint8_t* __restrict__ keep,
                                  const float* __restrict__ stats, float* __restrict__ attn) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -505,6 +551,15 @@ extern "C" int mil_pool_num_partials(int64_t L) {
 extern "C" int mil_pool_merge_f32(const float* part, int n_part, int H, float* stats, float* pooled, mil_stream_t stream) {
   MIL_CHECK_ARG(part && stats && pooled && n_part > 0 && n_part <= MERGE_MAXP && H > 0, "mil_pool_merge_f32: bad arguments (n_part <= %d)", MERGE_MAXP);
   pool_merge_kernel<<<(H + MERGE_COLS - 1) / MERGE_COLS, MERGE_COLS * MERGE_GROUPS, 0, (cudaStream_t)stream>>>(part, n_part, H, stats, pooled);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mil_shard_merge_cls_f32(const float* rec, int n_rec, int H, const float* Wcls, const float* bcls, int n_cls, float* stats,
+                                       float* pooled, float* logits, mil_stream_t stream) {
+  MIL_CHECK_ARG(rec && stats && pooled && n_rec > 0 && n_rec <= 1024 && H > 0 && H <= 8192, "mil_shard_merge_cls_f32: bad arguments (n_rec <= 1024, H <= 8192)");
+  MIL_CHECK_ARG(!logits || (Wcls && n_cls > 0), "mil_shard_merge_cls_f32: logits needs Wcls and n_cls > 0");
+  shard_merge_cls_kernel<<<1, 512, (size_t)(n_rec + H) * sizeof(float), (cudaStream_t)stream>>>(rec, n_rec, H, Wcls, bcls, n_cls, stats, pooled, logits);
   MIL_LAUNCH_CHECK();
   return 0;
 }

@@ -10,6 +10,9 @@
 namespace mil {
 
 constexpr uint64_t WAIT_TIMEOUT_CYCLES = 4000000000ull;   // ~2 s: trap instead of hanging the GPU on a pipeline bug
+// fp16 hi+lo weight images are built from W * 16: typical weights (|w| ~ 0.03 .. 1) then keep their rounding residual in fp16's normal
+// range (>= 6.1e-5) instead of its subnormals; the epilogue multiplies the accumulator by 1/16 (exact).
+constexpr float W_SCALE_FP16X3 = 16.f;
 constexpr int HMAX = 512;               // embedding width = accumulator columns of one 128-row tile
 
 struct FusedParams {
@@ -24,11 +27,13 @@ struct FusedParams {
   float* c_out; int64_t ldc;   // MODE_STORE
   const uint8_t* w1_img; const uint8_t* wa_img;   // pre-swizzled 16-bit weight images (see split_weights_kernel)
   float* stats; float* pooled; unsigned int* counter;      // in-kernel finalisation by the last CTA to finish
+  float* rec_out;       // nullable [2 + H]: (m, l, P = sum e^{s-m} h) = the exchange record of an instance-sharded bag
   const float* Wcls; const float* bcls; int n_cls; float* logits;
   int* err;
   long long* trace;     // optional [16 tiles][16 slots] clock64 stamps of CTA 0 (MHIMK_TRACE=1), see tools/trace_fused.py
   // dropout on h (mhim.py:193-194, abmil.py:188-189): 0 = none, 1 = caller-supplied keep bits, 2 = in-kernel Philox4x32-10
   int drop_mode; const uint32_t* drop_bits; uint32_t drop_thresh; float drop_scale; uint32_t drop_seed[2]; uint32_t drop_off[2];
+  float w1_inv, wa_inv; // 1 / (power-of-two scale of the W1 / Wa image): MIL_W_SCALE_FP16X3 in the fp16x3 arithmetic, else 1
   int dbg;              // MHIMK_DEBUG bitmask (timing attribution only): 1 skip W1 TMA, 2 skip X TMA, 4 skip GEMM1 MMA, 8 skip convert, 16 skip Wa TMA, 32 skip pooling, 64 skip GEMM2 MMA
 };
 
@@ -237,13 +242,24 @@ __device__ __forceinline__ uint32_t make_idesc(int fp16, int n, int m = 128) {
 template <bool FP16>
 __device__ __forceinline__ uint32_t pack_hi(float x0, float x1) {
   uint32_t r;
-  if (FP16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+  if (FP16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));   // |x| > 65504 saturates instead of becoming inf
   else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
   return r;
 }
 __device__ __forceinline__ uint32_t pack_lo_bf16(float x0, float x1, uint32_t hi) {
   const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xFFFF0000u);
   return pack_hi<false>(x0 - h0, x1 - h1);
+}
+
+// packed 16-bit rounding residual of (x0, x1) against their packed 16-bit hi parts, in the same format as hi
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack_lo(float x0, float x1, uint32_t hi) {
+  if (FP16) {
+    float h0, h1;
+    asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(h0), "=f"(h1) : "r"(hi));
+    return pack_hi<true>(x0 - h0, x1 - h1);
+  }
+  return pack_lo_bf16(x0, x1, hi);
 }
 
 // Write one row (32 consecutive K elements) of a [128 x 32] 16-bit operand tile in the UMMA K-major SWIZZLE_64B layout.
@@ -257,7 +273,7 @@ __device__ __forceinline__ void write_operand_row(uint32_t a_hi, uint32_t a_lo, 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       h[i] = pack_hi<FP16>(x[8 * c + 2 * i], x[8 * c + 2 * i + 1]);
-      if (LO) l[i] = pack_lo_bf16(x[8 * c + 2 * i], x[8 * c + 2 * i + 1], h[i]);
+      if (LO) l[i] = pack_lo<FP16>(x[8 * c + 2 * i], x[8 * c + 2 * i + 1], h[i]);
     }
     const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
@@ -272,7 +288,7 @@ __device__ __forceinline__ void pack_operand_row(const float (&x)[32], uint32_t 
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     h[i] = pack_hi<FP16>(x[2 * i], x[2 * i + 1]);
-    l[i] = LO ? pack_lo_bf16(x[2 * i], x[2 * i + 1], h[i]) : 0u;
+    l[i] = LO ? pack_lo<FP16>(x[2 * i], x[2 * i + 1], h[i]) : 0u;
   }
 }
 template <bool LO>
@@ -307,11 +323,13 @@ __device__ __forceinline__ float gelu_fast(float x) {
 // v[i] = act(v[i] + bias[i]); bias points into shared memory (broadcast reads).  ACT is a compile-time constant in the fused
 // kernel (one variant per instantiation keeps the epilogue small); ACT = -1 selects at run time (store mode only).
 template <int ACT>
-__device__ __forceinline__ void bias_act32(float (&v)[32], const float* bias, int act_rt) {
+// inv_scale undoes the power-of-two scale the weight image was built with (fp16x3 arithmetic; 1 otherwise: fma(v, 1, b) == v + b).
+__device__ __forceinline__ void bias_act32(float (&v)[32], const float* bias, int act_rt, float inv_scale = 1.f) {
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
     const float4 b = *reinterpret_cast<const float4*>(bias + i);
-    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+    v[i] = fmaf(v[i], inv_scale, b.x); v[i + 1] = fmaf(v[i + 1], inv_scale, b.y);
+    v[i + 2] = fmaf(v[i + 2], inv_scale, b.z); v[i + 3] = fmaf(v[i + 3], inv_scale, b.w);
   }
   const int act = ACT >= 0 ? ACT : act_rt;
   if (act == MIL_ACT_RELU) {
@@ -460,6 +478,10 @@ __device__ __forceinline__ void grid_finalize(const FusedParams& p, int et, int 
   }
   fstamp(3);
   float* pooled_s = scratch;                             // wgt is dead: [512] merged pooled vector
+  if (p.rec_out) {
+    *reinterpret_cast<float2*>(p.rec_out + 2 + c2) = v;
+    if (et == 0) { p.rec_out[0] = mg; p.rec_out[1] = lg; }
+  }
   v.x /= lg; v.y /= lg;
   *reinterpret_cast<float2*>(pooled_s + c2) = v;
   *reinterpret_cast<float2*>(p.pooled + c2) = v;
@@ -480,11 +502,18 @@ __device__ __forceinline__ void grid_finalize(const FusedParams& p, int et, int 
 // ---- host helpers shared by the fused-pass translation units (defined in mil_fused_sm100.cu) ----
 int make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                 uint32_t box_cols, CUtensorMapSwizzle sw);
+// the same with a leading dimension `ld` (elements) different from `cols`; rows past `rows` read as zeros
+int make_map_2d_ld(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                   uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle sw);
 void prof_begin(cudaStream_t stream);        // kernel-only timing hooks (mil_profile_enable)
 void prof_end(cudaStream_t stream);
 int debug_mask();
 // pair (cta_group::2) pipeline of the fused pass, mil_fused2_sm100.cu
 size_t pair_weight_image_bytes(int D, int H, int Da);
+// MIL_PREC_* -> (NPROD, FP16) of the kernel templates
+inline bool prec_fp16(int precision) { return precision == MIL_PREC_FP16 || precision == MIL_PREC_FP16X3; }
+inline bool prec_split(int precision) { return precision == MIL_PREC_BF16X3 || precision == MIL_PREC_FP16X3; }
+inline float prec_wscale(int precision) { return precision == MIL_PREC_FP16X3 ? W_SCALE_FP16X3 : 1.f; }
 int pair_build_images(const float* W1, int H, int D, const float* Wa, int Da, uint8_t* w1_img, uint8_t* wa_img, int precision, cudaStream_t stream);
 int pair_fused_launch(const float* X, FusedParams p, int precision, cudaStream_t stream);
 // fills the dropout fields of p from the ABI struct (nullptr / mode 0 = no dropout); <0 on a bad argument

@@ -105,19 +105,23 @@ def allreduce_grads(params: Sequence[torch.nn.Parameter], group=None, average: b
 
 @torch.no_grad()
 def sharded_abmil_forward(model, x_local: torch.Tensor, group=None, want_scores: bool = False):
-    """Instance-sharded forward of a mhimk DAttention (BASELINE config 4: giant bag split along N).
+    """Instance-sharded forward of a mhimk DAttention (BASELINE config 5: giant bag split along N).
 
     x_local: this rank's rows [n_g, D] (may be empty on trailing ranks).  Returns (logits [1,C], stats, s_local or None).
+    Three launches per rank: the fused pass (its tail writes the exchange record (m, l, P[H]) itself), ONE all-gather of
+    2056 B per rank (NCCL, on the compute stream), one merge + classifier kernel (mil_shard_merge_cls_f32).
     """
     from . import ops
     f0, a0, a2 = model.feature[0], model.attention[0], model.attention[2]
     H = f0.out_features
+    world = dist.get_world_size(group)
     if x_local.shape[0] > 0:
         out = ops.abmil_fused_forward(x_local, f0.weight, f0.bias, model.act, a0.weight, a0.bias, a2.weight, a2.bias, "tanh",
-                                      want_scores=want_scores, precision=model.precision, volatile=model.training)
-        partial, s = make_partial(out["stats"], out["pooled"]), out["s"]
+                                      want_scores=want_scores, precision=model.precision, volatile=model.training, want_record=True)
+        rec, s = out["record"], out["s"]
     else:
-        partial, s = torch.zeros(2 + H, device=x_local.device), None
-    stats, pooled = exchange_and_merge(partial, group)
-    logits = ops.linear_act(pooled[None], model.classifier.weight, model.classifier.bias, "none")
+        rec, s = torch.zeros(2 + H, device=x_local.device), None
+    gathered = torch.empty((world, 2 + H), dtype=torch.float32, device=x_local.device)
+    dist.all_gather_into_tensor(gathered.view(-1), rec, group=group)
+    stats, _, logits = ops.shard_merge_cls(gathered, model.classifier.weight, model.classifier.bias)
     return logits, stats, s

@@ -16,7 +16,13 @@ import torch
 from . import _lib
 from ._lib import ACT, PREC, check, ptr, stream_ptr
 
+# Arithmetic of the tensor-core contractions.  "bf16x3" (bf16 hi + lo, 3 products; fp32's exponent range) is the parity arithmetic.
+# "fp16x3" (fp16 hi + lo, operands must satisfy |x| <= 65504) has a 32x smaller operand roundoff at the same cost, but measured on a
+# B200 it buys little where it would matter: the fp32 accumulation inside tcgen05.mma is not round-to-nearest and its error grows with
+# the contraction length -- 3.5e-7 at K = 32, 7.7e-7 at K = 128, 2.3e-6 at K = 512, 4.2e-6 at K = 1024 (fp16x3) against 6.0e-6 / 4.6e-6 /
+# 4.8e-6 / 6.9e-6 (bf16x3), tests/test_gpu_umma.py -- so at the path's K = 512 .. 1536 both sit on the accumulator's floor.
 DEFAULT_PRECISION = "bf16x3"
+GRAD_PRECISION = "bf16x3"
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -40,22 +46,22 @@ class DropSpec:
         return ctypes.byref(self._c)
 
 
-_DROP_STATE = {"seed": None, "offset": 0}
 DROPOUT_HOOK = None          # tests: callable (rows, ncols, p, device) -> DropSpec, e.g. keep bits packed from the reference's own mask
 
 
 def next_dropout(p, rows=None, ncols=None, device=None):
-    """A fresh DropSpec: seed = torch's global seed (torch.manual_seed makes runs reproducible), offset = a per-process call counter
-    that restarts whenever the seed changes.  DROPOUT_HOOK, when set, supplies the spec instead (mask-in parity tests)."""
+    """A fresh DropSpec drawn from torch's CUDA generator of the device, the way torch's own CUDA dropout does it: seed = the
+    generator's seed, offset = its Philox offset, which this call advances -- so torch.manual_seed() makes runs reproducible and
+    successive calls get independent streams.  DROPOUT_HOOK, when set, supplies the spec instead (mask-in parity tests)."""
     if p <= 0.0:
         return None
     if DROPOUT_HOOK is not None:
         return DROPOUT_HOOK(rows, ncols, p, device)
-    seed = torch.initial_seed()
-    if _DROP_STATE["seed"] != seed:
-        _DROP_STATE["seed"], _DROP_STATE["offset"] = seed, 0
-    _DROP_STATE["offset"] += 1
-    return DropSpec(p, seed, _DROP_STATE["offset"])
+    idx = device.index if isinstance(device, torch.device) and device.index is not None else torch.cuda.current_device()
+    gen = torch.cuda.default_generators[idx]
+    off = gen.get_offset()
+    gen.set_offset(off + 4)                            # torch requires multiples of 4 (one Philox4x32 call)
+    return DropSpec(p, gen.initial_seed(), off // 4)
 
 
 def pack_keep_bits(keep: torch.Tensor) -> torch.Tensor:
@@ -119,6 +125,13 @@ TC_MIN_ROWS = 256            # below this the exact-fp32 CUDA-core GEMM is as fa
 def _tc_supported(M, N, K, W):
     return (M >= TC_MIN_ROWS and K % 32 == 0 and K >= 32 and N % 64 == 0 and N >= 64 and W.is_contiguous() and W.data_ptr() % 16 == 0
             and _lib.lib().mil_device_supported())
+
+
+SKINNY = True                # tests can switch the GEMV-shaped kernels off (the 128 x 128-tile fp32 GEMM then takes those shapes)
+
+
+def _skinny(M, N, K):
+    return SKINNY and (N <= 8 or M <= 8) and _lib.lib().mil_skinny_supported(M, N, K) != 0
 
 
 def _drop_dead(cache, limit):
@@ -196,7 +209,11 @@ def linear_forward(x, W, b, act, pre=None, precision=None, volatile=False, dropo
     N = W.shape[0]
     precision = precision or DEFAULT_PRECISION
     if not _tc_supported(M, N, K, W):
-        y = sgemm(x, K, 1, W, K, 1, M, N, K, bias=b, act=act, pre_out=pre)
+        if _skinny(M, N, K) and W.is_contiguous():                  # GEMV-shaped: streaming kernel instead of 128 x 128 GEMM tiles
+            y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+            check(_lib.lib().mil_skinny_fwd_f32(ptr(x), K, M, K, ptr(W), ptr(b), N, ACT[act], ptr(pre), ptr(y), stream_ptr()), "mil_skinny_fwd_f32")
+        else:
+            y = sgemm(x, K, 1, W, K, 1, M, N, K, bias=b, act=act, pre_out=pre)
         return apply_dropout(y, dropout) if dropout else y
     widths, left = [], N
     while left > 0:                                   # 512-wide blocks, then one of 256 / 192 / 128 / 64
@@ -259,9 +276,23 @@ class _LinearAct(torch.autograd.Function):
             g_pre = torch.empty_like(g_y)
             check(L.mil_act_bwd_f32(ptr(g_y), ptr(saved), g_y.numel(), ACT[ctx.act], ptr(g_pre), stream_ptr()), "mil_act_bwd_f32")
         gx = gW = gb = None
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if _skinny(M, N, K) and W.is_contiguous() and x.is_contiguous():
+            g_pre = g_pre.contiguous()
+            if ctx.needs_input_grad[1]:
+                gW = torch.empty((N, K), dtype=torch.float32, device=x.device)
+                gb = torch.empty(N, dtype=torch.float32, device=x.device) if want_b else None
+            elif want_b:
+                gb = g_pre.sum(0)
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty((M, K), dtype=torch.float32, device=x.device)
+            ws = _ws(L.mil_skinny_workspace_bytes(M, N, K), x.device)
+            check(L.mil_skinny_bwd_f32(ptr(g_pre), ptr(x), K, ptr(W), M, N, K, ptr(gW), ptr(gb) if gW is not None else None, ptr(gx), ptr(ws), ws.numel(),
+                                       stream_ptr()), "mil_skinny_bwd_f32")
+            return gx, gW, gb, None, None, None
         if ctx.needs_input_grad[1]:
-            gW = weight_grad(g_pre, x)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gW, gb = weight_grad(g_pre, x, want_b)
+        if want_b and gb is None:
             gb = torch.empty(N, dtype=torch.float32, device=x.device)
             ws = _ws(64 * N * 4, x.device)
             check(L.mil_colsum_f32(ptr(g_pre), M, N, ptr(gb), ptr(ws), ws.numel(), stream_ptr()), "mil_colsum_f32")
@@ -269,18 +300,31 @@ class _LinearAct(torch.autograd.Function):
             # gx[m,k] = sum_n g_pre[m,n] W[n,k].  With W^T materialised ([K,N], a few hundred KB) this is the NT form again and
             # runs on the tensor cores; otherwise A(m,n) = g_pre[m*N + n], B(k,n) = W[n*K + k] on the CUDA cores.
             if _tc_supported(M, K, N, W) and N % 32 == 0 and K % 64 == 0:
-                gx = linear_forward(g_pre.contiguous(), _transposed(W, ctx.volatile), None, "none")
+                gx = linear_forward(g_pre.contiguous(), _transposed(W, ctx.volatile), None, "none", precision=GRAD_PRECISION)
             else:
                 gx = sgemm(g_pre, N, 1, W, 1, K, M, K, N)
         return gx, gW, gb, None, None, None
 
 
-def weight_grad(g_pre, x):
-    """gW[n,k] = sum_m g_pre[m,n] x[m,k] (the contraction over the instances).  fp32 CUDA-core split-K GEMM:
-    A(n,m) = g_pre[m*N + n], B(k,m) = x[m*K + k]."""
+WGRAD_TC = True              # tests / profiling can switch the tensor-core weight gradient off (exact fp32 CUDA-core split-K GEMM instead)
+
+
+def weight_grad(g_pre, x, want_bias=False):
+    """(gW[n,k] = sum_m g_pre[m,n] x[m,k], gb[n] = sum_m g_pre[m,n] or None): the contraction over the instances.
+    Tensor cores (mil_wgrad_tc_f32: bf16 hi+lo, 3 products, deterministic slice reduction, bias gradient from the same pass) when
+    the shape allows -- N % 128 == 0, K % 256 == 0, M >= 256 -- else the fp32 CUDA-core split-K GEMM
+    (A(n,m) = g_pre[m*N + n], B(k,m) = x[m*K + k]; the caller adds mil_colsum_f32 for the bias)."""
     M, K = x.shape
     N = g_pre.shape[1]
-    return sgemm(g_pre, 1, N, x, 1, K, N, K, M, splitk=_splitk_for(N, K, M))
+    L = _lib.lib()
+    if (WGRAD_TC and M >= TC_MIN_ROWS and N % 128 == 0 and K % 256 == 0 and g_pre.is_contiguous() and x.is_contiguous()
+            and g_pre.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0 and L.mil_device_supported()):
+        gW = torch.empty((N, K), dtype=torch.float32, device=x.device)
+        gb = torch.empty(N, dtype=torch.float32, device=x.device) if want_bias else None
+        ws = _ws(L.mil_wgrad_tc_workspace_bytes(M, N, K), x.device)
+        check(L.mil_wgrad_tc_f32(ptr(g_pre), N, ptr(x), K, M, N, K, ptr(gW), ptr(gb), ptr(ws), ws.numel(), stream_ptr()), "mil_wgrad_tc_f32")
+        return gW, gb
+    return sgemm(g_pre, 1, N, x, 1, K, N, K, M, splitk=_splitk_for(N, K, M)), None
 
 
 def linear_act(x: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor] = None, act: str = "none",
@@ -451,7 +495,7 @@ def _fused_workspace(W1, Wa, precision, pipeline="pair", volatile=False):
 @torch.no_grad()
 def abmil_fused_forward(x, W1, b1, act, Wa, ba, wc, bc, att_act="tanh", keep=None, Wp=None, want_scores=False, want_h=False,
                         precision: str = DEFAULT_PRECISION, Wcls=None, bcls=None, pipeline=None, volatile: bool = False,
-                        dropout: Optional[DropSpec] = None):
+                        dropout: Optional[DropSpec] = None, want_record: bool = False):
     """One streaming pass over x [N,D]: returns dict(pooled[H], stats[2] = (m, l), s[N]?, t[N,C]?, h[N,H]?, part).
 
     h = act(x W1^T + b1); s = wc . att_act(Wa h + ba) + bc; pooled = softmax_N(s) @ h; logits = Wcls pooled + bcls when a
@@ -473,15 +517,31 @@ def abmil_fused_forward(x, W1, b1, act, Wa, ba, wc, bc, att_act="tanh", keep=Non
     h = torch.empty((N, H), dtype=torch.float32, device=dev) if want_h else None
     ncls = Wcls.shape[0] if Wcls is not None else 0
     logits = torch.empty((1, ncls), dtype=torch.float32, device=dev) if Wcls is not None else None
+    rec = torch.empty(2 + H, dtype=torch.float32, device=dev) if want_record else None
     pipeline = _pipeline(pipeline, precision)
     ws, ready, commit = _fused_workspace(W1, Wa, precision, pipeline, volatile)
     check(L.mil_abmil_fused_fwd_f32(ptr(x), N, D, H, ptr(W1), ptr(b1), ACT[act], ptr(Wa), ptr(ba), None, None, Da, ACT[att_act], ptr(wc),
                                     ptr(bc), ptr(keep), ptr(Wp), C, ptr(s), ptr(t), ptr(h), ptr(part), ptr(stats), ptr(pooled),
-                                    ptr(Wcls), ptr(bcls), ncls, ptr(logits), dropout.c() if dropout else None, ptr(ws), ws.numel(), ready,
+                                    ptr(rec), ptr(Wcls), ptr(bcls), ncls, ptr(logits), dropout.c() if dropout else None, ptr(ws), ws.numel(), ready,
                                     PREC[precision] | (PIPELINES[pipeline] << 8), stream_ptr()),
           "mil_abmil_fused_fwd_f32")
     commit()
-    return {"pooled": pooled, "stats": stats, "s": s, "t": t, "h": h, "part": part, "logits": logits}
+    return {"pooled": pooled, "stats": stats, "s": s, "t": t, "h": h, "part": part, "logits": logits, "record": rec}
+
+
+def shard_merge_cls(rec: torch.Tensor, Wcls=None, bcls=None):
+    """Merge the gathered per-rank records [(m, l, P[H])] and apply the classifier in one launch -> (stats[2], pooled[H], logits[1,C]?)
+    (mil_shard_merge_cls_f32; the tail of an instance-sharded forward)."""
+    L = _lib.lib()
+    rec = _need(rec, "rec")
+    n, w = rec.shape
+    stats = torch.empty(2, dtype=torch.float32, device=rec.device)
+    pooled = torch.empty(w - 2, dtype=torch.float32, device=rec.device)
+    ncls = Wcls.shape[0] if Wcls is not None else 0
+    logits = torch.empty((1, ncls), dtype=torch.float32, device=rec.device) if Wcls is not None else None
+    check(L.mil_shard_merge_cls_f32(ptr(rec), n, w - 2, ptr(Wcls), ptr(bcls), ncls, ptr(stats), ptr(pooled), ptr(logits), stream_ptr()),
+          "mil_shard_merge_cls_f32")
+    return stats, pooled, logits
 
 
 def profile_fused(enable: bool):

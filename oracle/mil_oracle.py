@@ -296,11 +296,42 @@ def mca(sd: SD, x: Tensor, q_in: Tensor, prefix: str = "merge.attn.", heads: int
     return affine(out, sd[prefix + "to_out.0.weight"], sd[prefix + "to_out.0.bias"])
 
 
+class _LayerNormInputReadAtBackward(torch.autograd.Function):
+    """LayerNorm whose backward reads its INPUT at backward time (mean / rstd from the forward), which is what aten's layer_norm
+    backward does with its saved input.  It matters for exactly one tensor of the path: the reference updates `global_q_mm` through
+    `.data` (merge.py:127-129; same storage as `global_q`) inside forward(), AFTER LayerNorm(global_q) has saved it and BEFORE
+    backward() runs -- autograd's version counter does not see a `.data` write -- so the reference's gradient of merge.norm.weight
+    (and of global_q) is evaluated with the already-updated tokens: 2e-4 away from the mathematically clean value at mm = 0.9999.
+    A drop-in follows the reference (it runs the same torch LayerNorm in the same order); so does this restatement."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, read_input, eps):
+        mu = x.mean(-1, keepdim=True)
+        rstd = 1.0 / torch.sqrt(((x - mu) ** 2).mean(-1, keepdim=True) + eps)
+        ctx.save_for_backward(w, mu, rstd)
+        ctx.read_input, ctx.has_b = read_input, b is not None
+        y = (x - mu) * rstd * w
+        return y if b is None else y + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        w, mu, rstd = ctx.saved_tensors
+        xh = (ctx.read_input().to(dy.dtype) - mu) * rstd
+        g = dy * w
+        dx = rstd * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+        return dx, (dy * xh).sum(0), (dy.sum(0) if ctx.has_b else None), None, None
+
+
 def merge_tokens(sd: SD, x: Tensor, prefix: str = "merge.") -> Tensor:
-    """merge.py:131-144 without the EMA side effect: MCA(LN(x), LN(global_q)) -> [k,512]."""
+    """merge.py:131-144: MCA(LN(x), LN(global_q)) -> [k,512].  The EMA side effect itself is applied by merge_forward."""
     nw, nb = sd[prefix + "norm.weight"], sd[prefix + "norm.bias"]
-    gq = sd[prefix + "global_q"][0]
-    return mca(sd, layer_norm(x, nw, nb), layer_norm(gq, nw, nb), prefix + "attn.")
+    holder = sd[prefix + "global_q"]
+    gq = holder[0]
+    if torch.is_grad_enabled() and (nw.requires_grad or holder.requires_grad):
+        qn = _LayerNormInputReadAtBackward.apply(gq, nw, nb, lambda: holder.data[0], 1e-5)
+    else:
+        qn = layer_norm(gq, nw, nb)
+    return mca(sd, layer_norm(x, nw, nb), qn, prefix + "attn.")
 
 
 def merge_forward(sd: SD, x: Tensor, merge_ratio: float, training: bool, mm: float,
@@ -319,7 +350,9 @@ def merge_forward(sd: SD, x: Tensor, merge_ratio: float, training: bool, mm: flo
         z = merge_tokens(sd, x[ids[n_keep:]], prefix)
         gq = sd[prefix + "global_q"]
         new_q = gq * mm + z.detach()[None].to(gq.dtype) * (1.0 - mm) if mm != 1.0 else None
-        return torch.cat([x[ids[:n_keep]], z], dim=0), new_q
+        if new_q is not None and torch.is_grad_enabled() and (gq.requires_grad or sd[prefix + "norm.weight"].requires_grad):
+            gq.data.copy_(new_q.detach())      # the reference's in-forward `.data` write (merge.py:127-129): backward sees the new tokens
+        return torch.cat([x[ids[:n_keep]], z], dim=0), (new_q.detach() if new_q is not None and new_q.requires_grad else new_q)
     return torch.cat([x, merge_tokens(sd, x, prefix)], dim=0), None
 
 

@@ -1,6 +1,6 @@
 """Import the live reference classes from /root/reference WITHOUT running modules/__init__.py
-(which pulls in `future`/`timm`, absent here).  Test infrastructure only; the GPU box has no
-/root/reference, so every user must guard with `have_reference()`.
+(which pulls in `future`/`timm`, absent here).  Test infrastructure only.  The GPU box has no /root/reference: there the
+unmodified copies under oracle/_ref/ (made by oracle/make_ref.py, git-ignored) are used when present; guard with `have_reference()`.
 """
 import importlib
 import importlib.util
@@ -8,7 +8,8 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("MHIM_REFERENCE_ROOT", "/root/reference")
+_SHIPPED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")     # oracle/make_ref.py
+REF_ROOT = os.environ.get("MHIM_REFERENCE_ROOT") or ("/root/reference" if os.path.isfile("/root/reference/modules/mhim.py") else _SHIPPED)
 
 
 def have_reference() -> bool:

@@ -8,7 +8,7 @@ from oracle import mil_oracle as O
 pytestmark = pytest.mark.gpu
 
 # relative tolerance (max|d| / max|ref|) per arithmetic; the north-star gate is 1e-4 for the parity mode
-TOL = {"bf16x3": 1e-4, "fp16": 2e-3, "bf16": 2e-2}
+TOL = {"bf16x3": 1e-4, "fp16x3": 1e-4, "fp16": 2e-3, "bf16": 2e-2}
 
 
 @pytest.fixture(scope="module")
@@ -31,7 +31,7 @@ def run_oracle(sd, x, act, keep=None):
 
 
 @pytest.mark.parametrize("pipe", ["pair", "single"])
-@pytest.mark.parametrize("prec", ["bf16x3", "fp16", "bf16"])
+@pytest.mark.parametrize("prec", ["fp16x3", "bf16x3", "fp16", "bf16"])
 @pytest.mark.parametrize("N,act,kind", [(1, "relu", "randn"), (100, "gelu", "randn"), (128, "relu", "randn"), (129, "relu", "relu"),
                                         (1024, "gelu", "randn"), (4099, "relu", "randn"), (50000, "relu", "randn")])
 def test_fused_forward(K, pipe, prec, N, act, kind):
@@ -59,7 +59,7 @@ def test_fused_forward(K, pipe, prec, N, act, kind):
 
 
 @pytest.mark.parametrize("pipe", ["pair", "single"])
-@pytest.mark.parametrize("prec", ["bf16x3", "fp16"])
+@pytest.mark.parametrize("prec", ["fp16x3", "bf16x3", "fp16"])
 @pytest.mark.parametrize("N,D", [(777, 1536), (300, 96), (150, 32), (2000, 2048)])
 def test_fused_forward_other_feature_widths(K, pipe, prec, N, D):
     """D = 1536 (GigaPath, BASELINE config 3), widths that are multiples of 32 but not of 64 (the pair pipeline's 32-wide stages),
@@ -95,7 +95,7 @@ def test_fused_forward_with_keep_mask(K, pipe):
 
 
 @pytest.mark.parametrize("pipe", ["pair", "single"])
-@pytest.mark.parametrize("prec", ["bf16x3", "fp16"])
+@pytest.mark.parametrize("prec", ["fp16x3", "bf16x3", "fp16"])
 def test_fused_forward_repeated_launches_are_identical(K, pipe, prec):
     """Pipeline-synchronisation regression: 3 tiles per CTA, cached weight images, 12 back-to-back launches must agree bit for bit
     (a skipped mbarrier phase in the converter groups used to corrupt a few rows of h or dead-lock about once in 20 launches)."""

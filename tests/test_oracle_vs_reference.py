@@ -139,3 +139,38 @@ def test_feature_dropout_mask_semantics(R, base, N):
     for a, b in pairs:
         assert cases.rel_err(a, b) <= 1e-6
     assert cases.rel_err(oloss, loss) <= 1e-6
+
+
+@pytest.mark.parametrize("base,N", [("attn", 2000), ("dsmil", 700)])
+def test_full_gradient_tensors_against_the_live_reference(R, base, N):
+    """Every gradient tensor of the student pass, element for element, against the live reference's autograd -- including
+    merge.norm.weight, whose reference value is taken with the ALREADY EMA-updated global_q (the in-forward `.data` write of
+    merge.py:127-129 precedes backward); the oracle reproduces that (oracle/mil_oracle.py:_LayerNormInputReadAtBackward)."""
+    import torch.nn.functional as F
+    d = 1536 if base == "dsmil" else 1024
+    kw = dict(cases.MHIM_KW, baseline=base, input_dim=d, dropout=0.0)
+    cfg = O.MHIMConfig(**dict(cases.MHIM_KW, baseline=base, input_dim=d))
+    sd_s, sd_t = cases.mhim_state(N, base, D=d), cases.mhim_state(N + 1, base, D=d)
+    stu, tea = zero_dropout(R.mhim.MHIM(**kw)), zero_dropout(R.mhim.MHIM(**kw))
+    stu.load_state_dict(sd_s, strict=True)
+    tea.load_state_dict(sd_t, strict=True)
+    stu.train(), tea.train()
+    x = cases.make_bag(N + 5, N, d)
+    ct, sc = tea.forward_teacher(x)
+    tcf = ct[0] if base == "dsmil" else ct
+    torch.manual_seed(9)
+    lg, loss, _, _ = stu(x, sc, tcf, i=0)
+    lt = 0.5 * lg[0].view(1, -1) + 0.5 * lg[1].view(1, -1) if base == "dsmil" else lg
+    (F.cross_entropy(lt, torch.tensor([1])) + 0.5 * loss).backward()
+    sd_ref = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd_s.items()}
+    torch.manual_seed(9)
+    olg, oloss, *_ = O.mhim_forward(cfg, sd_ref, x, sc, tcf, i=0, training=True)
+    olt = 0.5 * olg[0].view(1, -1) + 0.5 * olg[1].view(1, -1) if base == "dsmil" else olg
+    (F.cross_entropy(olt, torch.tensor([1])) + 0.5 * oloss).backward()
+    n = 0
+    for k, p in stu.named_parameters():
+        if p.grad is None or k not in sd_ref or sd_ref[k].grad is None or float(p.grad.abs().max()) == 0:
+            continue
+        assert cases.rel_err(sd_ref[k].grad, p.grad) <= 2e-5, (k, cases.rel_err(sd_ref[k].grad, p.grad))
+        n += 1
+    assert n >= 10
