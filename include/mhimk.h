@@ -55,8 +55,11 @@ typedef void* mil_stream_t; /* cudaStream_t */
  *           reference's own Bernoulli mask this way);
  *   mode 2: in-kernel Philox4x32-10: counter = (row, column/8, offset_lo, offset_hi), key = (seed_lo, seed_hi); each call yields
  *           eight 16-bit uniforms u (low half-word first), keep iff u < round((1-p)*65536).  Stateless in (row, column): the same
- *           (seed, offset) regenerates the same mask in the backward pass or on the host (tests/philox_ref.py). */
-enum { MIL_DROP_NONE = 0, MIL_DROP_BITS = 1, MIL_DROP_PHILOX = 2 };
+ *           (seed, offset) regenerates the same mask in the backward pass or on the host (tests/philox_ref.py).
+ *   mode 3: as mode 2, but (seed, offset) are read by the kernel from DEVICE memory: keep_bits points to uint64[2] = {seed, offset}.
+ *           For CUDA-graph capture: the host values of mode 2 would be baked into the graph and every replay would repeat one mask;
+ *           here a captured generator kernel refreshes the two words before every replay (mhimk.engines.GraphedStep). */
+enum { MIL_DROP_NONE = 0, MIL_DROP_BITS = 1, MIL_DROP_PHILOX = 2, MIL_DROP_PHILOX_DEV = 3 };
 typedef struct {
   int             mode;
   float           p;
@@ -223,6 +226,10 @@ int    mil_topk_f32(const float* score, int64_t N, int64_t k, int largest, int64
 int    mil_mask_from_indices(const int64_t* idx, int64_t k, int64_t N, int64_t* mask_ids, uint8_t* keep,
                              int64_t* len_keep_out, void* ws, size_t ws_bytes, mil_stream_t stream);
 size_t mil_topk_workspace_bytes(int64_t N);
+/* Critical instance per class: idx_out[c] = argmax_m A[m,c] over the M instances (lowest index among equal maxima), val_out[c]
+ * (nullable) = that maximum.  Replaces the full `torch.sort(c, 0, descending=True)` the reference runs only to read row 0
+ * (modules/dsmil.py:91-92, mhim_modules/baseline.py:137-138) and the max-pooling of the instance logits (dsmil.py:160). */
+int    mil_col_argmax_f32(const float* A, int64_t M, int C, int64_t* idx_out, float* val_out, mil_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * EMA teacher update as ONE launch over all parameters.  Replaces the per-parameter loop

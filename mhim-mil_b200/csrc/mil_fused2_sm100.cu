@@ -654,7 +654,10 @@ static int launch_pair(const CUtensorMap& mx, const CUtensorMap& mw1, const CUte
   constexpr int NOP = NPROD == 3 ? 2 : 1;
   const size_t smem = 1024 + (size_t)XS * X_SLOT + (size_t)NST * KSUB * NOP * (A_OP + B_OP) + (size_t)G2S * NOP * A2_OP + 2 * (size_t)G2B_BUF + MISC_BYTES;
   auto kern = mil_fused2_kernel<NPROD, FP16, NST, XS, KSUB, ACT, ATT>;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};        // the attribute is per device (context): one flag per device ordinal
+  int attr_dev = 0;
+  cudaGetDevice(&attr_dev);
+  bool& attr_set = attr_set_dev[attr_dev & 63];
   if (!attr_set) {
     MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;

@@ -631,7 +631,10 @@ static int launch_fused(const CUtensorMap& mx, const FusedParams& p, int grid, c
   constexpr int NOP = NPROD == 3 ? 2 : 1;
   const size_t smem = 1024 + (size_t)XS * X_SLOT_BYTES + (size_t)NST * NOP * (A_OP_BYTES + B_OP_BYTES) + 512 + 1024 + 4096 + 16 + (HMAX + 256) * 4 + 8 * 256 * 4;
   auto kern = mil_fused_kernel<NPROD, FP16, NST, MODE, ACT, ATT>;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};        // the attribute is per device (context): one flag per device ordinal
+  int attr_dev = 0;
+  cudaGetDevice(&attr_dev);
+  bool& attr_set = attr_set_dev[attr_dev & 63];
   if (!attr_set) {
     MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
@@ -679,10 +682,10 @@ int set_dropout(FusedParams& p, const mil_dropout_t* drop, int ncols) {
   p.drop_mode = 0; p.drop_bits = nullptr; p.drop_thresh = 65536u; p.drop_scale = 1.f;
   p.drop_seed[0] = p.drop_seed[1] = p.drop_off[0] = p.drop_off[1] = 0u;
   if (!drop || drop->mode == MIL_DROP_NONE || drop->p == 0.f) return 0;
-  MIL_CHECK_ARG(drop->mode == MIL_DROP_BITS || drop->mode == MIL_DROP_PHILOX, "dropout: bad mode %d", drop->mode);
+  MIL_CHECK_ARG(drop->mode == MIL_DROP_BITS || drop->mode == MIL_DROP_PHILOX || drop->mode == MIL_DROP_PHILOX_DEV, "dropout: bad mode %d", drop->mode);
   MIL_CHECK_ARG(drop->p > 0.f && drop->p < 1.f, "dropout: p=%g must be in [0, 1)", (double)drop->p);
   MIL_CHECK_ARG(ncols % 32 == 0, "dropout: the dropped tensor must have a multiple of 32 columns (got %d)", ncols);
-  MIL_CHECK_ARG(drop->mode != MIL_DROP_BITS || drop->keep_bits, "dropout: mode 1 needs keep_bits");
+  MIL_CHECK_ARG(drop->mode == MIL_DROP_PHILOX || drop->keep_bits, "dropout: modes 1 and 3 need keep_bits");
   p.drop_mode = drop->mode;
   p.drop_bits = drop->keep_bits;
   p.drop_scale = 1.f / (1.f - drop->p);
@@ -693,9 +696,10 @@ int set_dropout(FusedParams& p, const mil_dropout_t* drop, int ncols) {
 }
 
 __global__ void dropout_bits_kernel(int64_t words, int words_per_row, uint32_t thresh, uint32_t s0, uint32_t s1, uint32_t o0, uint32_t o1,
-                                    uint32_t* __restrict__ out) {
+                                    const uint32_t* __restrict__ dev, uint32_t* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= words) return;
+  if (dev) { s0 = dev[0]; s1 = dev[1]; o0 = dev[2]; o1 = dev[3]; }
   const uint32_t seed[2] = {s0, s1}, off[2] = {o0, o1};
   out[i] = philox_keep_word((uint32_t)(i / words_per_row), (uint32_t)(i % words_per_row), thresh, seed, off);
 }
@@ -736,13 +740,14 @@ extern "C" int mil_profile_collect(double* total_ms) {
 
 extern "C" int mil_dropout_bits(int64_t rows, int ncols, const mil_dropout_t* drop, uint32_t* keep_bits_out, mil_stream_t stream_) {
   MIL_CHECK_ARG(rows > 0 && rows < (1ll << 31) && ncols > 0 && ncols % 32 == 0 && drop && keep_bits_out, "mil_dropout_bits: bad argument");
-  MIL_CHECK_ARG(drop->mode == MIL_DROP_PHILOX && drop->p > 0.f && drop->p < 1.f, "mil_dropout_bits: needs mode 2 and 0 < p < 1");
+  MIL_CHECK_ARG((drop->mode == MIL_DROP_PHILOX || drop->mode == MIL_DROP_PHILOX_DEV) && drop->p > 0.f && drop->p < 1.f, "mil_dropout_bits: needs mode 2 or 3 and 0 < p < 1");
   FusedParams p;
   int rc;
   if ((rc = set_dropout(p, drop, ncols))) return rc;
   const int64_t words = rows * (ncols / 32);
   dropout_bits_kernel<<<(unsigned)((words + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(words, ncols / 32, p.drop_thresh, p.drop_seed[0], p.drop_seed[1],
-                                                                                         p.drop_off[0], p.drop_off[1], keep_bits_out);
+                                                                                         p.drop_off[0], p.drop_off[1],
+                                                                                         p.drop_mode == 3 ? p.drop_bits : nullptr, keep_bits_out);
   MIL_LAUNCH_CHECK();
   return 0;
 }

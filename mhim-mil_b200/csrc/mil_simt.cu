@@ -176,6 +176,7 @@ __global__ void act_bwd_drop_kernel(const float* __restrict__ g, const float* __
                                     uint32_t o0, uint32_t o1, float* __restrict__ out) {
   const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= rows * words_per_row) return;
+  if (mode == 3) { s0 = bits[0]; s1 = bits[1]; o0 = bits[2]; o1 = bits[3]; }
   const uint32_t seed[2] = {s0, s1}, off[2] = {o0, o1};
   const uint32_t word = mode == 1 ? bits[w] : mil::philox_keep_word((uint32_t)(w / words_per_row), (uint32_t)(w % words_per_row), thresh, seed, off);
   const float4* g4 = reinterpret_cast<const float4*>(g + w * 32);
@@ -515,9 +516,9 @@ extern "C" int mil_act_bwd_f32(const float* g_y, const float* y_or_pre, int64_t 
 extern "C" int mil_act_bwd_drop_f32(const float* g_y, const float* y_or_pre, int64_t rows, int ncols, int act, const mil_dropout_t* drop,
                                     float* g_pre, mil_stream_t stream) {
   MIL_CHECK_ARG(g_y && y_or_pre && g_pre && rows >= 0 && rows < (1ll << 31) && ncols > 0 && ncols % 32 == 0, "mil_act_bwd_drop_f32: bad arguments");
-  MIL_CHECK_ARG(drop && (drop->mode == MIL_DROP_BITS || drop->mode == MIL_DROP_PHILOX) && drop->p > 0.f && drop->p < 1.f,
-                "mil_act_bwd_drop_f32: needs a dropout description (mode 1 or 2, 0 < p < 1)");
-  MIL_CHECK_ARG(drop->mode != MIL_DROP_BITS || drop->keep_bits, "mil_act_bwd_drop_f32: mode 1 needs keep_bits");
+  MIL_CHECK_ARG(drop && drop->mode >= MIL_DROP_BITS && drop->mode <= MIL_DROP_PHILOX_DEV && drop->p > 0.f && drop->p < 1.f,
+                "mil_act_bwd_drop_f32: needs a dropout description (mode 1, 2 or 3, 0 < p < 1)");
+  MIL_CHECK_ARG(drop->mode == MIL_DROP_PHILOX || drop->keep_bits, "mil_act_bwd_drop_f32: modes 1 and 3 need keep_bits");
   MIL_CHECK_ARG((uintptr_t)g_y % 16 == 0 && (uintptr_t)y_or_pre % 16 == 0 && (uintptr_t)g_pre % 16 == 0, "mil_act_bwd_drop_f32: pointers must be 16-byte aligned");
   if (rows == 0) return 0;
   const int64_t words = rows * (ncols / 32);

@@ -51,51 +51,62 @@ __global__ void __launch_bounds__(256) thin_fwd_kernel(const float* __restrict__
   }
 }
 
-// partial[blk][j][k] = sum over the CTA's rows of G[m,j] X[m,k];  partial_b[blk][j] = sum G[m,j]
+// partial[blk][j][k] = sum over the CTA's rows of G[m,j] X[m,k];  partial_b[blk][j] = sum G[m,j].
+// 256 threads = 8 row groups x 32 lanes; lane l owns columns k = l + 32 c; a thread keeps NV = N * ceil(K / 32) accumulators
+// (a = j * kv + c), walks the rows rg, rg + 8, ... of the CTA's slice, and the 8 row groups are summed through shared memory in a
+// fixed order.  Rows are independent loads, so the row loop pipelines (the first version walked 256 rows per thread serially).
+template <int NV>
 __global__ void __launch_bounds__(256) thin_wgrad_kernel(const float* __restrict__ G, const float* __restrict__ X, int64_t ldx, int64_t M, int K, int N,
                                                          int64_t rows_per_cta, float* __restrict__ partial, float* __restrict__ partial_b) {
-  __shared__ float sg[64][MAXS];
+  extern __shared__ float red[];                        // [8][N * kv * 32 + N]
+  const int rg = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv = (K + 31) / 32;
   const int64_t m0 = (int64_t)blockIdx.x * rows_per_cta;
   int64_t m1 = m0 + rows_per_cta;
   if (m1 > M) m1 = M;
-  constexpr int CPT = 6;                               // columns per thread: K <= 1536
-  float acc[MAXS][CPT];
+  float acc[NV];
 #pragma unroll
-  for (int j = 0; j < MAXS; ++j)
+  for (int a = 0; a < NV; ++a) acc[a] = 0.f;
+  float accb[MAXS];
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) acc[j][c] = 0.f;
-  float accb = 0.f;                                    // thread j < N: bias partial
-  for (int64_t mb = m0; mb < m1; mb += 64) {
-    const int nr = (int)((m1 - mb) < 64 ? (m1 - mb) : 64);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nr * N; i += blockDim.x) sg[i / N][i % N] = G[(mb + i / N) * N + i % N];
-    __syncthreads();
-    if ((int)threadIdx.x < N)
-      for (int r = 0; r < nr; ++r) accb += sg[r][threadIdx.x];
-    for (int r = 0; r < nr; ++r) {
-      const float* x = X + (mb + r) * ldx;
+  for (int j = 0; j < MAXS; ++j) accb[j] = 0.f;
+  for (int64_t m = m0 + rg; m < m1; m += 8) {
+    const float* x = X + m * ldx;
+    float g[MAXS];
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        const int k = threadIdx.x + c * 256;
-        if (k < K) {
-          const float xv = x[k];
+    for (int j = 0; j < MAXS; ++j) g[j] = j < N ? G[m * N + j] : 0.f;
 #pragma unroll
-          for (int j = 0; j < MAXS; ++j)
-            if (j < N) acc[j][c] = fmaf(sg[r][j], xv, acc[j][c]);
-        }
-      }
+    for (int j = 0; j < MAXS; ++j) accb[j] += g[j];
+#pragma unroll
+    for (int a = 0; a < NV; ++a) {
+      const int j = a / kv, c = a - j * kv, k = lane + 32 * c;
+      if (a < N * kv && k < K) acc[a] = fmaf(g[j], x[k], acc[a]);
     }
   }
+  const int per = N * kv * 32 + N;
+  float* mine = red + rg * per;
+#pragma unroll
+  for (int a = 0; a < NV; ++a)
+    if (a < N * kv) mine[a * 32 + lane] = acc[a];
+  if (lane == 0)
+    for (int j = 0; j < N; ++j) mine[N * kv * 32 + j] = accb[j];
+  __syncthreads();
   float* out = partial + (int64_t)blockIdx.x * N * K;
+  for (int i = threadIdx.x; i < N * kv * 32; i += 256) {
+    const int a = i >> 5, l = i & 31, j = a / kv, c = a - j * kv, k = l + 32 * c;
+    if (k < K) {
+      float v = 0.f;
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) {
-    const int k = threadIdx.x + c * 256;
-    if (k < K)
-#pragma unroll
-      for (int j = 0; j < MAXS; ++j)
-        if (j < N) out[j * K + k] = acc[j][c];
+      for (int r = 0; r < 8; ++r) v += red[r * per + i];
+      out[j * K + k] = v;
+    }
   }
-  if (partial_b && (int)threadIdx.x < N) partial_b[(int64_t)blockIdx.x * N + threadIdx.x] = accb;
+  if (partial_b && (int)threadIdx.x < N) {
+    float v = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v += red[r * per + N * kv * 32 + threadIdx.x];
+    partial_b[(int64_t)blockIdx.x * N + threadIdx.x] = v;
+  }
 }
 
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_part, int64_t n, float* __restrict__ out,
@@ -183,28 +194,41 @@ __global__ void short_wgrad_kernel(const float* __restrict__ G, const float* __r
   }
 }
 
-// dX[i,k] = sum_n G[i,n] W[n,k]
-__global__ void __launch_bounds__(128) short_dx_kernel(const float* __restrict__ G, const float* __restrict__ W, int M, int K, int N,
+// dX[i,k] = sum_n G[i,n] W[n,k].  One CTA per 32 columns k; its 8 warps split the N rows of W (warp w: n = w, w + 8, ...; lanes =
+// 32 consecutive k, coalesced), then a fixed-order sum over the 8 warps through shared memory.
+__global__ void __launch_bounds__(256) short_dx_kernel(const float* __restrict__ G, const float* __restrict__ W, int M, int K, int N,
                                                        float* __restrict__ dX) {
-  extern __shared__ float sgm[];                       // [M][N]
+  extern __shared__ float sgm[];                       // [M][N] | [8][MAXS][32]
+  float* red = sgm + M * N;
   for (int i = threadIdx.x; i < M * N; i += blockDim.x) sgm[i] = G[i];
   __syncthreads();
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 32 + lane;
   float acc[MAXS];
 #pragma unroll
   for (int i = 0; i < MAXS; ++i) acc[i] = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const float wv = W[(int64_t)n * K + k];
+  if (k < K) {
+#pragma unroll 4
+    for (int n = warp; n < N; n += 8) {
+      const float wv = W[(int64_t)n * K + k];
 #pragma unroll
-    for (int i = 0; i < MAXS; ++i)
-      if (i < M) acc[i] = fmaf(sgm[i * N + n], wv, acc[i]);
+      for (int i = 0; i < MAXS; ++i)
+        if (i < M) acc[i] = fmaf(sgm[i * N + n], wv, acc[i]);
+    }
   }
-  for (int i = 0; i < M; ++i) dX[(int64_t)i * K + k] = acc[i];
+#pragma unroll
+  for (int i = 0; i < MAXS; ++i) red[(warp * MAXS + i) * 32 + lane] = acc[i];
+  __syncthreads();
+  if (warp < M && k < K) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[(w * MAXS + warp) * 32 + lane];
+    dX[(int64_t)warp * K + k] = v;
+  }
 }
 
 static int thin_ctas(int64_t M) {
-  int64_t c = (M + 255) / 256;                         // >= 256 rows per CTA
+  int64_t c = (M + 63) / 64;                           // >= 64 rows per CTA (8 per thread)
   const int cap = 2 * num_sms();
   if (c > cap) c = cap;
   if (c < 1) c = 1;
@@ -218,8 +242,9 @@ using namespace mil;
 
 extern "C" int mil_skinny_supported(int64_t M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0 || K > 1536) return 0;
-  if (N <= skinny::MAXS) return (size_t)N * K * 4 <= 48 * 1024 ? 1 : 0;
-  if (M <= skinny::MAXS) return ((size_t)M * K * 4 <= 48 * 1024 && (size_t)M * N * 4 <= 48 * 1024) ? 2 : 0;
+  // thin: W fits shared memory and the weight gradient fits 64 accumulators per thread (N * ceil(K / 32) <= 64)
+  if (N <= skinny::MAXS) return ((size_t)N * K * 4 <= 48 * 1024 && N * ((K + 31) / 32) <= 64) ? 1 : 0;
+  if (M <= skinny::MAXS) return ((size_t)M * K * 4 <= 48 * 1024 && (size_t)M * N * 4 + 8 * skinny::MAXS * 32 * 4 <= 48 * 1024) ? 2 : 0;
   return 0;
 }
 
@@ -262,7 +287,15 @@ extern "C" int mil_skinny_bwd_f32(const float* G, const float* X, int64_t ldx, c
       const int64_t rows = (M + ctas - 1) / ctas;
       float* partial = (float*)ws;
       float* partial_b = partial + (size_t)ctas * N * K;
-      skinny::thin_wgrad_kernel<<<ctas, 256, 0, stream>>>(G, X, ldx, M, K, N, rows, partial, db ? partial_b : nullptr);
+      const int nv = N * ((K + 31) / 32);
+      const size_t sm = (size_t)8 * (nv * 32 + N) * sizeof(float);
+      if (nv <= 4) skinny::thin_wgrad_kernel<4><<<ctas, 256, sm, stream>>>(G, X, ldx, M, K, N, rows, partial, db ? partial_b : nullptr);
+      else if (nv <= 16) skinny::thin_wgrad_kernel<16><<<ctas, 256, sm, stream>>>(G, X, ldx, M, K, N, rows, partial, db ? partial_b : nullptr);
+      else if (nv <= 32) skinny::thin_wgrad_kernel<32><<<ctas, 256, sm, stream>>>(G, X, ldx, M, K, N, rows, partial, db ? partial_b : nullptr);
+      else {
+        MIL_CUDA(cudaFuncSetAttribute(skinny::thin_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        skinny::thin_wgrad_kernel<64><<<ctas, 256, sm, stream>>>(G, X, ldx, M, K, N, rows, partial, db ? partial_b : nullptr);
+      }
       MIL_LAUNCH_CHECK();
       const int64_t n = (int64_t)N * K;
       skinny::reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(partial, ctas, n, dW, partial_b, N, db);
@@ -280,7 +313,7 @@ extern "C" int mil_skinny_bwd_f32(const float* G, const float* X, int64_t ldx, c
       MIL_LAUNCH_CHECK();
     }
     if (dX) {
-      skinny::short_dx_kernel<<<(K + 127) / 128, 128, (size_t)M * N * 4, stream>>>(G, W, (int)M, K, N, dX);
+      skinny::short_dx_kernel<<<(K + 31) / 32, 256, (size_t)M * N * 4 + 8 * skinny::MAXS * 32 * 4, stream>>>(G, W, (int)M, K, N, dX);
       MIL_LAUNCH_CHECK();
     }
   }

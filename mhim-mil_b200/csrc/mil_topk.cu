@@ -229,6 +229,50 @@ __global__ void __launch_bounds__(TK_THREADS) mask_from_indices_kernel(const int
 
 using namespace mil;
 
+// idx[c] = argmax_m A[m, c] (lowest row index among equal maxima), val[c] = the maximum: one CTA per column.
+__global__ void __launch_bounds__(1024) col_argmax_kernel(const float* __restrict__ A, int64_t M, int C, int64_t* __restrict__ idx, float* __restrict__ val) {
+  __shared__ float sv[32];
+  __shared__ long long si[32];
+  const int c = blockIdx.x;
+  float best = -INFINITY;
+  long long bi = 0x7fffffffffffffffll;
+  for (int64_t m = threadIdx.x; m < M; m += blockDim.x) {
+    const float v = A[m * C + c];
+    if (v > best || (v == best && m < bi)) { best = v; bi = m; }
+  }
+  auto better = [](float v, long long i, float bv, long long bj) { return v > bv || (v == bv && i < bj); };
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = threadIdx.x < (blockDim.x >> 5) ? sv[threadIdx.x] : -INFINITY;
+    bi = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : 0x7fffffffffffffffll;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) {
+      if (bi == 0x7fffffffffffffffll) bi = 0;        // all NaN / -inf: row 0, like an empty comparison
+      idx[c] = bi;
+      if (val) val[c] = best;
+    }
+  }
+}
+
+extern "C" int mil_col_argmax_f32(const float* A, int64_t M, int C, int64_t* idx_out, float* val_out, mil_stream_t stream) {
+  MIL_CHECK_ARG(A && idx_out && M > 0 && C > 0 && C <= 65535, "mil_col_argmax_f32: bad arguments");
+  col_argmax_kernel<<<C, 1024, 0, (cudaStream_t)stream>>>(A, M, C, idx_out, val_out);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" size_t mil_topk_workspace_bytes(int64_t N) { return (size_t)N * 24 + 256; }
 
 extern "C" int mil_topk_f32(const float* score, int64_t N, int64_t k, int largest, int64_t* idx_out, void* ws, size_t ws_bytes, mil_stream_t stream) {
@@ -245,7 +289,10 @@ extern "C" int mil_topk_f32(const float* score, int64_t N, int64_t k, int larges
   const size_t dyn_max = 200 * 1024, dyn_min = 32 * 256 * sizeof(int);
   size_t dyn = (size_t)N * sizeof(uint32_t);
   dyn = dyn < dyn_min ? dyn_min : (dyn > dyn_max ? dyn_max : dyn);
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};        // the attribute is per device (context): one flag per device ordinal
+  int attr_dev = 0;
+  cudaGetDevice(&attr_dev);
+  bool& attr_set = attr_set_dev[attr_dev & 63];
   if (!attr_set) {
     MIL_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max));
     attr_set = true;
@@ -261,7 +308,10 @@ extern "C" int mil_mask_from_indices(const int64_t* idx, int64_t k, int64_t N, i
   MIL_CHECK_ARG(mask_ids && keep && len_keep_out && N > 0 && k >= 0 && k <= N && (idx || k == 0), "mil_mask_from_indices: bad arguments");
   const size_t dyn_max = 200 * 1024;
   const size_t dyn = (size_t)N < dyn_max ? (((size_t)N + 15) & ~(size_t)15) : dyn_max;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};        // the attribute is per device (context): one flag per device ordinal
+  int attr_dev = 0;
+  cudaGetDevice(&attr_dev);
+  bool& attr_set = attr_set_dev[attr_dev & 63];
   if (!attr_set) {
     MIL_CUDA(cudaFuncSetAttribute(mask_from_indices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max));
     attr_set = true;

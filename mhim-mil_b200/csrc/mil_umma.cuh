@@ -77,9 +77,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
   }
 }
 static void mil_set_notrap() {
-  static int done = 0;
+  static bool done_dev[64] = {false};           // the symbol lives per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& done = done_dev[dev & 63];
   if (done) return;
-  done = 1;
+  done = true;
   const char* e = getenv("MHIMK_NOTRAP");
   const int v = e ? atoi(e) : 0;
   if (v) cudaMemcpyToSymbol(g_mil_notrap, &v, sizeof(int));
@@ -357,6 +360,10 @@ __device__ __forceinline__ void bias_act32(float (&v)[32], const float* bias, in
 // words_per_row = ncols / 32 of the tensor the mask belongs to
 __device__ __forceinline__ uint32_t drop_keep_word(const FusedParams& p, int64_t row, int chunk, int words_per_row) {
   if (p.drop_mode == 1) return row < p.N ? __ldg(p.drop_bits + row * words_per_row + chunk) : 0u;
+  if (p.drop_mode == 3) {                                  // (seed, offset) live in device memory (CUDA-graph replays)
+    const uint32_t seed[2] = {__ldg(p.drop_bits), __ldg(p.drop_bits + 1)}, off[2] = {__ldg(p.drop_bits + 2), __ldg(p.drop_bits + 3)};
+    return philox_keep_word((uint32_t)row, (uint32_t)chunk, p.drop_thresh, seed, off);
+  }
   return philox_keep_word((uint32_t)row, (uint32_t)chunk, p.drop_thresh, p.drop_seed, p.drop_off);
 }
 __device__ __forceinline__ void drop_apply32(float (&v)[32], uint32_t word, float scale) {

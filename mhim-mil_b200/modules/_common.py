@@ -39,6 +39,15 @@ def lin(layer: nn.Linear, x: torch.Tensor, act: str = "none") -> torch.Tensor:
     return ops.linear_act(x, layer.weight, layer.bias, act, volatile=layer.training)
 
 
+def conv1d_full(conv: nn.Conv1d, B: torch.Tensor) -> torch.Tensor:
+    """DSMIL's bag head `Conv1d(C, C, kernel_size=K)` applied to B [1, C, K] (dsmil.py:98-99, baseline.py:149-150): the kernel spans the
+    whole length, so it is the Linear pred[o] = sum_{c,k} w[o,c,k] B[c,k] + b[o] over the flattened C*K inputs -> [1, C].  Runs in the
+    library's own (GEMV-shaped) kernel with its CUDA backward instead of cuDNN."""
+    Cc, Kk = B.shape[1], B.shape[2]
+    W = conv.weight.reshape(conv.out_channels, Cc * Kk)
+    return ops.linear_act(B.reshape(1, Cc * Kk), W, conv.bias, "none", volatile=conv.training)
+
+
 class MilModule(nn.Module):
     """Base of the drop-in modules.  Behaves exactly like nn.Module (no parameters, no state_dict keys, no hooks); it only tells
     the weight-image caches of `ops` that a train()/eval() switch happened, so the first forward after the switch rebuilds its

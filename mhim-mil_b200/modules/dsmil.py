@@ -32,7 +32,7 @@ class BClassifier(C.MilModule):
         f, cl = feats[0], c[0]
         V = C.lin(self.v[1], self.v[0](f), "relu") if self.passing_v else f
         Q = self._q(f)
-        crit = torch.sort(cl, 0, descending=True).indices[0]
+        crit, _ = ops.col_argmax(cl)                                   # the reference sorts all N rows to read row 0 (dsmil.py:91-92)
         q_max = self._q(f.index_select(0, crit))
         logit = ops.linear_act(Q, q_max, None, "none") / math.sqrt(Q.shape[-1])
         Bs, As = [], []
@@ -41,7 +41,7 @@ class BClassifier(C.MilModule):
             Bs.append(pooled)
             As.append(a)
         B = torch.stack(Bs)[None]
-        pred = self.fcc(B).squeeze(-1)
+        pred = C.conv1d_full(self.fcc, B)                              # Conv1d(C, C, kernel = K) on [1, C, K] == one Linear over C * K inputs
         return pred, torch.stack(As, dim=1)[None], B
 
 
@@ -70,7 +70,8 @@ class MILNet(C.MilModule):
         feats = self.dp(C.lin(self.feature[0], x[0], self.act))[None]
         classes = C.lin(self.i_classifier, feats[0])[None]
         pred, A, B = self.b_classifier(feats, classes)
-        inst = classes.max(dim=1).values
+        crit, _ = ops.col_argmax(classes[0])                           # max-pooling of the instance logits (dsmil.py:160) as a gather of the
+        inst = classes[0][crit, torch.arange(classes.shape[-1], device=crit.device)][None]    # critical rows (differentiable)
         if self.training:
             if isinstance(loss, nn.CrossEntropyLoss):
                 max_loss = loss(inst.view(bs, -1), label)

@@ -106,7 +106,7 @@ class BClassifier(C.MilModule):
         if self.passing_v:
             V = C.lin(self.v[1], self.v[0](feats), "relu")
         Q = self._q(feats)
-        crit = torch.sort(c, 0, descending=True).indices[0]          # critical instance per class (= argmax over N)
+        crit, _ = ops.col_argmax(c)                                    # critical instance per class (the reference sorts all N rows, :137)
         q_max = self._q(feats.index_select(0, crit))
         logit = ops.linear_act(Q, q_max, None, "none") / math.sqrt(Q.shape[1])
         Bs, As = [], []
@@ -116,7 +116,7 @@ class BClassifier(C.MilModule):
             As.append(a)
         B = torch.stack(Bs)[None]                                      # [1,C,K]
         A = logit if no_norm else torch.stack(As, dim=1)
-        pred = self.fcc(B).view(1, -1)
+        pred = C.conv1d_full(self.fcc, B).view(1, -1)
         return pred, A, B
 
 
@@ -131,7 +131,8 @@ class DSMIL(C.MilModule):
         feats = x.squeeze(0)
         classes = C.lin(self.i_classifier[0], feats)
         pred, A, B = self.b_classifier(feats, classes, no_norm)
-        inst = classes.max(dim=0).values
+        crit, _ = ops.col_argmax(classes)                              # max over instances = gather of the critical rows (differentiable)
+        inst = classes[crit, torch.arange(classes.shape[1], device=crit.device)]
         attn = None
         if return_attn:
             src = classes if self.cls_attn else A

@@ -29,17 +29,23 @@ GRAD_PRECISION = "bf16x3"
 # dropout inside the kernels (mil_dropout_t)
 # --------------------------------------------------------------------------------------------------------------
 class DropSpec:
-    """Host description of a dropout fused into a kernel: probability `p` and either the in-kernel Philox stream (seed, offset)
-    or caller-supplied keep bits (int32 [rows, ncols/32], bit i of word (r, c) = keep flag of column 32c+i)."""
-    __slots__ = ("p", "seed", "offset", "keep_bits", "_c")
+    """Host description of a dropout fused into a kernel: probability `p` and one of
+      * the in-kernel Philox stream (seed, offset) given as host integers (mode 2),
+      * caller-supplied keep bits (int32 [rows, ncols/32], bit i of word (r, c) = keep flag of column 32c+i; mode 1),
+      * `seed_dev`: an int64 CUDA tensor [2] = (seed, offset) the kernel reads at run time (mode 3; CUDA-graph replays)."""
+    __slots__ = ("p", "seed", "offset", "keep_bits", "seed_dev", "_c")
 
-    def __init__(self, p, seed=0, offset=0, keep_bits=None):
+    def __init__(self, p, seed=0, offset=0, keep_bits=None, seed_dev=None):
         if not 0.0 <= p < 1.0:
             raise ValueError(f"mhimk: dropout p={p} must be in [0, 1)")
         if keep_bits is not None:
             keep_bits = _need(keep_bits, "keep_bits", torch.int32)
-        self.p, self.seed, self.offset, self.keep_bits = float(p), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), keep_bits
-        self._c = _lib.DropoutT(1 if keep_bits is not None else 2, self.p, self.seed, self.offset, None if keep_bits is None else keep_bits.data_ptr())
+        if seed_dev is not None:
+            seed_dev = _need(seed_dev, "seed_dev", torch.int64)
+        self.p, self.seed, self.offset = float(p), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1)
+        self.keep_bits, self.seed_dev = keep_bits, seed_dev
+        mode, pointer = (1, keep_bits.data_ptr()) if keep_bits is not None else ((3, seed_dev.data_ptr()) if seed_dev is not None else (2, None))
+        self._c = _lib.DropoutT(mode, self.p, self.seed, self.offset, pointer)
 
     def c(self):
         import ctypes
@@ -57,6 +63,10 @@ def next_dropout(p, rows=None, ncols=None, device=None):
         return None
     if DROPOUT_HOOK is not None:
         return DROPOUT_HOOK(rows, ncols, p, device)
+    if torch.cuda.is_current_stream_capturing():
+        # inside a CUDA-graph capture host integers would be frozen into the graph: draw (seed, offset) on the DEVICE with torch's
+        # graph-safe generator (the drawing kernel is part of the graph, so every replay gets a fresh pair) -- mil_dropout_t mode 3
+        return DropSpec(p, seed_dev=torch.randint(0, 2 ** 62, (2,), dtype=torch.int64, device=device if device is not None else "cuda"))
     idx = device.index if isinstance(device, torch.device) and device.index is not None else torch.cuda.current_device()
     gen = torch.cuda.default_generators[idx]
     off = gen.get_offset()
@@ -429,6 +439,17 @@ def topk(score: torch.Tensor, k: int, largest: bool = True) -> torch.Tensor:
     ws = _ws(L.mil_topk_workspace_bytes(n), score.device)
     check(L.mil_topk_f32(ptr(score), n, k, 1 if largest else 0, ptr(idx), ptr(ws), ws.numel(), stream_ptr()), "mil_topk_f32")
     return idx
+
+
+def col_argmax(a: torch.Tensor):
+    """(idx int64 [C], val [C]): the row of the maximum of every column of a [M, C], lowest row first among ties (the critical
+    instance of DSMIL, dsmil.py:91-92; no gradient)."""
+    a = _need(a.detach(), "a")
+    M, C = a.shape
+    idx = torch.empty(C, dtype=torch.int64, device=a.device)
+    val = torch.empty(C, dtype=torch.float32, device=a.device)
+    check(_lib.lib().mil_col_argmax_f32(ptr(a), M, C, ptr(idx), ptr(val), stream_ptr()), "mil_col_argmax_f32")
+    return idx, val
 
 
 def mask_from_indices(idx: torch.Tensor, n: int):
