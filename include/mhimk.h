@@ -232,6 +232,28 @@ size_t mil_topk_workspace_bytes(int64_t N);
 int    mil_col_argmax_f32(const float* A, int64_t M, int C, int64_t* idx_out, float* val_out, mil_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Row selection by a permutation, forward and backward.  Replaces the gathers of modules/mhim_modules/masking.py:91-110 (mask_fn:
+ * x[mask_ids[:len_keep]]) and modules/mhim_modules/merge.py:171-174 (keep / drop split by argsort(rand(L))) and their autograd
+ * (torch: index_put_ with accumulate, which sorts the indices).  `perm` is a permutation of the rows of x (or a prefix of one).
+ *   take:    out[i,:] = x[perm[i],:], i < n_out.
+ *   scatter: gx[perm[i],:] = i < n_a ? ga[i,:] : (gb ? gb[i-n_a,:] : 0), i < n_rows -- every row of gx written exactly once.
+ * cols % 4 == 0, 16-byte aligned. */
+int mil_take_rows_f32(const float* x, const int64_t* perm, int64_t n_out, int cols, float* out, mil_stream_t stream);
+int mil_scatter_rows_f32(const float* ga, const float* gb, const int64_t* perm, int64_t n_a, int64_t n_rows, int cols, float* gx,
+                         mil_stream_t stream);
+
+/* Merge's cross-attention (modules/mhim_modules/merge.py:52-65): kq <= 8 query tokens over L instances, `heads` x dh (dh <= 64).
+ * q [kq, heads*dh]; kv [L, 2*heads*dh] = [K | V] (the to_kv output).  P [heads, kq, L] receives softmax_L(scale q.K) (kept for the
+ * backward); pmask (nullable, same shape) is the attention dropout mask already scaled by 1/(1-p) (merge.py:60);
+ * out [kq, heads*dh] = (P * pmask) V.  Backward: dq [kq, heads*dh], dkv [L, 2*heads*dh]; dS_scratch [heads, kq, L].
+ * ws >= mil_mca_workspace_bytes(L, kq, heads, dh).  Deterministic (chunk partials summed in a fixed order). */
+int    mil_mca_fwd_f32(const float* q, const float* kv, int64_t L, int kq, int heads, int dh, float scale, const float* pmask, float* P,
+                       float* out, void* ws, size_t ws_bytes, mil_stream_t stream);
+int    mil_mca_bwd_f32(const float* g_out, const float* q, const float* kv, const float* P, const float* pmask, int64_t L, int kq, int heads,
+                       int dh, float scale, float* dS_scratch, float* dq, float* dkv, void* ws, size_t ws_bytes, mil_stream_t stream);
+size_t mil_mca_workspace_bytes(int64_t L, int kq, int heads, int dh);
+
+/* ---------------------------------------------------------------------------------------------
  * EMA teacher update as ONE launch over all parameters.  Replaces the per-parameter loop
  * `param_k.data.mul_(mm).add_(param_q.data, alpha=1 - mm)` of engines/base_engine.py:166-167 (and :488-489).
  * segs_dev: device array of n_seg records; the caller cuts every parameter into segments of a few 10^4 elements (one CTA
@@ -239,6 +261,15 @@ int    mil_col_argmax_f32(const float* A, int64_t M, int C, int64_t* idx_out, fl
  * mm outside [0, 1] is an argument error (the reference asserts the same, base_engine.py:164). */
 typedef struct { float* dst; const float* src; int64_t n; } mil_ema_seg_t;
 int mil_ema_update_f32(const mil_ema_seg_t* segs_dev, int n_seg, float mm, float one_minus_mm, mil_stream_t stream);
+
+/* Adam / AdamW optimiser step as ONE launch over all parameters (the reference builds torch.optim.Adam / AdamW,
+ * train_utils.py:55-65, and calls optimizer.step() once per bag, engines/base_engine.py:110-120).  segs_dev: device array of records
+ * (parameter, gradient, exp_avg, exp_avg_sq, n) cut into segments of a few 10^4 elements (one CTA each).  decoupled = 0: Adam (L2
+ * weight decay added to the gradient), 1: AdamW.  bias_correction1 = 1 - beta1^t, bias_correction2_sqrt = sqrt(1 - beta2^t) for the
+ * step count t of THIS step; step_dev (nullable) = device float holding t instead (capturable: CUDA-graph replays). */
+typedef struct { float* p; const float* g; float* m; float* v; int64_t n; } mil_adam_seg_t;
+int mil_adam_step_f32(const mil_adam_seg_t* segs_dev, int n_seg, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      int decoupled, float bias_correction1, float bias_correction2_sqrt, const float* step_dev, mil_stream_t stream);
 
 /* Self-test hook for the tcgen05/TMA plumbing: C[M,N] = A[M,K] B[N,K]^T with the fused pass's operand pipeline
  * (fp32 in HBM -> TMA -> bf16/fp16 split in shared memory -> tcgen05.mma -> TMEM -> registers).  M % 128 == 0,

@@ -57,6 +57,13 @@ _SIGS = {
     "mil_shard_merge_cls_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mil_cam_score_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_float, c_void_p, c_void_p]),
     "mil_cam_score_dev_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mil_take_rows_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "mil_scatter_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "mil_mca_fwd_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mil_mca_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_size_t, c_void_p]),
+    "mil_mca_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
+    "mil_adam_step_f32": (c_int, [c_void_p, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_float, c_void_p, c_void_p]),
     "mil_ema_update_f32": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p]),
     "mil_topk_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mil_mask_from_indices": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

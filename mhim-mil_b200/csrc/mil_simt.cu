@@ -614,6 +614,44 @@ extern "C" int mil_cam_score_dev_f32(const float* s, const float* t, int64_t L, 
   return 0;
 }
 
+// Adam / AdamW step over a device table of parameter segments: ONE launch for the whole model (torch's foreach path issues ~12
+// multi-tensor launches per step, its single-tensor path ~10 per parameter).  Same arithmetic as torch.optim.Adam(W)'s reference
+// implementation (torch/optim/adam.py:_single_tensor_adam): L2 (Adam) or decoupled (AdamW) weight decay, lerp for the first moment,
+// mul + addcmul for the second, denom = sqrt(v) / sqrt(bias_correction2) + eps, p -= lr / bias_correction1 * m / denom.
+__global__ void adam_step_kernel(const mil_adam_seg_t* __restrict__ segs, float lr, float beta1, float beta2, float eps, float wd, int decoupled,
+                                 float bc1, float bc2_sqrt, const float* __restrict__ step_dev) {
+  const mil_adam_seg_t sg = segs[blockIdx.x];
+  if (step_dev) {                                      // capturable: the step count lives on the device (CUDA-graph replays)
+    const float t = step_dev[0];
+    bc1 = 1.f - powf(beta1, t);
+    bc2_sqrt = sqrtf(1.f - powf(beta2, t));
+  }
+  const float step_size = lr / bc1;
+  for (int64_t i = threadIdx.x; i < sg.n; i += blockDim.x) {
+    float p = sg.p[i], g = sg.g[i], m = sg.m[i], v = sg.v[i];
+    if (decoupled) p *= 1.f - lr * wd;
+    else if (wd != 0.f) g = fmaf(wd, p, g);
+    m = fmaf(1.f - beta1, g - m, m);
+    v = fmaf(1.f - beta2, g * g, v * beta2);
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    p -= step_size * (m / denom);
+    sg.p[i] = p; sg.m[i] = m; sg.v[i] = v;
+  }
+}
+
+extern "C" int mil_adam_step_f32(const mil_adam_seg_t* segs_dev, int n_seg, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                 int decoupled, float bias_correction1, float bias_correction2_sqrt, const float* step_dev, mil_stream_t stream) {
+  MIL_CHECK_ARG(segs_dev && n_seg >= 0, "mil_adam_step_f32: bad arguments");
+  MIL_CHECK_ARG(lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && weight_decay >= 0.f,
+                "mil_adam_step_f32: invalid hyper-parameters (same checks as torch.optim.Adam)");
+  MIL_CHECK_ARG(step_dev || (bias_correction1 > 0.f && bias_correction2_sqrt > 0.f), "mil_adam_step_f32: bias corrections must be positive");
+  if (n_seg == 0) return 0;
+  adam_step_kernel<<<n_seg, 256, 0, (cudaStream_t)stream>>>(segs_dev, lr, beta1, beta2, eps, weight_decay, decoupled, bias_correction1,
+                                                            bias_correction2_sqrt, step_dev);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int mil_ema_update_f32(const mil_ema_seg_t* segs_dev, int n_seg, float mm, float one_minus_mm, mil_stream_t stream) {
   MIL_CHECK_ARG(n_seg >= 0 && (segs_dev || n_seg == 0), "mil_ema_update_f32: bad segment table");
   MIL_CHECK_ARG(mm >= 0.f && mm <= 1.f, "mil_ema_update_f32: momentum %f outside [0, 1]", (double)mm);

@@ -57,4 +57,7 @@ def select_mask_fn(ps, attn, largest, mask_ratio, mask_ids_other=None, len_keep_
 def mask_fn(x, ids_shuffle=None, len_keep=None):
     """Rows of x [1, L, D] at the first len_keep ids (masking.py:91-110)."""
     assert ids_shuffle is not None
+    if x.is_cuda and x.dim() == 3 and x.shape[0] == 1 and x.dtype == torch.float32 and x.shape[2] % 4 == 0 and ids_shuffle.shape[1] == x.shape[1]:
+        # mask_ids is a permutation of the rows: own gather, and a backward that writes every row once (no index sort)
+        return ops.take_rows(x[0], ids_shuffle[0], len_keep)[None]
     return x[:, ids_shuffle[0, :len_keep]]

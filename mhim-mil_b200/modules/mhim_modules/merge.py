@@ -8,6 +8,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from ... import ops
 from .. import _common as C
 from .masking import select_mask_fn
 
@@ -27,10 +28,18 @@ class MCA(C.MilModule):
         kv = C.lin(self.to_kv, x[0])
         q = C.lin(self.to_q, _q[0])
         inner = q.shape[-1]
-        split = lambda t: t.reshape(t.shape[0], self.heads, -1).permute(1, 0, 2)
-        qh, kh, vh = split(q), split(kv[:, :inner]), split(kv[:, inner:])
-        attn = self.dropout(self.attend(qh @ kh.transpose(-1, -2) * self.scale))
-        out = (attn @ vh).permute(1, 0, 2).reshape(q.shape[0], inner)
+        if q.shape[0] <= 8 and inner // self.heads <= 64 and kv.shape[1] == 2 * inner:
+            # own kernels: scores, softmax over the n instances, weighted sum (and their backward); the attention dropout
+            # (merge.py:60) enters as a pre-scaled keep mask drawn by torch's generator
+            pmask = None
+            if self.training and self.dropout.p > 0:
+                pmask = F.dropout(torch.ones((self.heads, q.shape[0], kv.shape[0]), dtype=torch.float32, device=q.device), self.dropout.p, True)
+            out = ops.mca_attend(q, kv, self.heads, self.scale, pmask)
+        else:
+            split = lambda t: t.reshape(t.shape[0], self.heads, -1).permute(1, 0, 2)
+            qh, kh, vh = split(q), split(kv[:, :inner]), split(kv[:, inner:])
+            attn = self.dropout(self.attend(qh @ kh.transpose(-1, -2) * self.scale))
+            out = (attn @ vh).permute(1, 0, 2).reshape(q.shape[0], inner)
         if isinstance(self.to_out, nn.Identity):
             return out[None]
         return self.to_out[1](C.lin(self.to_out[0], out))[None]
@@ -79,6 +88,9 @@ class Merge(C.MilModule):
         else:                                                        # 'low'
             n_keep, order = select_mask_fn(L, attn, False, 1 - self.merge_ratio)
             order = order.squeeze(0)
+        if x.is_cuda and x.shape[0] == 1 and x.dtype == torch.float32 and x.shape[2] % 4 == 0 and order.numel() == L and 0 < n_keep < L:
+            keep, drop = ops.split_rows(x[0], order, n_keep)             # one gather each; the backward is a single scatter
+            return keep[None], drop[None]
         return x[:, order[:n_keep]], x[:, order[n_keep:]]
 
     def forward(self, x, attn=None):

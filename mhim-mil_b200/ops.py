@@ -8,7 +8,7 @@ No-grad fused paths:
   abmil_fused_forward   one streaming tcgen05 pass X -> (scores, pooled)  (teacher / inference)
   topk, mask_from_indices, cam_score                    (masked hard-instance selection, scoring.py:37-58)
 """
-from ctypes import c_float, c_int, c_int64, c_size_t
+from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p
 from typing import Optional, Tuple
 
 import torch
@@ -461,6 +461,91 @@ def mask_from_indices(idx: torch.Tensor, n: int):
     len_keep = torch.empty(1, dtype=torch.int64, device=idx.device)
     check(L.mil_mask_from_indices(ptr(idx), idx.numel(), n, ptr(mask_ids), ptr(keep), ptr(len_keep), None, 0, stream_ptr()), "mil_mask_from_indices")
     return mask_ids, keep, len_keep
+
+
+# --------------------------------------------------------------------------------------------------------------
+# row selection by a permutation; Merge's cross-attention
+# --------------------------------------------------------------------------------------------------------------
+class _SplitRows(torch.autograd.Function):
+    """(x[perm[:n_a]], x[perm[n_a:n_a+n_b]]) for perm = (a prefix of) a permutation of the rows; rows of perm beyond n_a + n_b get a zero
+    gradient.  The backward is one scatter in which every row of gx is written once (no index sort, no atomics)."""
+
+    @staticmethod
+    def forward(ctx, x, perm, n_a, n_b):
+        x, perm = _need(x, "x"), _need(perm.reshape(-1), "perm", torch.int64)
+        rows, cols = x.shape
+        L = _lib.lib()
+        a = torch.empty((n_a, cols), dtype=torch.float32, device=x.device)
+        b = torch.empty((n_b, cols), dtype=torch.float32, device=x.device) if n_b else None
+        check(L.mil_take_rows_f32(ptr(x), ptr(perm), n_a, cols, ptr(a), stream_ptr()), "mil_take_rows_f32")
+        if n_b:
+            check(L.mil_take_rows_f32(ptr(x), c_void_p(perm.data_ptr() + 8 * n_a), n_b, cols, ptr(b), stream_ptr()), "mil_take_rows_f32")
+        ctx.save_for_backward(perm)
+        ctx.dims = (rows, cols, n_a, n_b)
+        if perm.numel() != rows:
+            raise RuntimeError("mhimk split_rows: `perm` must be a permutation of all rows of x")
+        return (a, b) if n_b else (a, a.new_empty(0, cols))
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        (perm,) = ctx.saved_tensors
+        rows, cols, n_a, n_b = ctx.dims
+        gx = torch.empty((rows, cols), dtype=torch.float32, device=perm.device)
+        ga = _need(ga, "grad") if ga is not None else torch.zeros((n_a, cols), dtype=torch.float32, device=perm.device)
+        gbp = ptr(_need(gb, "grad")) if (n_b and gb is not None) else None
+        # rows perm[n_a + n_b:] (masked instances) receive zeros: the kernel writes 0 wherever gb is absent, so pass gb only when it spans them all
+        if n_b and n_a + n_b != rows:
+            raise RuntimeError("mhimk split_rows: the two parts must cover the permutation")
+        check(_lib.lib().mil_scatter_rows_f32(ptr(ga), gbp, ptr(perm), n_a, rows, cols, ptr(gx), stream_ptr()), "mil_scatter_rows_f32")
+        return gx, None, None, None
+
+
+def take_rows(x: torch.Tensor, perm: torch.Tensor, n_take: int) -> torch.Tensor:
+    """x[perm[:n_take]] for a full permutation `perm` of the rows of x [rows, cols] (mask_fn, masking.py:108); differentiable."""
+    return _SplitRows.apply(x, perm, n_take, 0)[0]
+
+
+def split_rows(x: torch.Tensor, perm: torch.Tensor, n_keep: int):
+    """(x[perm[:n_keep]], x[perm[n_keep:]]) (Merge's random keep / drop split, merge.py:171-174); differentiable."""
+    return _SplitRows.apply(x, perm, n_keep, x.shape[0] - n_keep)
+
+
+class _MCA(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, kv, heads, scale, pmask):
+        q, kv = _need(q, "q"), _need(kv, "kv")
+        kq, inner = q.shape
+        L_, dh = kv.shape[0], inner // heads
+        lib = _lib.lib()
+        P = torch.empty((heads, kq, L_), dtype=torch.float32, device=q.device)
+        out = torch.empty((kq, inner), dtype=torch.float32, device=q.device)
+        ws = _ws(lib.mil_mca_workspace_bytes(L_, kq, heads, dh), q.device)
+        check(lib.mil_mca_fwd_f32(ptr(q), ptr(kv), L_, kq, heads, dh, c_float(scale), ptr(pmask), ptr(P), ptr(out), ptr(ws), ws.numel(), stream_ptr()),
+              "mil_mca_fwd_f32")
+        ctx.save_for_backward(q, kv, P, pmask if pmask is not None else q.new_empty(0))
+        ctx.cfg = (heads, scale, pmask is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, kv, P, pmask = ctx.saved_tensors
+        heads, scale, has_mask = ctx.cfg
+        kq, inner = q.shape
+        L_, dh = kv.shape[0], inner // heads
+        lib = _lib.lib()
+        g = _need(g, "grad")
+        dS = torch.empty_like(P)
+        dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+        ws = _ws(lib.mil_mca_workspace_bytes(L_, kq, heads, dh), q.device)
+        check(lib.mil_mca_bwd_f32(ptr(g), ptr(q), ptr(kv), ptr(P), ptr(pmask) if has_mask else None, L_, kq, heads, dh, c_float(scale), ptr(dS), ptr(dq),
+                                  ptr(dkv), ptr(ws), ws.numel(), stream_ptr()), "mil_mca_bwd_f32")
+        return dq, dkv, None, None, None
+
+
+def mca_attend(q: torch.Tensor, kv: torch.Tensor, heads: int, scale: float, pmask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Merge's cross-attention core (merge.py:52-65): q [k, heads*dh] (k <= 8), kv [L, 2*heads*dh] = [K | V] -> [k, heads*dh] =
+    concat_h( dropout(softmax_L(scale q_h K_h^T)) V_h ); pmask [heads, k, L] is the dropout mask scaled by 1/(1-p) or None."""
+    return _MCA.apply(q, kv, heads, float(scale), pmask)
 
 
 # --------------------------------------------------------------------------------------------------------------
