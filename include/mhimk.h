@@ -132,6 +132,12 @@ int mil_sgemm_f32(const float* A, int64_t sAm, int64_t sAk, const int64_t* row_i
                   float* C, int64_t ldc, float* pre_out,
                   int64_t M, int64_t N, int64_t K, int act, int splitk, void* ws, size_t ws_bytes, mil_stream_t stream);
 
+/* Batched fp32 GEMM: C_b[M,N] = sum_k A_b(m,k) B_b(n,k) for b < batch, operand b at base + b * bA / bB / bC elements (strides as in
+ * mil_sgemm_f32, no bias / activation / split-K).  The 8 x (256 x 256 x 256) products of the Moore-Penrose iteration
+ * (nystrom_attention.py:12-27) and the small landmark products of the Nystrom layers. */
+int mil_sgemm_batched_f32(const float* A, int64_t sAm, int64_t sAk, int64_t bA, const float* B, int64_t sBn, int64_t sBk, int64_t bB,
+                          float* C, int64_t ldc, int64_t bC, int64_t M, int64_t N, int64_t K, int batch, mil_stream_t stream);
+
 /* Tensor-core variant of the NT form: Y[M,N] = act(X[M,K] W[N,K]^T + bias) through the fused pass's TMA -> 16-bit split ->
  * tcgen05 pipeline (fp32-class results in MIL_PREC_BF16X3).  K % 32 == 0; N in {64,128,192,256,512}; pre_out nullable
  * (pre-activation, ld = N).  ws >= mil_linear_tc_workspace_bytes(N, K) holds the weight image; ws_ready as above.
@@ -139,6 +145,11 @@ int mil_sgemm_f32(const float* A, int64_t sAm, int64_t sAk, const int64_t* row_i
 int    mil_linear_act_tc_f32(const float* X, int64_t M, int K, const float* W, const float* bias, int N, int act, float* pre_out,
                              float* Y, const mil_dropout_t* drop /* nullable: dropout on Y (N % 32 == 0) */,
                              void* ws, size_t ws_bytes, int ws_ready, int precision, mil_stream_t stream);
+/* The same on operands that are column blocks of wider row-major buffers: X has leading dimension ldx (>= K), Y and pre_out have ldy (>= N);
+ * both multiples of 4.  (Per-head slices of the qkv buffer, head-wise outputs of the Nystrom aggregation.) */
+int    mil_linear_act_tc_ld_f32(const float* X, int64_t ldx, int64_t M, int K, const float* W, const float* bias, int N, int act, float* pre_out,
+                                float* Y, int64_t ldy, const mil_dropout_t* drop, void* ws, size_t ws_bytes, int ws_ready, int precision,
+                                mil_stream_t stream);
 size_t mil_linear_tc_workspace_bytes(int N, int K);
 
 /* Skinny Linear layers (GEMV-shaped), forward and backward, exact fp32 streaming kernels: Y[M,N] = act(X[M,K] W[N,K]^T + b) with
@@ -262,13 +273,36 @@ size_t mil_mca_workspace_bytes(int64_t L, int kq, int heads, int dh);
 typedef struct { float* dst; const float* src; int64_t n; } mil_ema_seg_t;
 int mil_ema_update_f32(const mil_ema_seg_t* segs_dev, int n_seg, float mm, float one_minus_mm, mil_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * CUDA-core pieces of the Nystrom / TransMIL path (modules/nystrom_attention.py:65-152, transmil.py:23-64, emb_position.py:85-120).
+ *   mil_layernorm_fwd_f32     y = LayerNorm(x) over the last axis (transmil.py:31, baseline.py:205).
+ *   mil_segment_mean_f32      landmarks: out[h][j][d] = scale * mean over segment j (seg_len rows) of x[row, col0 + h*dh + d]
+ *                             (nystrom_attention.py:93-109; x = the qkv buffer, leading dimension ld).
+ *   mil_row_softmax_f32       in-place softmax over the last axis of S [rows, cols <= 1024] (attn1, attn2: :127).
+ *   mil_colsoftmax_pool_f32   out[j,:] = sum_n softmax_n(S[n,j]) V[n,:] for S [n, m <= 256] = (k q_l^T), V [n, dh <= 64] (leading dimension ldv):
+ *                             attn3 @ v without materialising attn3 (SURVEY 9.7 pass A); also returns the column maxima / sums.
+ *   mil_expdot_rows_f32       out[r] = sum_j w[j] exp(S[r,j] - M[j])  -- the cls-row attention over the keys (:143-150).
+ *   mil_dwconv_tokens_f32     out[r, c] (+)= sum_t w[head(c)][t] v[r + t - taps/2, c]: the depth-wise residual conv over tokens (:135-136).
+ *   mil_ppeg_f32              y = depth-wise 7x7 conv (zero padded) of the [H*W, C] token grid with an effective kernel w49 [C,49] (= 7x7 + padded
+ *                             5x5 + padded 3x3 + identity) + bias (transmil.py:50-64, emb_position.py:85-120). */
+int    mil_layernorm_fwd_f32(const float* x, int64_t rows, int cols, const float* w, const float* b, float eps, float* y, mil_stream_t stream);
+int    mil_segment_mean_f32(const float* x, int64_t ld, int m, int seg_len, int col0, int heads, int dh, float scale, float* out, mil_stream_t stream);
+int    mil_row_softmax_f32(float* S, int64_t rows, int cols, mil_stream_t stream);
+int    mil_colsoftmax_pool_f32(const float* S, const float* V, int64_t ldv, int64_t n, int m, int dh, float* out, float* colmax, float* colsum,
+                               void* ws, size_t ws_bytes, mil_stream_t stream);
+size_t mil_colsoftmax_pool_workspace_bytes(int64_t n, int m);
+int    mil_expdot_rows_f32(const float* S, int64_t rows, int m, const float* M, const float* w, float* out, mil_stream_t stream);
+int    mil_dwconv_tokens_f32(const float* v, int64_t ldv, int64_t rows, int heads, int dh, const float* w, int taps, float* out, int64_t ldo,
+                             int accumulate, mil_stream_t stream);
+int    mil_ppeg_f32(const float* x, int H, int W, int C, const float* w49, const float* bias, float* y, mil_stream_t stream);
+
 /* Adam / AdamW optimiser step as ONE launch over all parameters (the reference builds torch.optim.Adam / AdamW,
  * train_utils.py:55-65, and calls optimizer.step() once per bag, engines/base_engine.py:110-120).  segs_dev: device array of records
  * (parameter, gradient, exp_avg, exp_avg_sq, n) cut into segments of a few 10^4 elements (one CTA each).  decoupled = 0: Adam (L2
  * weight decay added to the gradient), 1: AdamW.  bias_correction1 = 1 - beta1^t, bias_correction2_sqrt = sqrt(1 - beta2^t) for the
- * step count t of THIS step; step_dev (nullable) = device float holding t instead (capturable: CUDA-graph replays). */
+ * step count t of THIS step (betas are doubles so that 1 - beta is rounded once, as torch's python scalars are); step_dev (nullable) = device float holding t instead (capturable: CUDA-graph replays). */
 typedef struct { float* p; const float* g; float* m; float* v; int64_t n; } mil_adam_seg_t;
-int mil_adam_step_f32(const mil_adam_seg_t* segs_dev, int n_seg, float lr, float beta1, float beta2, float eps, float weight_decay,
+int mil_adam_step_f32(const mil_adam_seg_t* segs_dev, int n_seg, float lr, double beta1, double beta2, float eps, float weight_decay,
                       int decoupled, float bias_correction1, float bias_correction2_sqrt, const float* step_dev, mil_stream_t stream);
 
 /* Self-test hook for the tcgen05/TMA plumbing: C[M,N] = A[M,K] B[N,K]^T with the fused pass's operand pipeline

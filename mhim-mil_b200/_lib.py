@@ -39,6 +39,18 @@ _SIGS = {
                               c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "mil_linear_act_tc_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                       c_int, c_int, c_void_p]),
+    "mil_linear_act_tc_ld_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                         c_size_t, c_int, c_int, c_void_p]),
+    "mil_sgemm_batched_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                      c_int64, c_int, c_void_p]),
+    "mil_layernorm_fwd_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "mil_segment_mean_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "mil_row_softmax_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p]),
+    "mil_colsoftmax_pool_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mil_colsoftmax_pool_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "mil_expdot_rows_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mil_dwconv_tokens_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p]),
+    "mil_ppeg_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mil_linear_tc_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mil_skinny_supported": (c_int, [c_int64, c_int, c_int]),
     "mil_skinny_fwd_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -63,7 +75,7 @@ _SIGS = {
     "mil_mca_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_size_t, c_void_p]),
     "mil_mca_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
-    "mil_adam_step_f32": (c_int, [c_void_p, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_float, c_void_p, c_void_p]),
+    "mil_adam_step_f32": (c_int, [c_void_p, c_int, c_float, ctypes.c_double, ctypes.c_double, c_float, c_float, c_int, c_float, c_float, c_void_p, c_void_p]),
     "mil_ema_update_f32": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p]),
     "mil_topk_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mil_mask_from_indices": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

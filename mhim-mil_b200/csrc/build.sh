@@ -8,7 +8,7 @@ OUT="$HERE/../libmhimk.so"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -I"$ROOT/include" -I"$HERE")
 mkdir -p "$HERE/build"
 pids=()
-SRCS="mil_api mil_simt mil_topk mil_fused_sm100 mil_fused2_sm100 mil_wgrad_sm100 mil_skinny mil_rows"
+SRCS="mil_api mil_simt mil_topk mil_fused_sm100 mil_fused2_sm100 mil_wgrad_sm100 mil_skinny mil_rows mil_nystrom"
 for f in $SRCS; do
   if [ ! -f "$HERE/build/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/build/$f.o" ] || [ "$HERE/mil_common.cuh" -nt "$HERE/build/$f.o" ] || [ "$HERE/mil_umma.cuh" -nt "$HERE/build/$f.o" ] || [ "$ROOT/include/mhimk.h" -nt "$HERE/build/$f.o" ]; then
     "$NVCC" "${FLAGS[@]}" ${PTXAS_V:+-Xptxas -v} ${KSTAMP:+-DMIL_KSTAMP} -c "$HERE/$f.cu" -o "$HERE/build/$f.o" &

@@ -848,12 +848,13 @@ extern "C" int mil_umma_selftest_f32(const float* A, const float* B, float* C, i
 
 extern "C" size_t mil_linear_tc_workspace_bytes(int N, int K) { return (size_t)N * K * 4 + 1024 + 64; }
 
-extern "C" int mil_linear_act_tc_f32(const float* X, int64_t M, int K, const float* W, const float* bias, int N, int act, float* pre_out,
-                                     float* Y, const mil_dropout_t* drop, void* ws, size_t ws_bytes, int ws_ready, int precision,
-                                     mil_stream_t stream_) {
+extern "C" int mil_linear_act_tc_ld_f32(const float* X, int64_t ldx, int64_t M, int K, const float* W, const float* bias, int N, int act, float* pre_out,
+                                        float* Y, int64_t ldy, const mil_dropout_t* drop, void* ws, size_t ws_bytes, int ws_ready, int precision,
+                                        mil_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MIL_CHECK_ARG(mil_device_supported(), "mil_linear_act_tc_f32: needs a compute-capability 10.x device");
   MIL_CHECK_ARG(X && W && Y && ws && M > 0 && M < (1ll << 31) - 256, "mil_linear_act_tc_f32: bad argument");
+  MIL_CHECK_ARG(ldx >= K && ldx % 4 == 0 && ldy >= N && ldy % 4 == 0, "mil_linear_act_tc_f32: leading dimensions must cover the rows and be multiples of 4");
   MIL_CHECK_ARG(N >= 64 && N <= 512 && N % 64 == 0 && (N <= 256 || N == 512), "mil_linear_act_tc_f32: N=%d must be 64,128,192,256 or 512", N);
   MIL_CHECK_ARG(K >= BK && K % BK == 0, "mil_linear_act_tc_f32: K=%d must be a positive multiple of %d", K, BK);
   MIL_CHECK_ARG(precision >= 0 && precision <= 3, "mil_linear_act_tc_f32: bad precision");
@@ -868,11 +869,11 @@ extern "C" int mil_linear_act_tc_f32(const float* X, int64_t M, int K, const flo
     MIL_CUDA(cudaMemsetAsync(err, 0, 4 * sizeof(int), stream));
   }
   CUtensorMap mx;
-  if ((rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)M, (uint64_t)K, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d_ld(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   FusedParams p;
   p.N = M; p.D = K; p.nout = N; p.Da = 128; p.act = act; p.att_act = MIL_ACT_NONE;
   p.b1 = bias; p.ba = nullptr; p.wc = nullptr; p.bc = nullptr; p.keep = nullptr; p.Wp = nullptr; p.C = 0;
-  p.s_out = nullptr; p.t_out = nullptr; p.h_out = pre_out; p.part = nullptr; p.c_out = Y; p.ldc = N; p.err = err; p.dbg = 0;
+  p.s_out = nullptr; p.t_out = nullptr; p.h_out = pre_out; p.part = nullptr; p.c_out = Y; p.ldc = ldy; p.err = err; p.dbg = 0;
   p.w1_img = w_img; p.wa_img = w_img; p.trace = nullptr;
   p.stats = nullptr; p.pooled = nullptr; p.rec_out = nullptr; p.counter = nullptr; p.Wcls = nullptr; p.bcls = nullptr; p.n_cls = 0; p.logits = nullptr;
   if ((rc = set_dropout(p, drop, N))) return rc;
@@ -880,4 +881,10 @@ extern "C" int mil_linear_act_tc_f32(const float* X, int64_t M, int K, const flo
   const int64_t n_tiles = (M + BM - 1) / BM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   return dispatch_fused(precision, MODE_STORE, mx, p, grid, stream);
+}
+
+extern "C" int mil_linear_act_tc_f32(const float* X, int64_t M, int K, const float* W, const float* bias, int N, int act, float* pre_out,
+                                     float* Y, const mil_dropout_t* drop, void* ws, size_t ws_bytes, int ws_ready, int precision,
+                                     mil_stream_t stream_) {
+  return mil_linear_act_tc_ld_f32(X, K, M, K, W, bias, N, act, pre_out, Y, N, drop, ws, ws_bytes, ws_ready, precision, stream_);
 }

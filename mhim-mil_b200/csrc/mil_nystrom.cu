@@ -1,0 +1,265 @@
+// CUDA-core pieces of the Nystrom / TransMIL path (nystrom_attention.py:65-152, transmil.py:23-64, emb_position.py:85-120) that sit
+// between the tensor-core projections: LayerNorm, landmark segment means, softmax over the landmark axis, the streaming
+// softmax-over-N aggregation kv = softmax_N(q_l k^T) v of SURVEY 9.7 (the [m x N] similarity never needs a transpose or a second
+// materialisation), the 33-tap depth-wise residual convolution over the token axis, the cls-row attention read-out, the PPEG
+// depth-wise convolution and a batched fp32 GEMM for the 256 x 256 pseudo-inverse iteration.  All bandwidth- or FFMA-bound
+// streaming kernels; the big contractions (qkv, q k_l^T, softmax . Z, to_out) run on tcgen05 (mil_linear_act_tc_ld_f32).
+#include "mil_common.cuh"
+
+namespace mil {
+namespace nys {
+
+// y[r, :] = (x[r, :] - mean) * rstd * w + b       one warp per row
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t rows, int cols, const float* __restrict__ w,
+                                                        const float* __restrict__ b, float eps, float* __restrict__ y) {
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* xr = x + r * cols;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / cols;
+  float v = 0.f;
+  for (int c = lane; c < cols; c += 32) { const float d = xr[c] - mean; v = fmaf(d, d, v); }
+  const float rstd = rsqrtf(warp_sum(v) / cols + eps);
+  for (int c = lane; c < cols; c += 32) y[r * cols + c] = (xr[c] - mean) * rstd * w[c] + (b ? b[c] : 0.f);
+}
+
+// out[h][j][d] = scale * mean over the rows of segment j of x[row, col0 + h * dh + d]      grid = m segments, block = heads * dh threads
+__global__ void segment_mean_kernel(const float* __restrict__ x, int64_t ld, int seg_len, int col0, int heads, int dh, float scale, int m,
+                                    float* __restrict__ out) {
+  const int j = blockIdx.x, c = threadIdx.x;
+  if (c >= heads * dh) return;
+  const float* p = x + (int64_t)j * seg_len * ld + col0 + c;
+  float s = 0.f;
+  for (int r = 0; r < seg_len; ++r) s += p[(int64_t)r * ld];
+  const int h = c / dh, d = c % dh;
+  out[((int64_t)h * m + j) * dh + d] = s * (scale / seg_len);
+}
+
+// in-place softmax over the last axis of S [rows, cols] (cols <= 1024)      one warp per row
+__global__ void __launch_bounds__(256) row_softmax_kernel(float* __restrict__ S, int64_t rows, int cols) {
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float* s = S + r * cols;
+  float v[32];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < cols ? s[c] : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+  m = warp_max(m);
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    v[i] = (lane + 32 * i) < cols ? expf(v[i] - m) : 0.f;
+    l += v[i];
+  }
+  const float inv = 1.f / warp_sum(l);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + 32 * i;
+    if (c < cols) s[c] = v[i] * inv;
+  }
+}
+
+// ---- kv[j, :] = sum_n softmax_n(S[n, j]) v[n, :]  with S = (k q_l^T) given [n, m] (the transpose of sim3), m = blockDim = 256 ----
+// pass 1: pmax[chunk][j] = max over the chunk's rows
+__global__ void __launch_bounds__(256) colmax_kernel(const float* __restrict__ S, int64_t n, int m, int64_t rows_per_chunk, float* __restrict__ pmax) {
+  const int j = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk;
+  int64_t r1 = r0 + rows_per_chunk;
+  if (r1 > n) r1 = n;
+  float mx = -INFINITY;
+  if (j < m)
+    for (int64_t r = r0; r < r1; ++r) mx = fmaxf(mx, S[r * m + j]);
+  if (j < m) pmax[(int64_t)blockIdx.x * m + j] = mx;
+}
+// pass 2: per chunk, thread j: e = exp(S[r, j] - M[j]); pl[chunk][j] = sum e; pacc[chunk][j][d] = sum e * v[r, d]   (dh <= 64)
+__global__ void __launch_bounds__(256) colsoftmax_pool_kernel(const float* __restrict__ S, const float* __restrict__ V, int64_t ldv, int64_t n, int m, int dh,
+                                                              int64_t rows_per_chunk, const float* __restrict__ pmax, int chunks,
+                                                              float* __restrict__ colmax_out, float* __restrict__ pl, float* __restrict__ pacc) {
+  __shared__ float sv[32][64];
+  const int j = threadIdx.x;
+  float M = -INFINITY;
+  if (j < m)
+    for (int c = 0; c < chunks; ++c) M = fmaxf(M, pmax[(int64_t)c * m + j]);
+  if (blockIdx.x == 0 && j < m) colmax_out[j] = M;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk;
+  int64_t r1 = r0 + rows_per_chunk;
+  if (r1 > n) r1 = n;
+  float acc[64];
+#pragma unroll
+  for (int d = 0; d < 64; ++d) acc[d] = 0.f;
+  float l = 0.f;
+  for (int64_t rb = r0; rb < r1; rb += 32) {
+    const int nr = (int)((r1 - rb) < 32 ? (r1 - rb) : 32);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nr * 64; i += 256) {
+      const int rr = i >> 6, d = i & 63;
+      sv[rr][d] = d < dh ? V[(rb + rr) * ldv + d] : 0.f;
+    }
+    __syncthreads();
+    if (j < m)
+      for (int rr = 0; rr < nr; ++rr) {
+        const float e = expf(S[(rb + rr) * m + j] - M);
+        l += e;
+#pragma unroll
+        for (int d = 0; d < 64; ++d) acc[d] = fmaf(e, sv[rr][d], acc[d]);
+      }
+  }
+  if (j < m) {
+    pl[(int64_t)blockIdx.x * m + j] = l;
+    float* o = pacc + ((int64_t)blockIdx.x * m + j) * 64;
+#pragma unroll
+    for (int d = 0; d < 64; d += 4) *reinterpret_cast<float4*>(o + d) = make_float4(acc[d], acc[d + 1], acc[d + 2], acc[d + 3]);
+  }
+}
+// pass 3: out[j][d] = sum_chunks pacc / L[j];  L[j] = sum_chunks pl
+__global__ void colsoftmax_finish_kernel(const float* __restrict__ pl, const float* __restrict__ pacc, int chunks, int m, int dh, float* __restrict__ colsum_out,
+                                         float* __restrict__ out) {
+  const int j = blockIdx.x, d = threadIdx.x;
+  float L = 0.f;
+  for (int c = 0; c < chunks; ++c) L += pl[(int64_t)c * m + j];
+  if (d == 0) colsum_out[j] = L;
+  if (d < dh) {
+    float a = 0.f;
+    for (int c = 0; c < chunks; ++c) a += pacc[((int64_t)c * m + j) * 64 + d];
+    out[(int64_t)j * dh + d] = a / L;
+  }
+}
+
+// out[r] = sum_j w[j] * exp(S[r, j] - M[j])      (cls-row attention over the keys: w = r / L, nystrom_attention.py:143-150)    one warp per row
+__global__ void __launch_bounds__(256) expdot_rows_kernel(const float* __restrict__ S, int64_t rows, int m, const float* __restrict__ M,
+                                                          const float* __restrict__ w, float* __restrict__ out) {
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float a = 0.f;
+  for (int j = lane; j < m; j += 32) a = fmaf(w[j], expf(S[r * m + j] - M[j]), a);
+  a = warp_sum(a);
+  if (lane == 0) out[r] = a;
+}
+
+// out[r, h*dh + d] (+)= sum_t w[h][t] * v[r + t - taps/2, h*dh + d]  (zero padding)     thread per (r, c)
+__global__ void dwconv_tokens_kernel(const float* __restrict__ v, int64_t ldv, int64_t rows, int heads, int dh, const float* __restrict__ w, int taps,
+                                     float* __restrict__ out, int64_t ldo, int accumulate) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  const int64_t r = blockIdx.x;
+  if (c >= heads * dh) return;
+  const float* wh = w + (c / dh) * taps;
+  float a = 0.f;
+  for (int t = 0; t < taps; ++t) {
+    const int64_t rr = r + t - taps / 2;
+    if (rr >= 0 && rr < rows) a = fmaf(wh[t], v[rr * ldv + c], a);
+  }
+  float* o = out + r * ldo + c;
+  *o = accumulate ? *o + a : a;
+}
+
+// PPEG: y[(yy, xx), c] = sum_{dy, dx} W[c][dy][dx] * x[(yy + dy - 3, xx + dx - 3), c] + bias[c]   (7 x 7 effective depth-wise kernel, zero padding)
+__global__ void ppeg_kernel(const float* __restrict__ x, int H, int W, int C, const float* __restrict__ w49, const float* __restrict__ bias,
+                            float* __restrict__ y) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  const int pos = blockIdx.x;
+  if (c >= C) return;
+  const int yy = pos / W, xx = pos % W;
+  const float* wc = w49 + (int64_t)c * 49;
+  float a = bias ? bias[c] : 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 7; ++dy) {
+    const int y2 = yy + dy - 3;
+    if (y2 < 0 || y2 >= H) continue;
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx) {
+      const int x2 = xx + dx - 3;
+      if (x2 < 0 || x2 >= W) continue;
+      a = fmaf(wc[dy * 7 + dx], x[((int64_t)y2 * W + x2) * C + c], a);
+    }
+  }
+  y[(int64_t)pos * C + c] = a;
+}
+
+static int pool_chunks(int64_t n) {
+  int64_t c = (n + 255) / 256;
+  const int cap = 2 * num_sms();
+  if (c > cap) c = cap;
+  return (int)(c < 1 ? 1 : c);
+}
+
+}  // namespace nys
+}  // namespace mil
+
+using namespace mil;
+
+extern "C" int mil_layernorm_fwd_f32(const float* x, int64_t rows, int cols, const float* w, const float* b, float eps, float* y, mil_stream_t stream) {
+  MIL_CHECK_ARG(x && w && y && rows >= 0 && cols > 0, "mil_layernorm_fwd_f32: bad arguments");
+  if (rows == 0) return 0;
+  nys::layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, w, b, eps, y);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mil_segment_mean_f32(const float* x, int64_t ld, int m, int seg_len, int col0, int heads, int dh, float scale, float* out, mil_stream_t stream) {
+  MIL_CHECK_ARG(x && out && m > 0 && seg_len > 0 && heads * dh > 0 && heads * dh <= 1024, "mil_segment_mean_f32: bad arguments (heads * dh <= 1024)");
+  nys::segment_mean_kernel<<<m, heads * dh, 0, (cudaStream_t)stream>>>(x, ld, seg_len, col0, heads, dh, scale, m, out);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mil_row_softmax_f32(float* S, int64_t rows, int cols, mil_stream_t stream) {
+  MIL_CHECK_ARG(S && rows >= 0 && cols > 0 && cols <= 1024, "mil_row_softmax_f32: bad arguments (cols <= 1024)");
+  if (rows == 0) return 0;
+  nys::row_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, rows, cols);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t mil_colsoftmax_pool_workspace_bytes(int64_t n, int m) { return (size_t)nys::pool_chunks(n) * m * (2 + 64) * sizeof(float) + 64; }
+
+extern "C" int mil_colsoftmax_pool_f32(const float* S, const float* V, int64_t ldv, int64_t n, int m, int dh, float* out, float* colmax, float* colsum,
+                                       void* ws, size_t ws_bytes, mil_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIL_CHECK_ARG(S && V && out && colmax && colsum && ws && n > 0 && m > 0 && m <= 256 && dh > 0 && dh <= 64 && ldv >= dh,
+                "mil_colsoftmax_pool_f32: bad arguments (m <= 256, dh <= 64)");
+  MIL_CHECK_ARG(ws_bytes >= mil_colsoftmax_pool_workspace_bytes(n, m), "mil_colsoftmax_pool_f32: workspace too small");
+  const int chunks = nys::pool_chunks(n);
+  const int64_t per = (n + chunks - 1) / chunks;
+  float* pmax = (float*)ws;
+  float* pl = pmax + (size_t)chunks * m;
+  float* pacc = pl + (size_t)chunks * m;
+  nys::colmax_kernel<<<chunks, 256, 0, stream>>>(S, n, m, per, pmax);
+  MIL_LAUNCH_CHECK();
+  nys::colsoftmax_pool_kernel<<<chunks, 256, 0, stream>>>(S, V, ldv, n, m, dh, per, pmax, chunks, colmax, pl, pacc);
+  MIL_LAUNCH_CHECK();
+  nys::colsoftmax_finish_kernel<<<m, 64, 0, stream>>>(pl, pacc, chunks, m, dh, colsum, out);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mil_expdot_rows_f32(const float* S, int64_t rows, int m, const float* M, const float* w, float* out, mil_stream_t stream) {
+  MIL_CHECK_ARG(S && M && w && out && rows >= 0 && m > 0, "mil_expdot_rows_f32: bad arguments");
+  if (rows == 0) return 0;
+  nys::expdot_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, rows, m, M, w, out);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mil_dwconv_tokens_f32(const float* v, int64_t ldv, int64_t rows, int heads, int dh, const float* w, int taps, float* out, int64_t ldo,
+                                     int accumulate, mil_stream_t stream) {
+  MIL_CHECK_ARG(v && w && out && rows > 0 && rows < (1ll << 31) && heads * dh > 0 && taps > 0 && (taps & 1), "mil_dwconv_tokens_f32: bad arguments (odd taps)");
+  const int C = heads * dh;
+  nys::dwconv_tokens_kernel<<<dim3((unsigned)rows, (C + 255) / 256), C < 256 ? C : 256, 0, (cudaStream_t)stream>>>(v, ldv, rows, heads, dh, w, taps, out, ldo, accumulate);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mil_ppeg_f32(const float* x, int H, int W, int C, const float* w49, const float* bias, float* y, mil_stream_t stream) {
+  MIL_CHECK_ARG(x && w49 && y && H > 0 && W > 0 && C > 0, "mil_ppeg_f32: bad arguments");
+  nys::ppeg_kernel<<<dim3((unsigned)(H * W), (C + 255) / 256), C < 256 ? C : 256, 0, (cudaStream_t)stream>>>(x, H, W, C, w49, bias, y);
+  MIL_LAUNCH_CHECK();
+  return 0;
+}

@@ -15,6 +15,7 @@ struct SgemmParams {
   const float* B; int64_t sBn, sBk;
   const float* bias; float* C; int64_t ldc; float* pre_out;
   int64_t M, N, K; int act; int64_t k_per_split; float* partial; int vecA, vecB;
+  int batch; int64_t bA, bB, bC;      // batch > 1: blockIdx.z = batch index (element strides bA / bB / bC), no split-K
 };
 
 // Load a [128 x 8] operand tile into registers (4 floats per thread).
@@ -73,8 +74,12 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_kernel(const SgemmParams 
   __shared__ __align__(16) float As[2][SG_BK][SG_BM];
   __shared__ __align__(16) float Bs[2][SG_BK][SG_BN];
   const int64_t m0 = (int64_t)blockIdx.y * SG_BM, n0 = (int64_t)blockIdx.x * SG_BN;
-  const int64_t kbeg = (int64_t)blockIdx.z * p.k_per_split;
-  const int64_t kend = min(p.K, kbeg + p.k_per_split);
+  const bool batched = p.batch > 1;
+  const float* __restrict__ Ap = batched ? p.A + (int64_t)blockIdx.z * p.bA : p.A;
+  const float* __restrict__ Bp = batched ? p.B + (int64_t)blockIdx.z * p.bB : p.B;
+  float* __restrict__ Cp = batched ? p.C + (int64_t)blockIdx.z * p.bC : p.C;
+  const int64_t kbeg = batched ? 0 : (int64_t)blockIdx.z * p.k_per_split;
+  const int64_t kend = batched ? p.K : min(p.K, kbeg + p.k_per_split);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 
   float acc[8][8];
@@ -84,8 +89,8 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_kernel(const SgemmParams 
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
   float ra[4], rb[4];
-  load_tile<A_KC>(p.A, p.sAm, p.sAk, p.row_ids, m0, p.M, kbeg, kend, p.vecA, ra);
-  load_tile<B_KC>(p.B, p.sBn, p.sBk, nullptr, n0, p.N, kbeg, kend, p.vecB, rb);
+  load_tile<A_KC>(Ap, p.sAm, p.sAk, p.row_ids, m0, p.M, kbeg, kend, p.vecA, ra);
+  load_tile<B_KC>(Bp, p.sBn, p.sBk, nullptr, n0, p.N, kbeg, kend, p.vecB, rb);
   store_tile<A_KC>(As[0], ra);
   store_tile<B_KC>(Bs[0], rb);
   __syncthreads();
@@ -94,8 +99,8 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_kernel(const SgemmParams 
   for (int64_t k0 = kbeg; k0 < kend; k0 += SG_BK) {
     const bool more = k0 + SG_BK < kend;
     if (more) {
-      load_tile<A_KC>(p.A, p.sAm, p.sAk, p.row_ids, m0, p.M, k0 + SG_BK, kend, p.vecA, ra);
-      load_tile<B_KC>(p.B, p.sBn, p.sBk, nullptr, n0, p.N, k0 + SG_BK, kend, p.vecB, rb);
+      load_tile<A_KC>(Ap, p.sAm, p.sAk, p.row_ids, m0, p.M, k0 + SG_BK, kend, p.vecA, ra);
+      load_tile<B_KC>(Bp, p.sBn, p.sBk, nullptr, n0, p.N, k0 + SG_BK, kend, p.vecB, rb);
     }
 #pragma unroll
     for (int kk = 0; kk < SG_BK; ++kk) {
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(SG_THREADS, 2) sgemm_kernel(const SgemmParams 
       } else {
         if (p.bias) v += p.bias[n];
         if (p.pre_out) p.pre_out[m * p.ldc + n] = v;
-        p.C[m * p.ldc + n] = act_apply(v, p.act);
+        Cp[m * p.ldc + n] = act_apply(v, p.act);
       }
     }
   }
@@ -485,6 +490,7 @@ extern "C" int mil_sgemm_f32(const float* A, int64_t sAm, int64_t sAk, const int
   const int splits = K > 0 ? (int)((K + kps - 1) / kps) : 1;
   p.k_per_split = kps;
   p.partial = nullptr;
+  p.batch = 1; p.bA = p.bB = p.bC = 0;
   if (splits > 1) {
     MIL_CHECK_ARG(ws && ws_bytes >= (size_t)splits * M * N * sizeof(float), "mil_sgemm_f32: workspace too small for splitk");
     p.partial = (float*)ws;
@@ -502,6 +508,29 @@ extern "C" int mil_sgemm_f32(const float* A, int64_t sAm, int64_t sAk, const int
     splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(p.partial, splits, M, N, bias, C, ldc, pre_out, act);
     MIL_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+extern "C" int mil_sgemm_batched_f32(const float* A, int64_t sAm, int64_t sAk, int64_t bA, const float* B, int64_t sBn, int64_t sBk, int64_t bB, float* C,
+                                     int64_t ldc, int64_t bC, int64_t M, int64_t N, int64_t K, int batch, mil_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIL_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0 && ldc >= N && batch >= 1 && batch <= 65535, "mil_sgemm_batched_f32: bad arguments");
+  MIL_CHECK_ARG((sAk == 1 || sAm == 1) && (sBk == 1 || sBn == 1), "mil_sgemm_batched_f32: operands need a unit stride");
+  const bool a_kc = (sAk == 1), b_kc = (sBk == 1);
+  SgemmParams p;
+  p.A = A; p.sAm = sAm; p.sAk = sAk; p.row_ids = nullptr; p.B = B; p.sBn = sBn; p.sBk = sBk;
+  p.bias = nullptr; p.C = C; p.ldc = ldc; p.pre_out = nullptr; p.M = M; p.N = N; p.K = K; p.act = MIL_ACT_NONE;
+  p.k_per_split = K; p.partial = nullptr;
+  p.batch = batch < 2 ? 2 : batch;                       // batch == 1 still takes the batched addressing (blockIdx.z = 0)
+  p.bA = bA; p.bB = bB; p.bC = bC;
+  p.vecA = ((uintptr_t)A % 16 == 0) && ((a_kc ? sAm : sAk) % 4 == 0) && (bA % 4 == 0);
+  p.vecB = ((uintptr_t)B % 16 == 0) && ((b_kc ? sBn : sBk) % 4 == 0) && (bB % 4 == 0);
+  dim3 grid((unsigned)((N + SG_BN - 1) / SG_BN), (unsigned)((M + SG_BM - 1) / SG_BM), (unsigned)batch);
+  if (a_kc && b_kc) sgemm_kernel<true, true><<<grid, SG_THREADS, 0, stream>>>(p);
+  else if (a_kc) sgemm_kernel<true, false><<<grid, SG_THREADS, 0, stream>>>(p);
+  else if (b_kc) sgemm_kernel<false, true><<<grid, SG_THREADS, 0, stream>>>(p);
+  else sgemm_kernel<false, false><<<grid, SG_THREADS, 0, stream>>>(p);
+  MIL_LAUNCH_CHECK();
   return 0;
 }
 
@@ -618,8 +647,8 @@ extern "C" int mil_cam_score_dev_f32(const float* s, const float* t, int64_t L, 
 // multi-tensor launches per step, its single-tensor path ~10 per parameter).  Same arithmetic as torch.optim.Adam(W)'s reference
 // implementation (torch/optim/adam.py:_single_tensor_adam): L2 (Adam) or decoupled (AdamW) weight decay, lerp for the first moment,
 // mul + addcmul for the second, denom = sqrt(v) / sqrt(bias_correction2) + eps, p -= lr / bias_correction1 * m / denom.
-__global__ void adam_step_kernel(const mil_adam_seg_t* __restrict__ segs, float lr, float beta1, float beta2, float eps, float wd, int decoupled,
-                                 float bc1, float bc2_sqrt, const float* __restrict__ step_dev) {
+__global__ void adam_step_kernel(const mil_adam_seg_t* __restrict__ segs, float lr, float beta1, float beta2, float omb1, float omb2, float eps, float wd,
+                                 int decoupled, float bc1, float bc2_sqrt, const float* __restrict__ step_dev) {
   const mil_adam_seg_t sg = segs[blockIdx.x];
   if (step_dev) {                                      // capturable: the step count lives on the device (CUDA-graph replays)
     const float t = step_dev[0];
@@ -631,23 +660,24 @@ __global__ void adam_step_kernel(const mil_adam_seg_t* __restrict__ segs, float 
     float p = sg.p[i], g = sg.g[i], m = sg.m[i], v = sg.v[i];
     if (decoupled) p *= 1.f - lr * wd;
     else if (wd != 0.f) g = fmaf(wd, p, g);
-    m = fmaf(1.f - beta1, g - m, m);
-    v = fmaf(1.f - beta2, g * g, v * beta2);
+    m = fmaf(omb1, g - m, m);                          // lerp_(grad, 1 - beta1); 1 - beta rounded from double like torch's python scalars
+    v = fmaf(omb2, g * g, v * beta2);
     const float denom = sqrtf(v) / bc2_sqrt + eps;
     p -= step_size * (m / denom);
     sg.p[i] = p; sg.m[i] = m; sg.v[i] = v;
   }
 }
 
-extern "C" int mil_adam_step_f32(const mil_adam_seg_t* segs_dev, int n_seg, float lr, float beta1, float beta2, float eps, float weight_decay,
+extern "C" int mil_adam_step_f32(const mil_adam_seg_t* segs_dev, int n_seg, float lr, double beta1_d, double beta2_d, float eps, float weight_decay,
                                  int decoupled, float bias_correction1, float bias_correction2_sqrt, const float* step_dev, mil_stream_t stream) {
+  const float beta1 = (float)beta1_d, beta2 = (float)beta2_d;
   MIL_CHECK_ARG(segs_dev && n_seg >= 0, "mil_adam_step_f32: bad arguments");
   MIL_CHECK_ARG(lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && weight_decay >= 0.f,
                 "mil_adam_step_f32: invalid hyper-parameters (same checks as torch.optim.Adam)");
   MIL_CHECK_ARG(step_dev || (bias_correction1 > 0.f && bias_correction2_sqrt > 0.f), "mil_adam_step_f32: bias corrections must be positive");
   if (n_seg == 0) return 0;
-  adam_step_kernel<<<n_seg, 256, 0, (cudaStream_t)stream>>>(segs_dev, lr, beta1, beta2, eps, weight_decay, decoupled, bias_correction1,
-                                                            bias_correction2_sqrt, step_dev);
+  adam_step_kernel<<<n_seg, 256, 0, (cudaStream_t)stream>>>(segs_dev, lr, beta1, beta2, (float)(1.0 - (double)beta1_d), (float)(1.0 - (double)beta2_d), eps,
+                                                            weight_decay, decoupled, bias_correction1, bias_correction2_sqrt, step_dev);
   MIL_LAUNCH_CHECK();
   return 0;
 }

@@ -7,6 +7,7 @@ constructor arguments, hyper-parameter defaults, param-group semantics (schedule
 ({"step", "exp_avg", "exp_avg_sq"} per parameter) as torch's, so checkpoints interchange; `step()` runs mil_adam_step_f32 over a
 cached device table of (param, grad, exp_avg, exp_avg_sq) segments -- one table and one launch per param group.
 """
+import ctypes
 import math
 
 import torch
@@ -77,7 +78,7 @@ class FusedAdam(torch.optim.Optimizer):
             else:
                 t = float(first)
                 bc1, bc2s, step_dev = 1.0 - b1 ** t, math.sqrt(1.0 - b2 ** t), None
-            _lib.check(L.mil_adam_step_f32(_lib.ptr(table), table.shape[0], _lib.c_float(group["lr"]), _lib.c_float(b1), _lib.c_float(b2),
+            _lib.check(L.mil_adam_step_f32(_lib.ptr(table), table.shape[0], _lib.c_float(group["lr"]), ctypes.c_double(b1), ctypes.c_double(b2),
                                            _lib.c_float(group["eps"]), _lib.c_float(group["weight_decay"]), 1 if group["adamw"] else 0,
                                            _lib.c_float(bc1), _lib.c_float(bc2s), step_dev, _lib.stream_ptr()), "mil_adam_step_f32")
         ops.weights_touched()                              # the fused pass's cached weight images follow the update

@@ -39,6 +39,14 @@ def lin(layer: nn.Linear, x: torch.Tensor, act: str = "none") -> torch.Tensor:
     return ops.linear_act(x, layer.weight, layer.bias, act, volatile=layer.training)
 
 
+def layer_norm(norm: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
+    """norm(x) for x [1, n, dim]: the library's own kernel when no autograd is needed, torch's differentiable one otherwise."""
+    if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[0] == 1 and norm.weight is not None
+            and not (torch.is_grad_enabled() and (x.requires_grad or norm.weight.requires_grad))):
+        return ops.layernorm(x[0], norm.weight, norm.bias, norm.eps)[None]
+    return norm(x)
+
+
 def conv1d_full(conv: nn.Conv1d, B: torch.Tensor) -> torch.Tensor:
     """DSMIL's bag head `Conv1d(C, C, kernel_size=K)` applied to B [1, C, K] (dsmil.py:98-99, baseline.py:149-150): the kernel spans the
     whole length, so it is the Linear pred[o] = sum_{c,k} w[o,c,k] B[c,k] + b[o] over the flattened C*K inputs -> [1, C].  Runs in the

@@ -4,6 +4,8 @@ import math
 import torch
 from torch import nn
 
+from .. import ops
+
 
 class PPEG(nn.Module):
     def __init__(self, dim=512, k=7, conv_1d=False, bias=True):
@@ -23,6 +25,12 @@ class PPEG(nn.Module):
             zp = H * W - (N + add)
             x = torch.cat([x, x.new_zeros(B, zp, Cc)], dim=1)
             add += zp
+        convs = (self.proj, self.proj1, self.proj2)
+        own = (B == 1 and x.is_cuda and x.dtype == torch.float32 and all(c.kernel_size[0] == c.kernel_size[1] and c.kernel_size[0] <= 7 for c in convs)
+               and not (torch.is_grad_enabled() and (x.requires_grad or self.proj.weight.requires_grad)))
+        if own:                                                  # one depth-wise 7x7 kernel of the library (summed kernels + identity)
+            y = ops.ppeg_forward(x[0].contiguous(), H, W, convs)[None]
+            return y[:, :-add] if add > 0 else y
         g = x.transpose(1, 2).reshape(B, Cc, H, W)
         y = (self.proj(g) + g + self.proj1(g) + self.proj2(g)).flatten(2).transpose(1, 2)
         return y[:, :-add] if add > 0 else y

@@ -154,10 +154,11 @@ class TransLayer(C.MilModule):
         self.attn = NystromAttention(dim=dim, dim_head=dim // 8, heads=head, num_landmarks=dim // 2, pinv_iterations=6, residual=True, dropout=0.1)
 
     def forward(self, x, need_attn=False, need_v=False, no_norm=False):
+        xn = C.layer_norm(self.norm, x)
         if need_attn:
-            z, attn, v = self.attn(self.norm(x), return_attn=True, no_norm=no_norm)
+            z, attn, v = self.attn(xn, return_attn=True, no_norm=no_norm)
             return (x + z, attn, v) if need_v else (x + z, attn)
-        return x + self.attn(self.norm(x))
+        return x + self.attn(xn)
 
 
 class SAttention(C.MilModule):
@@ -191,7 +192,7 @@ class SAttention(C.MilModule):
             attn.append(a.clone())
         else:
             x = self.layer2(x)
-        cls = self.norm(x)[:, 0, :]
+        cls = C.layer_norm(self.norm, x[:, :1])[:, 0, :]               # only the cls row is read (baseline.py:281)
         if return_attn:
             out = [cls, attn]
             if return_act:

@@ -1,8 +1,10 @@
 """Nystrom self-attention with the reference's interface (modules/nystrom_attention.py:12-27, 31-152).
 
-Round-1 scope: the N-row projections (to_qkv, to_out) run in the CUDA GEMM of libmhimk; the landmark similarities,
-softmaxes, Moore-Penrose iteration and the depth-wise residual conv are expressed with torch CUDA ops (library kernels).
-DESIGN.md lists the fused landmark kernels as the next step for this row.
+Without autograd (inference, MHIM's teacher pass) the whole layer runs on the library's own kernels in the streaming form of SURVEY 9.7
+(ops.nystrom_attention_forward): tensor cores for to_qkv, q k_l^T, k q_l^T, softmax . Z and to_out; CUDA-core kernels for the landmark
+means, the softmaxes, the softmax-over-N aggregation, the 256 x 256 pseudo-inverse products (batched fp32 GEMM) and the 33-tap
+residual convolution -- no cuBLAS / cuDNN call.  With autograd (the selfattn student) the N-row projections run in the library's
+GEMMs and the landmark algebra is expressed with differentiable torch ops.
 """
 from math import ceil
 
@@ -10,6 +12,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .. import ops
 from . import _common as C
 
 
@@ -44,6 +47,13 @@ class NystromAttention(C.MilModule):
         if b != 1:
             raise RuntimeError("mhimk NystromAttention: batch must be 1 bag")
         h, m, iters = self.heads, self.num_landmarks, self.pinv_iterations
+        if not C.grad_needed(self, x) and m <= 256 and (self.to_qkv.weight.shape[0] // 3) // h <= 64 and x.dtype == torch.float32 and n > 1:
+            res = ops.nystrom_attention_forward(x[0], self.to_qkv.weight, self.to_out[0].weight, self.to_out[0].bias,
+                                                self.res_conv.weight if self.residual else None, h, m, iters, self.scale, return_attn=return_attn,
+                                                no_norm=no_norm, volatile=self.training)
+            if not return_attn:
+                return self.to_out[1](res)[None]
+            return self.to_out[1](res[0])[None], res[1][None], res[2][None]
         t = x[0]
         pad = (m - n % m) % m                                   # FRONT zero padding to a multiple of m (:70-73)
         if pad:

@@ -4,6 +4,7 @@ import math
 import torch
 from torch import nn
 
+from .. import ops
 from . import _common as C
 from .nystrom_attention import NystromAttention
 
@@ -16,10 +17,11 @@ class TransLayer(C.MilModule):
                                      dropout=0.1)
 
     def forward(self, x, need_attn=False, need_v=False, no_norm=False):
+        xn = C.layer_norm(self.norm, x)
         if need_attn:
-            z, attn, v = self.attn(self.norm(x), return_attn=True, no_norm=no_norm)
+            z, attn, v = self.attn(xn, return_attn=True, no_norm=no_norm)
             return (x + z, attn, v) if need_v else (x + z, attn)
-        return x + self.attn(self.norm(x))
+        return x + self.attn(xn)
 
 
 class PPEG(C.MilModule):
@@ -32,6 +34,8 @@ class PPEG(C.MilModule):
     def forward(self, x, H, W):
         B, _, Cc = x.shape
         cls, tok = x[:, :1], x[:, 1:]
+        if B == 1 and x.is_cuda and not C.grad_needed(self, x) and x.dtype == torch.float32:
+            return torch.cat((cls, ops.ppeg_forward(tok[0].contiguous(), H, W, (self.proj, self.proj1, self.proj2))[None]), dim=1)
         g = tok.transpose(1, 2).reshape(B, Cc, H, W)
         y = (self.proj(g) + g + self.proj1(g) + self.proj2(g)).flatten(2).transpose(1, 2)
         return torch.cat((cls, y), dim=1)
@@ -102,7 +106,7 @@ class TransMIL(C.MilModule):
             attn.append((a[:, :, :-add] if add > 0 else a).clone())
         else:
             h = self.layer2(h)
-        logits = C.lin(self.classifier, self.norm(h)[:, 0])
+        logits = C.lin(self.classifier, C.layer_norm(self.norm, h[:, :1])[:, 0])          # only the cls row is read (transmil.py:164-165)
         if return_attn:
             out = [logits, attn]
             if return_act:

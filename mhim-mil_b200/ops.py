@@ -207,8 +207,10 @@ def _tc_block(x, Wb, bb, act, pre_b, y_b, key_obj, blk, precision, volatile=Fals
         _drop_dead(_TC_CACHE, 256)
     if not ready:                                     # not valid until the call below has rebuilt the image (a failed
         _TC_CACHE[key] = (weakref.ref(key_obj), None, ws, where)   # call must not leave a "ready" entry behind)
-    check(L.mil_linear_act_tc_f32(ptr(x), M, K, ptr(Wb), ptr(bb), N, ACT[act], ptr(pre_b), ptr(y_b), dropout.c() if dropout else None,
-                                  ptr(ws), ws.numel(), ready, PREC[precision], stream_ptr()), "mil_linear_act_tc_f32")
+    # x / y may be column blocks of wider row-major buffers: pass their row strides as leading dimensions
+    check(L.mil_linear_act_tc_ld_f32(c_void_p(x.data_ptr()), x.stride(0), M, K, ptr(Wb), ptr(bb), N, ACT[act], ptr(pre_b), c_void_p(y_b.data_ptr()),
+                                     y_b.stride(0), dropout.c() if dropout else None, ptr(ws), ws.numel(), ready, PREC[precision], stream_ptr()),
+          "mil_linear_act_tc_f32")
     if not ready:
         _TC_CACHE[key] = (weakref.ref(key_obj), ver, ws, where)
 
@@ -461,6 +463,163 @@ def mask_from_indices(idx: torch.Tensor, n: int):
     len_keep = torch.empty(1, dtype=torch.int64, device=idx.device)
     check(L.mil_mask_from_indices(ptr(idx), idx.numel(), n, ptr(mask_ids), ptr(keep), ptr(len_keep), None, 0, stream_ptr()), "mil_mask_from_indices")
     return mask_ids, keep, len_keep
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Nystrom / TransMIL forward (no autograd): every contraction on the library's own kernels
+# --------------------------------------------------------------------------------------------------------------
+NYSTROM_PRECISION = "fp16x3"     # K = 64 / 256 contractions of O(1) operands: fp16 hi+lo sits well below bf16 hi+lo there (tests/test_gpu_umma.py)
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], eps: float = 1e-5) -> torch.Tensor:
+    """LayerNorm over the last axis of x [rows, cols] (no autograd; mil_layernorm_fwd_f32)."""
+    x = _need(x, "x")
+    y = torch.empty_like(x)
+    check(_lib.lib().mil_layernorm_fwd_f32(ptr(x), x.shape[0], x.shape[1], ptr(w), ptr(b), c_float(eps), ptr(y), stream_ptr()), "mil_layernorm_fwd_f32")
+    return y
+
+
+def bmm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """[B, M, K] @ [B, K, N] in exact fp32 on the CUDA cores (mil_sgemm_batched_f32); contiguous operands, no autograd."""
+    a, b = _need(a, "a"), _need(b, "b")
+    B, M, K = a.shape
+    N = b.shape[2]
+    c = torch.empty((B, M, N), dtype=torch.float32, device=a.device)
+    check(_lib.lib().mil_sgemm_batched_f32(ptr(a), K, 1, M * K, ptr(b), 1, N, K * N, ptr(c), N, M * N, M, N, K, B, stream_ptr()), "mil_sgemm_batched_f32")
+    return c
+
+
+def bmm_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """[B, M, K] @ [B, N, K]^T (contiguous) -> [B, M, N], exact fp32."""
+    a, b = _need(a, "a"), _need(b, "b")
+    B, M, K = a.shape
+    N = b.shape[1]
+    c = torch.empty((B, M, N), dtype=torch.float32, device=a.device)
+    check(_lib.lib().mil_sgemm_batched_f32(ptr(a), K, 1, M * K, ptr(b), K, 1, N * K, ptr(c), N, M * N, M, N, K, B, stream_ptr()), "mil_sgemm_batched_f32")
+    return c
+
+
+def _tc_nt_view(x_view, W, y_view, ws, precision):
+    """y_view[M, N] = x_view[M, K] @ W[N, K]^T on the tensor cores for operands that are column blocks of wider buffers (row stride =
+    leading dimension); W contiguous, its image is rebuilt on every call (it is an activation, not a parameter)."""
+    M, K = x_view.shape
+    N = W.shape[0]
+    check(_lib.lib().mil_linear_act_tc_ld_f32(c_void_p(x_view.data_ptr()), x_view.stride(0), M, K, ptr(W), None, N, ACT["none"], None,
+                                              c_void_p(y_view.data_ptr()), y_view.stride(0), None, ptr(ws), ws.numel(), 0, PREC[precision], stream_ptr()),
+          "mil_linear_act_tc_ld_f32")
+
+
+def pinv_iter(x: torch.Tensor, iters: int = 6) -> torch.Tensor:
+    """Moore-Penrose iteration of nystrom_attention.py:12-27 on x [heads, m, m]; ONE global scalar normaliser over all heads (:18).
+    The 4 x iters batched products run in mil_sgemm_batched_f32 (exact fp32); the affine combinations are elementwise."""
+    ax = x.abs()
+    z = (x.transpose(-1, -2) / (ax.sum(dim=-1).max() * ax.sum(dim=-2).max())).contiguous()
+    eye = torch.eye(x.shape[-1], device=x.device, dtype=x.dtype)[None]
+    for _ in range(iters):
+        xz = bmm(x, z)
+        z = 0.25 * bmm(z, 13 * eye - bmm(xz, 15 * eye - bmm(xz, 7 * eye - xz)))
+    return z
+
+
+@torch.no_grad()
+def nystrom_attention_forward(xn, Wqkv, Wout, bout, conv_w, heads, m, iters, scale, return_attn=False, no_norm=False, volatile=False):
+    """NystromAttention.forward (nystrom_attention.py:65-152) for one bag without autograd, in the streaming form of SURVEY 9.7.
+
+    xn [n, dim] (already normalised by the caller's LayerNorm).  Returns out [n, dim] and, with return_attn, the cls-row attention
+    over the other tokens [heads, n-1] and v [heads, n-1, dh].
+      to_qkv                     tensor cores, written as three column blocks of ONE [n_pad, 3*inner] buffer (no cat)
+      landmarks                  segment means of q and k (mil_segment_mean_f32)
+      pass A, per head           S = k q_l^T [n_pad, m] (tensor cores) -> kv = softmax_N(S)^T v with column max / sum
+                                 (mil_colsoftmax_pool_f32): attn3 @ v without a transposed / second similarity tensor
+      landmark block             A2 = softmax(q_l k_l^T) (batched fp32 GEMM + row softmax), A2^+ (pinv_iter), Z = A2^+ kv
+      pass B, per head           P = softmax_m(q k_l^T) [n_pad, m] (tensor cores + row softmax) -> out_h = P Z_h (tensor cores, written
+                                 into its 64 columns of the merged-heads buffer); reassociated: (attn1 @ attn2^+) @ (attn3 @ v)
+                                 = attn1 @ (attn2^+ @ (attn3 @ v)) saves the [n, m] x [m, m] product
+      residual conv              33 taps over the token axis, depth-wise per head, accumulated into the same buffer
+      to_out                     tensor cores
+    """
+    L = _lib.lib()
+    xn = _need(xn, "x")
+    n, dim = xn.shape
+    inner = Wqkv.shape[0] // 3
+    dh = inner // heads
+    dev = xn.device
+    pad = (m - n % m) % m
+    npad = n + pad
+    seg = npad // m
+    xp = torch.cat([xn.new_zeros(pad, dim), xn], dim=0) if pad else xn                       # FRONT zero padding (:70-73)
+    qkv = torch.empty((npad, 3 * inner), dtype=torch.float32, device=dev)
+    for blk in range(3):                                                                      # q | k | v column blocks, no bias (:52)
+        Wb = Wqkv[blk * inner:(blk + 1) * inner]
+        _tc_block(xp, Wb, None, "none", None, qkv[:, blk * inner:(blk + 1) * inner], Wqkv, blk, DEFAULT_PRECISION, volatile)
+    ql, kl = torch.empty((heads, m, dh), dtype=torch.float32, device=dev), torch.empty((heads, m, dh), dtype=torch.float32, device=dev)
+    check(L.mil_segment_mean_f32(ptr(qkv), 3 * inner, m, seg, 0, heads, dh, c_float(scale), ptr(ql), stream_ptr()), "mil_segment_mean_f32")   # q is scaled (:89)
+    check(L.mil_segment_mean_f32(ptr(qkv), 3 * inner, m, seg, inner, heads, dh, c_float(1.0), ptr(kl), stream_ptr()), "mil_segment_mean_f32")
+    kl_s = kl * scale                                                                         # (scale q) k_l^T == q (scale k_l)^T
+    s2 = bmm_nt(ql, kl)                                                                       # [heads, m, m]
+    a2 = s2.clone()
+    check(L.mil_row_softmax_f32(ptr(a2), heads * m, m, stream_ptr()), "mil_row_softmax_f32")
+    S = torch.empty((npad, m), dtype=torch.float32, device=dev)
+    ws_t = _ws(L.mil_linear_tc_workspace_bytes(max(m, dh), max(m, dh)), dev)
+    ws_p = _ws(L.mil_colsoftmax_pool_workspace_bytes(npad, m), dev)
+    kv = torch.empty((heads, m, dh), dtype=torch.float32, device=dev)
+    M3, L3 = torch.empty((heads, m), dtype=torch.float32, device=dev), torch.empty((heads, m), dtype=torch.float32, device=dev)
+    for h in range(heads):                                                                    # pass A
+        _tc_nt_view(qkv[:, inner + h * dh: inner + (h + 1) * dh], ql[h], S, ws_t, NYSTROM_PRECISION)
+        check(L.mil_colsoftmax_pool_f32(ptr(S), c_void_p(qkv.data_ptr() + 4 * (2 * inner + h * dh)), 3 * inner, npad, m, dh, ptr(kv[h]), ptr(M3[h]), ptr(L3[h]),
+                                        ptr(ws_p), ws_p.numel(), stream_ptr()), "mil_colsoftmax_pool_f32")
+    a2i = pinv_iter(a2, iters)
+    Zt = bmm(a2i, kv).transpose(1, 2).contiguous()                                            # [heads, dh, m]: the "weight" of the second product
+    out = torch.empty((npad, inner), dtype=torch.float32, device=dev)
+    cls_rows = torch.empty((heads, m), dtype=torch.float32, device=dev) if return_attn else None
+    for h in range(heads):                                                                    # pass B
+        _tc_nt_view(qkv[:, h * dh:(h + 1) * dh], kl_s[h], S, ws_t, NYSTROM_PRECISION)
+        if return_attn and no_norm:
+            cls_rows[h].copy_(S[pad])                                                         # raw similarities of the cls query (:146-147)
+        check(L.mil_row_softmax_f32(ptr(S), npad, m, stream_ptr()), "mil_row_softmax_f32")
+        if return_attn and not no_norm:
+            cls_rows[h].copy_(S[pad])
+        _tc_nt_view(S, Zt[h], out[:, h * dh:(h + 1) * dh], ws_t, NYSTROM_PRECISION)
+    if conv_w is not None:                                                                    # out += res_conv(v) (:135-136)
+        taps = conv_w.shape[2]
+        check(L.mil_dwconv_tokens_f32(c_void_p(qkv.data_ptr() + 4 * 2 * inner), 3 * inner, npad, heads, dh, ptr(conv_w.reshape(heads, taps).contiguous()), taps, ptr(out),
+                                      inner, 1, stream_ptr()), "mil_dwconv_tokens_f32")
+    y = linear_forward(out, Wout, bout, "none", volatile=volatile)[pad:]
+    if not return_attn:
+        return y
+    # cls-row attention over the last n-1 keys (:143-150): r = attn1[cls] @ attn2^+ (no_norm: raw sims and the pinv of the raw block)
+    r = bmm(cls_rows[:, None, :].contiguous(), pinv_iter(s2, iters) if no_norm else a2i)[:, 0]            # [heads, m]
+    attn = torch.empty((heads, n - 1), dtype=torch.float32, device=dev)
+    rows0 = pad + 1
+    for h in range(heads):
+        Sk = S[: n - 1]
+        _tc_nt_view(qkv[rows0:, inner + h * dh: inner + (h + 1) * dh], ql[h], Sk, ws_t, NYSTROM_PRECISION)          # sim3^T for the real keys
+        if no_norm:
+            check(L.mil_skinny_fwd_f32(ptr(Sk), m, n - 1, m, ptr(r[h].contiguous()), None, 1, ACT["none"], None, ptr(attn[h]), stream_ptr()), "mil_skinny_fwd_f32")
+        else:
+            check(L.mil_expdot_rows_f32(ptr(Sk), n - 1, m, ptr(M3[h]), ptr((r[h] / L3[h]).contiguous()), ptr(attn[h]), stream_ptr()), "mil_expdot_rows_f32")
+    v = qkv[rows0:, 2 * inner:].reshape(n - 1, heads, dh).permute(1, 0, 2)
+    return y, attn, v
+
+
+@torch.no_grad()
+def ppeg_forward(tokens, H, W, convs):
+    """PPEG on the [H*W, C] token grid (transmil.py:50-64, emb_position.py:85-120): proj(x) + x + proj1(x) + proj2(x) as ONE depth-wise 7x7
+    convolution with the summed kernel (5x5 and 3x3 zero-padded to 7x7, identity at the centre) and summed bias."""
+    tokens = _need(tokens, "tokens")
+    C = tokens.shape[1]
+    w = torch.zeros((C, 7, 7), dtype=torch.float32, device=tokens.device)
+    bias = torch.zeros(C, dtype=torch.float32, device=tokens.device)
+    for conv in convs:
+        k = conv.weight.shape[-1]
+        o = (7 - k) // 2
+        w[:, o:o + k, o:o + k] += conv.weight[:, 0]
+        if conv.bias is not None:
+            bias += conv.bias
+    w[:, 3, 3] += 1.0
+    y = torch.empty_like(tokens)
+    check(_lib.lib().mil_ppeg_f32(ptr(tokens), H, W, C, ptr(w.reshape(C, 49).contiguous()), ptr(bias), ptr(y), stream_ptr()), "mil_ppeg_f32")
+    return y
 
 
 # --------------------------------------------------------------------------------------------------------------
