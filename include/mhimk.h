@@ -283,7 +283,7 @@ int mil_ema_update_f32(const mil_ema_seg_t* segs_dev, int n_seg, float mm, float
  *                             attn3 @ v without materialising attn3 (SURVEY 9.7 pass A); also returns the column maxima / sums.
  *   mil_expdot_rows_f32       out[r] = sum_j w[j] exp(S[r,j] - M[j])  -- the cls-row attention over the keys (:143-150).
  *   mil_dwconv_tokens_f32     out[r, c] (+)= sum_t w[head(c)][t] v[r + t - taps/2, c]: the depth-wise residual conv over tokens (:135-136).
- *   mil_ppeg_f32              y = depth-wise 7x7 conv (zero padded) of the [H*W, C] token grid with an effective kernel w49 [C,49] (= 7x7 + padded
+ *   mil_ppeg_f32              y = depth-wise 7x7 conv (zero padded) of the [H*W, C] token grid with an effective kernel w49 [49,C] (tap-major; = 7x7 + padded
  *                             5x5 + padded 3x3 + identity) + bias (transmil.py:50-64, emb_position.py:85-120). */
 int    mil_layernorm_fwd_f32(const float* x, int64_t rows, int cols, const float* w, const float* b, float eps, float* y, mil_stream_t stream);
 int    mil_segment_mean_f32(const float* x, int64_t ld, int m, int seg_len, int col0, int heads, int dh, float scale, float* out, mil_stream_t stream);

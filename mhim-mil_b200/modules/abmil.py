@@ -12,23 +12,36 @@ from torch import nn
 
 from .. import ops
 from ._common import MilModule, act_module, grad_needed, init_linear_layers, lin, require_cuda
+from .emb_position import SINCOS
 
 
 class DAttention(MilModule):
     def __init__(self, input_dim, n_classes, dropout, act, mil_norm=None, mil_bias=True, mil_cls_bias=True, inner_dim=512,
                  embed_feat=True, embed_norm_pos=0, pos=None, **kwargs):
         super().__init__()
-        if mil_norm not in (None, "none"):
-            raise NotImplementedError("mhimk DAttention: mil_norm='bn'/'ln' (abmil.py:167-176) is outside the accelerated path")
-        if pos not in ("none", None):
-            raise NotImplementedError("mhimk DAttention: pos='sincos' (abmil.py:162-163) is outside the accelerated path")
+        assert pos in ("sincos", "none", None) and embed_norm_pos in (0, 1)                   # abmil.py:159-160
         self.L, self.D, self.K = inner_dim, 128, 1
-        self.mil_norm, self.embed_norm_pos, self.pos = None, embed_norm_pos, pos
+        self.mil_norm = mil_norm if mil_norm in ("bn", "ln") else None
+        self.embed_norm_pos, self.pos = embed_norm_pos, pos
         self.act = act.lower() if act.lower() == "gelu" else "relu"       # anything but gelu falls back to ReLU (abmil.py:183-186)
         self.p_drop = 0.25 if dropout else 0.0                            # hard-coded 0.25 when truthy (abmil.py:188-189)
         if mil_bias:
             mil_cls_bias = True
+        self.pos_embed = SINCOS() if pos == "sincos" else nn.Identity()
         layers = []
+        # the norm layers own their parameters under the reference's keys (abmil.py:167-178): `norm.*` / `norm1.*`, or `feature.0.*` for
+        # the input LayerNorm, which shifts the Linear to `feature.1.*`
+        self.norm1 = self.norm = nn.Identity()
+        if self.mil_norm == "bn":
+            self.norm = nn.BatchNorm1d(input_dim if embed_norm_pos == 0 else inner_dim)
+            self.norm1 = nn.BatchNorm1d(self.L * self.K)
+        elif self.mil_norm == "ln":
+            if embed_norm_pos == 0:
+                layers += [nn.LayerNorm(input_dim, bias=mil_bias)]
+            else:
+                self.norm = nn.LayerNorm(inner_dim, bias=mil_bias)
+            self.norm1 = nn.LayerNorm(self.L * self.K, bias=mil_bias)
+        self._lin = len(layers)                                            # index of the Linear inside `feature`
         if embed_feat:
             layers += [nn.Linear(input_dim, inner_dim, bias=mil_bias), act_module(self.act)]
             if dropout:
@@ -36,15 +49,13 @@ class DAttention(MilModule):
         self.feature = nn.Sequential(*layers) if layers else nn.Identity()
         self.attention = nn.Sequential(nn.Linear(self.L, self.D, bias=mil_bias), nn.Tanh(), nn.Linear(self.D, self.K, bias=mil_bias))
         self.classifier = nn.Linear(self.L * self.K, n_classes, bias=mil_cls_bias)
-        self.norm = self.norm1 = nn.Identity()
-        self.pos_embed = nn.Identity()
         self.embed_feat = embed_feat
         self.precision = ops.DEFAULT_PRECISION
         init_linear_layers(self)
 
     def _fused_ok(self, x):
-        return (self.embed_feat and self.feature[0].bias is not None and self.L == 512 and x.shape[-1] % 32 == 0
-                and self.classifier.out_features <= 64)
+        return (self.embed_feat and self.mil_norm is None and self.pos != "sincos" and self.feature[0].bias is not None and self.L == 512
+                and x.shape[-1] % 32 == 0 and self.classifier.out_features <= 64)
 
     def _dropout(self, rows, device):
         if self.training and self.p_drop > 0 and self.embed_feat:
@@ -69,17 +80,29 @@ class DAttention(MilModule):
             attn = torch.exp(out["s"] - out["stats"][0]) / out["stats"][1] if return_attn else None
             h = out["h"]
         else:
+            # composed path (autograd, or a configuration outside the fused kernel: mil_norm bn / ln, pos = sincos)
+            if self.mil_norm == "bn" and self.embed_norm_pos == 0:
+                x2 = self.norm(x2)                                         # BatchNorm1d over the instances (abmil.py:207-211: the transposes only move the channel axis)
             if self.embed_feat:                                            # dropout inside the GEMM's epilogue (abmil.py:188-189)
-                f0 = self.feature[0]
+                if self._lin == 1:
+                    x2 = self.feature[0](x2)                               # input LayerNorm (mil_norm = 'ln', embed_norm_pos = 0)
+                f0 = self.feature[self._lin]
                 h = ops.linear_act(x2, f0.weight, f0.bias, self.act, volatile=f0.training, dropout=self._dropout(x2.shape[0], x2.device))
             else:
-                h = x2
+                h = self.feature(x2) if self._lin == 1 else x2
+            if self.pos == "sincos":
+                h = self.pos_embed(h[None], pos=pos)[0]
+            if self.embed_norm_pos == 1 and self.mil_norm is not None:
+                h = self.norm(h)
             u = lin(att0, h, "tanh")
             s = lin(att2, u)[:, 0]
             pooled, attn = ops.softmax_pool(s, h)
             fused_logits = None
         img_feat = pooled[None]
-        logits = fused_logits if fused_logits is not None else lin(self.classifier, img_feat)
+        if fused_logits is not None:
+            logits = fused_logits
+        else:
+            logits = lin(self.classifier, self.norm1(img_feat))
         if return_img_feat:
             logits = [logits, img_feat]
         if return_attn:

@@ -7,6 +7,28 @@ from torch import nn
 from .. import ops
 
 
+class SINCOS(nn.Module):
+    """2-D sin/cos positional embedding added to the embedded instances (reference: modules/emb_position.py:5-84, used by
+    abmil.DAttention(pos='sincos'), abmil.py:162-163, 214-215).  `pos` [1, N+1, 2] or [N+1, 2]: row 0 = (W, H) of the slide's patch grid,
+    rows 1.. = (x, y) of every instance.  The reference builds the full H x W table and gathers row y * W + x; the entry only depends on
+    (x, y), so it is evaluated directly: [sin(x w), cos(x w), sin(y w), cos(y w)], w_k = 10000^(-k / (C/4)), k < C/4."""
+
+    def forward(self, x, pos=None):
+        B, N, C = x.shape
+        if pos is None:
+            raise RuntimeError("SINCOS needs the patch coordinates `pos`")
+        if pos.dim() == 3:
+            if pos.size(0) != 1:
+                raise RuntimeError("mhimk SINCOS: batch must be 1 bag")
+            pos = pos[0]
+        xy = pos[1:].to(device=x.device, dtype=torch.float32)
+        quarter = C // 4
+        omega = 1.0 / (10000 ** (torch.arange(quarter, dtype=torch.float32, device=x.device) / quarter))
+        ax, ay = xy[:, 0:1] * omega, xy[:, 1:2] * omega
+        emb = torch.cat([torch.sin(ax), torch.cos(ax), torch.sin(ay), torch.cos(ay)], dim=1)
+        return x + emb[None]
+
+
 class PPEG(nn.Module):
     def __init__(self, dim=512, k=7, conv_1d=False, bias=True):
         super().__init__()

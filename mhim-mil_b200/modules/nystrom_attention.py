@@ -47,7 +47,8 @@ class NystromAttention(C.MilModule):
         if b != 1:
             raise RuntimeError("mhimk NystromAttention: batch must be 1 bag")
         h, m, iters = self.heads, self.num_landmarks, self.pinv_iterations
-        if not C.grad_needed(self, x) and m <= 256 and (self.to_qkv.weight.shape[0] // 3) // h <= 64 and x.dtype == torch.float32 and n > 1:
+        if (not C.grad_needed(self, x) and m <= 256 and (self.to_qkv.weight.shape[0] // 3) // h <= 64 and x.dtype == torch.float32 and n > 1
+                and (not self.residual or self.res_conv.weight.shape[2] <= 33)):
             res = ops.nystrom_attention_forward(x[0], self.to_qkv.weight, self.to_out[0].weight, self.to_out[0].bias,
                                                 self.res_conv.weight if self.residual else None, h, m, iters, self.scale, return_attn=return_attn,
                                                 no_norm=no_norm, volatile=self.training)

@@ -100,7 +100,12 @@ def _need(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise RuntimeError(f"mhimk: `{name}` must be a CUDA tensor -- there is no CPU path (got {getattr(t, 'device', type(t))})")
     if t.dtype != dtype:
-        raise RuntimeError(f"mhimk: `{name}` must be {dtype} (got {t.dtype})")
+        if dtype == torch.float32 and t.dtype in (torch.float16, torch.bfloat16):
+            # `--amp` (engines/base_engine.py:78: torch.autocast(float16)) hands the kernels half-precision activations produced by
+            # autocast'ed torch ops: compute in fp32 like torch.amp.custom_fwd(cast_inputs=torch.float32) would
+            t = t.float()
+        else:
+            raise RuntimeError(f"mhimk: `{name}` must be {dtype} (got {t.dtype})")
     return t if t.is_contiguous() else t.contiguous()
 
 
@@ -618,7 +623,7 @@ def ppeg_forward(tokens, H, W, convs):
             bias += conv.bias
     w[:, 3, 3] += 1.0
     y = torch.empty_like(tokens)
-    check(_lib.lib().mil_ppeg_f32(ptr(tokens), H, W, C, ptr(w.reshape(C, 49).contiguous()), ptr(bias), ptr(y), stream_ptr()), "mil_ppeg_f32")
+    check(_lib.lib().mil_ppeg_f32(ptr(tokens), H, W, C, ptr(w.reshape(C, 49).t().contiguous()), ptr(bias), ptr(y), stream_ptr()), "mil_ppeg_f32")
     return y
 
 
@@ -773,16 +778,24 @@ def abmil_fused_forward(x, W1, b1, act, Wa, ba, wc, bc, att_act="tanh", keep=Non
     H, Da = W1.shape[0], Wa.shape[0]
     dev = x.device
     npart = L.mil_fused_num_partials()
-    part = torch.empty((npart, 2 + H), dtype=torch.float32, device=dev)
-    stats = torch.empty(2, dtype=torch.float32, device=dev)
-    pooled = torch.empty(H, dtype=torch.float32, device=dev)
+    ncls = Wcls.shape[0] if Wcls is not None else 0
+    # one allocation for every small output (partials, stats, pooled, logits, exchange record): the host side of a bag is a handful of
+    # python calls, and at 8 ranks per node each torch.empty is a contended allocator round trip (7 % at N > 1)
+    n_part = npart * (2 + H)
+    n_small = n_part + (-n_part) % 4 + 4 + H + (-H) % 4 + ((ncls + 3) // 4) * 4 + (2 + H if want_record else 0)
+    small = torch.empty(n_small, dtype=torch.float32, device=dev)            # every sub-buffer starts 16-byte aligned
+    o = n_part + (-n_part) % 4
+    part, stats = small[:n_part].view(npart, 2 + H), small[o:o + 2]
+    o += 4
+    pooled = small[o:o + H]
+    o += H + (-H) % 4
+    logits = small[o:o + ncls].view(1, ncls) if Wcls is not None else None
+    o += ((ncls + 3) // 4) * 4
+    rec = small[o:o + 2 + H] if want_record else None
     s = torch.empty(N, dtype=torch.float32, device=dev) if want_scores else None
     C = Wp.shape[0] if Wp is not None else 0
     t = torch.empty((N, C), dtype=torch.float32, device=dev) if Wp is not None else None
     h = torch.empty((N, H), dtype=torch.float32, device=dev) if want_h else None
-    ncls = Wcls.shape[0] if Wcls is not None else 0
-    logits = torch.empty((1, ncls), dtype=torch.float32, device=dev) if Wcls is not None else None
-    rec = torch.empty(2 + H, dtype=torch.float32, device=dev) if want_record else None
     pipeline = _pipeline(pipeline, precision)
     ws, ready, commit = _fused_workspace(W1, Wa, precision, pipeline, volatile)
     check(L.mil_abmil_fused_fwd_f32(ptr(x), N, D, H, ptr(W1), ptr(b1), ACT[act], ptr(Wa), ptr(ba), None, None, Da, ACT[att_act], ptr(wc),

@@ -86,25 +86,63 @@ def merge_partials(ms: Sequence[Tensor], ls: Sequence[Tensor], Ps: Sequence[Tens
 # ----------------------------------------------------------------------------------------------
 # a1 / a2 : plain ABMIL heads
 # ----------------------------------------------------------------------------------------------
+def sincos_embed(pos: Tensor, C: int) -> Tensor:
+    """modules/emb_position.py:9-72: row y * W + x of the 2-D sin/cos table = [sin(x w), cos(x w), sin(y w), cos(y w)] with
+    w_k = 10000^(-k / (C/4)).  pos [N+1, 2]: row 0 = (W, H), rows 1.. = (x, y) per instance.  -> [N, C]"""
+    xy = pos[1:].to(torch.float32)
+    q = C // 4
+    omega = 1.0 / (10000 ** (torch.arange(q, dtype=torch.float32) / q))
+    ax, ay = xy[:, 0:1] * omega, xy[:, 1:2] * omega
+    return torch.cat([torch.sin(ax), torch.cos(ax), torch.sin(ay), torch.cos(ay)], dim=1)
+
+
+def _batchnorm_rows(x: Tensor, sd: SD, key: str, training: bool, eps: float = 1e-5) -> Tensor:
+    """nn.BatchNorm1d over the instances (abmil.py:207-211, 217-221: transposing [1,N,C] -> [1,C,N] only moves the channel axis)."""
+    if training:
+        mu, var = x.mean(0), x.var(0, unbiased=False)
+    else:
+        mu, var = sd[key + ".running_mean"], sd[key + ".running_var"]
+    return (x - mu) / torch.sqrt(var + eps) * sd[key + ".weight"] + sd[key + ".bias"]
+
+
 def abmil_dattention(sd: SD, x: Tensor, act: str = "relu", return_attn: bool = False,
-                     return_act: bool = False, return_img_feat: bool = False, drop_mask: Optional[Tensor] = None):
-    """modules/abmil.py:203-251 (DAttention.forward), mil_norm=None, pos=None.  drop_mask [N,512] (keep/(1-p), i.e. what
-    nn.Dropout(0.25) of `feature` (:188-189) multiplies by in train mode) or None for dropout off.
+                     return_act: bool = False, return_img_feat: bool = False, drop_mask: Optional[Tensor] = None,
+                     mil_norm: Optional[str] = None, embed_norm_pos: int = 0, pos: Optional[Tensor] = None, training: bool = False):
+    """modules/abmil.py:203-251 (DAttention.forward).  drop_mask [N,512] (keep/(1-p), i.e. what nn.Dropout(0.25) of `feature`
+    (:188-189) multiplies by in train mode) or None for dropout off.  mil_norm in (None, 'bn', 'ln') with embed_norm_pos 0 / 1
+    (:167-178, 207-223): 'ln' at position 0 is feature.0 (the Linear moves to feature.1); pos [N+1, 2] = sincos coordinates (:214-215).
 
     feature (:213) -> attention Linear/Tanh/Linear (:229) -> softmax over N (:231-232) ->
-    weighted sum (:234) -> classifier (:238).
+    weighted sum (:234) -> norm1 (:237) -> classifier (:238).
     """
     if x.dim() == 2:
         x = x.unsqueeze(0)
     h = x[0]
-    if "feature.0.weight" in sd:
-        h = apply_act(affine(h, sd["feature.0.weight"], sd.get("feature.0.bias")), act)
+    lin = "feature.0"
+    if mil_norm == "bn" and embed_norm_pos == 0:
+        h = _batchnorm_rows(h, sd, "norm", training)
+    if mil_norm == "ln" and embed_norm_pos == 0:
+        h = layer_norm(h, sd["feature.0.weight"], sd.get("feature.0.bias"))
+        lin = "feature.1"
+    if lin + ".weight" in sd:
+        h = apply_act(affine(h, sd[lin + ".weight"], sd.get(lin + ".bias")), act)
         if drop_mask is not None:
             h = h * drop_mask.to(h.dtype)
+    if pos is not None:
+        h = h + sincos_embed(pos[0] if pos.dim() == 3 else pos, h.shape[1]).to(h.dtype)
+    if embed_norm_pos == 1 and mil_norm == "bn":
+        h = _batchnorm_rows(h, sd, "norm", training)
+    elif embed_norm_pos == 1 and mil_norm == "ln":
+        h = layer_norm(h, sd["norm.weight"], sd.get("norm.bias"))
     u = torch.tanh(affine(h, sd["attention.0.weight"], sd.get("attention.0.bias")))
     s = affine(u, sd["attention.2.weight"], sd.get("attention.2.bias"))[:, 0]
     p, a = softmax_pool(s, h)
-    logits = affine(p[None], sd["classifier.weight"], sd.get("classifier.bias"))
+    z = p[None]
+    if mil_norm == "ln":
+        z = layer_norm(z, sd["norm1.weight"], sd.get("norm1.bias"))
+    elif mil_norm == "bn":
+        z = _batchnorm_rows(z, sd, "norm1", False)           # batch of one bag: only meaningful in eval mode (train mode raises upstream)
+    logits = affine(z, sd["classifier.weight"], sd.get("classifier.bias"))
     out = [logits, p[None]] if return_img_feat else logits
     if return_attn:
         res = [out, a[None]]

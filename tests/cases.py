@@ -53,6 +53,36 @@ def abmil_state(seed, D=1024, H=512, Da=128, C=2):
     return sd
 
 
+def abmil_norm_state(seed, mil_norm, embed_norm_pos, D=1024, H=512, Da=128, C=2):
+    """abmil.DAttention with mil_norm 'bn' / 'ln' (abmil.py:167-178): the reference's keys for each variant."""
+    g, sd = _g(seed), {}
+    lin = "feature.0"
+    if mil_norm == "ln" and embed_norm_pos == 0:
+        _ln(sd, g, "feature.0", D)
+        lin = "feature.1"
+    _lin(sd, g, lin, H, D)
+    _lin(sd, g, "attention.0", Da, H)
+    _lin(sd, g, "attention.2", 1, Da)
+    _lin(sd, g, "classifier", C, H)
+    if mil_norm == "ln":
+        if embed_norm_pos == 1:
+            _ln(sd, g, "norm", H)
+        _ln(sd, g, "norm1", H)
+    elif mil_norm == "bn":
+        for key, n in (("norm", D if embed_norm_pos == 0 else H), ("norm1", H)):
+            _ln(sd, g, key, n)
+            sd[key + ".running_mean"] = 0.1 * torch.randn(n, generator=g)
+            sd[key + ".running_var"] = 1.0 + 0.2 * torch.rand(n, generator=g)
+            sd[key + ".num_batches_tracked"] = torch.tensor(3)
+    return sd
+
+
+def sincos_pos(seed, N, W=97, H=61):
+    g = _g(seed)
+    xy = torch.stack([torch.randint(0, W, (N,), generator=g), torch.randint(0, H, (N,), generator=g)], 1)
+    return torch.cat([torch.tensor([[W, H]]), xy])[None]
+
+
 def gated_state(seed, D=1024, H=512, Da=384, C=2):
     g, sd = _g(seed), {}
     _lin(sd, g, "feature.0", H, D)

@@ -310,3 +310,47 @@ def test_ema_update_odd_sizes_and_alignment(M):
     ema_update(q, k, 0.99)
     for p, w in zip(k.parameters(), want):
         assert same_fma_result(p.detach().cpu(), w)
+
+
+@pytest.mark.parametrize("mil_norm,pos_", [("ln", 0), ("ln", 1), ("bn", 0), ("bn", 1)])
+def test_dattention_mil_norm_variants(M, mil_norm, pos_):
+    """The reference's legal non-default DAttention configurations (abmil.py:162-178, 207-223) load with strict=True under the
+    reference's keys (the input LayerNorm is feature.0, the Linear feature.1) and match the oracle, eval forward and ('ln') backward."""
+    N = 1333
+    x = cases.make_bag(N, N, 1024)
+    sd = cases.abmil_norm_state(N + pos_, mil_norm, pos_)
+    m = M.DAttention(1024, 2, dropout=0.0, act="gelu", mil_norm=mil_norm, embed_norm_pos=pos_).cuda().eval()
+    m.load_state_dict(cuda_sd(sd), strict=True)
+    with torch.no_grad():
+        got = m(x.cuda(), return_attn=True, return_act=True)
+        ref = O.abmil_dattention(sd, x, "gelu", return_attn=True, return_act=True, mil_norm=mil_norm, embed_norm_pos=pos_)
+    for a, b in zip(got, ref):
+        assert cases.rel_err(a, b) < TOL
+    if mil_norm == "ln":
+        m.train()
+        lg = m(x.cuda())
+        sd_ref = {k: v.clone().requires_grad_() for k, v in sd.items()}
+        rl = O.abmil_dattention(sd_ref, x, "gelu", mil_norm=mil_norm, embed_norm_pos=pos_)
+        F.cross_entropy(lg, torch.tensor([1]).cuda()).backward()
+        F.cross_entropy(rl, torch.tensor([1])).backward()
+        for k, p in m.named_parameters():
+            if k != "attention.2.bias":                                # mathematically zero
+                assert cases.rel_err(p.grad, sd_ref[k].grad) < TOL, k
+
+
+def test_dattention_sincos_and_amp(M):
+    N = 777
+    x, pos = cases.make_bag(N, N, 1024), cases.sincos_pos(5, N)
+    sd = cases.abmil_state(N)
+    m = M.DAttention(1024, 2, dropout=0.0, act="relu", pos="sincos").cuda().eval()
+    m.load_state_dict(cuda_sd(sd), strict=True)
+    with torch.no_grad():
+        assert cases.rel_err(m(x.cuda(), pos=pos.cuda()), O.abmil_dattention(sd, x, "relu", pos=pos)) < TOL
+    # --amp (engines/base_engine.py:78): autocast hands fp16 tensors to the kernels; they compute in fp32 instead of raising
+    plain = M.DAttention(1024, 2, dropout=0.0, act="relu").cuda().eval()
+    plain.load_state_dict(cuda_sd(sd), strict=True)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        a = plain(x.cuda().half())
+        b = plain(x.cuda())
+    ref = O.abmil_dattention(sd, x, "relu")
+    assert cases.rel_err(b, ref) < TOL and cases.rel_err(a, O.abmil_dattention(sd, x.half().float(), "relu")) < TOL

@@ -174,3 +174,23 @@ def test_full_gradient_tensors_against_the_live_reference(R, base, N):
         assert cases.rel_err(sd_ref[k].grad, p.grad) <= 2e-5, (k, cases.rel_err(sd_ref[k].grad, p.grad))
         n += 1
     assert n >= 10
+
+
+@pytest.mark.parametrize("mil_norm,pos_", [("ln", 0), ("ln", 1), ("bn", 0), ("bn", 1)])
+def test_dattention_mil_norm_and_sincos(R, mil_norm, pos_):
+    """abmil.DAttention's legal non-default configurations (abmil.py:162-178, 207-223): mil_norm bn / ln at both positions (eval mode: the
+    reference's BatchNorm of a single pooled vector raises in train mode) and pos='sincos'."""
+    N = 333
+    x = cases.make_bag(N, N, 1024)
+    sd = cases.abmil_norm_state(N + pos_, mil_norm, pos_)
+    m = R.abmil.DAttention(1024, 2, dropout=0.0, act="gelu", mil_norm=mil_norm, embed_norm_pos=pos_).eval()
+    m.load_state_dict(sd, strict=True)
+    ref = m(x.clone(), return_attn=True, return_act=True)
+    got = O.abmil_dattention(sd, x, "gelu", return_attn=True, return_act=True, mil_norm=mil_norm, embed_norm_pos=pos_)
+    for a, b in zip(got, ref):
+        assert cases.rel_err(a, b) <= 2e-6
+    if mil_norm == "ln" and pos_ == 0:
+        sd0, pos = cases.abmil_state(N + 9), cases.sincos_pos(5, N)
+        ms = R.abmil.DAttention(1024, 2, dropout=0.0, act="relu", pos="sincos").eval()
+        ms.load_state_dict(sd0, strict=True)
+        assert cases.rel_err(O.abmil_dattention(sd0, x, "relu", pos=pos), ms(x.clone(), pos=pos)) <= 2e-6

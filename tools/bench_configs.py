@@ -1,4 +1,5 @@
-"""Step times of the BASELINE.json configs on one B200 (ours) next to the CPU oracle port, for profiles/round1_summary.md.
+"""Step times of the BASELINE.json configs on one B200 (ours, eager and CUDA-graph replay) next to (a) the CPU oracle port and (b) -- informational,
+SURVEY 2.2's bar "beat aten / cuBLAS on the same box" -- the SAME oracle functions run eagerly on the GPU (torch ops = aten + cuBLAS + cuDNN).
 cfg0 ABMIL gated fwd/bwd N=1024; cfg1 MHIM(attn) N=10k (teacher, student fwd, bwd); cfg2 MHIM(selfattn) N=50k forward_test /
 teacher; cfg3 MHIM(dsmil) N=10k D=1536; cfg4 is tools/bench_sharded.py (multi-GPU)."""
 import json, os, sys, time
@@ -79,8 +80,30 @@ def mhim_cfg(base, N, D, tag, do_cpu=True, student=True):
             lt = 0.5 * lg[0].view(1, -1) + 0.5 * lg[1].view(1, -1) if base == "dsmil" else lg
             (F.cross_entropy(lt, LABEL) + 0.5 * loss).backward()
         res["train_step_ms"] = gpu_time(full)
+        from mhimk.engines import GraphedStep
+        gfull = GraphedStep(lambda bag: full())
+        res["train_step_graphed_ms"] = gpu_time(lambda: gfull(xb))
     stu.eval()
     res["forward_test_ms"] = gpu_time(lambda: stu.forward_test(xb))
+    # informational: the oracle's torch ops on the same GPU (eager PyTorch CUDA: aten / cuBLAS / cuDNN kernels)
+    cfg_ = O.MHIMConfig(**dict(cases.MHIM_KW, baseline=base, input_dim=D))
+    sds_g = {k: v.to(dev) for k, v in cases.mhim_state(1, base, D=D).items()}
+    sdt_g = {k: v.to(dev) for k, v in cases.mhim_state(2, base, D=D).items()}
+    with torch.no_grad():
+        res["eager_torch_cuda_forward_test_ms"] = gpu_time(lambda: O.mhim_forward_test(cfg_, sds_g, xb))
+        res["eager_torch_cuda_teacher_ms"] = gpu_time(lambda: O.mhim_forward_teacher(cfg_, sdt_g, xb))
+    if student:
+        sdl_g = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sds_g.items()}
+        def eager_step():
+            for v in sdl_g.values():
+                v.grad = None
+            with torch.no_grad():
+                rc_, rs_ = O.mhim_forward_teacher(cfg_, sdt_g, xb)
+            t_ = rc_[0] if base == "dsmil" else rc_
+            lg, loss, *_ = O.mhim_forward(cfg_, sdl_g, xb, rs_, t_, i=0, training=True)
+            lt = 0.5 * lg[0].view(1, -1) + 0.5 * lg[1].view(1, -1) if base == "dsmil" else lg
+            (F.cross_entropy(lt, LABEL) + 0.5 * loss).backward()
+        res["eager_torch_cuda_train_step_ms"] = gpu_time(eager_step, max(2, REPS // 2))
     if CPU and do_cpu:
         cfg = O.MHIMConfig(**dict(cases.MHIM_KW, baseline=base, input_dim=D))
         sds, sdt = cases.mhim_state(1, base, D=D), cases.mhim_state(2, base, D=D)
@@ -109,8 +132,16 @@ def transmil():
     # plain TransMIL eval forward at N=50k
     t = M.TransMIL(1024, 2, dropout=0.0, act="relu").to(dev).eval()
     xb = cases.make_bag(5, 50000, 1024).to(dev)
+    sd_g = {k: v.detach() for k, v in t.state_dict().items()}
     with torch.no_grad():
         out["transmil_eval_fwd_N50000_ms"] = gpu_time(lambda: t(xb), 5)
+        out["transmil_eager_torch_cuda_N50000_ms"] = gpu_time(lambda: O.transmil_forward(sd_g, xb, "relu"), 3)
+    # the headline module next to eager torch
+    a = M.DAttention(1024, 2, dropout=0.0, act="relu").to(dev).eval()
+    sda = {k: v.detach() for k, v in a.state_dict().items()}
+    with torch.no_grad():
+        out["abmil_N50000_fused_ms"] = gpu_time(lambda: a(xb), 20)
+        out["abmil_N50000_eager_torch_cuda_ms"] = gpu_time(lambda: O.abmil_dattention(sda, xb, "relu"), 10)
 
 
 guarded("transmil", transmil)
