@@ -10,7 +10,9 @@
  *   - all work is enqueued on `stream` (a cudaStream_t); no call synchronises the device;
  *   - return 0 on success, <0 for an argument error, >0 = cudaError_t; mil_last_error() describes the
  *     last failure on the calling thread;
- *   - batch is always one bag (as everywhere in the reference); fp32 in / fp32 out; indices int64.
+ *   - batch is always one bag (as everywhere in the reference); fp32 in / fp32 out; indices int64;
+ *   - calls that share a workspace (`ws`: weight images + the fused pass's finalisation counter) must be ordered on ONE stream; calls with
+ *     different workspaces are independent.
  */
 #ifndef MHIMK_H_
 #define MHIMK_H_
@@ -76,13 +78,14 @@ int         mil_device_supported(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused ABMIL forward pass: ONE streaming pass over the bag.
- *   h_n = act(W1 x_n + b1);  s_n = wc . (tanh(Wa h_n + ba) [* sigmoid(Wb h_n + bb)]) + bc   (att_act generalises tanh)
+ *   h_n = drop(act(W1 x_n + b1));  s_n = wc . att_act(Wa h_n + ba) + bc   (att_act: tanh, or relu / gelu for MHIM's da_act)
  *   per-CTA online softmax over its rows -> partial (m, l, P[H]) -> merged (m, l, pooled = P/l)
  * Replaces: modules/abmil.py:213-234 (DAttention.forward), :121-139 (AttentionGated.forward),
  *           modules/mhim.py:193 + modules/mhim_modules/baseline.py:31-41,97-110 (feature + DAttention),
  *           and with `keep` the gather of modules/mhim_modules/masking.py:91-110.
- * X [N,D] row-major, 16-byte aligned, D % 32 == 0, H == 512, Da == 128; Wb / bb (the gated branch) must be NULL here: the gated
- * heads run through mil_gated_attn_pool_f32 below.
+ * X [N,D] row-major, 16-byte aligned, D % 32 == 0, H == 512, Da == 128; Wb / bb (the gated branch) must be NULL: the gated heads
+ * (abmil.py:111-143, Da = 384) are NOT fused -- their two 128 x 384 GEMM2 accumulators do not fit the 512 TMEM columns next to h
+ *  -- and run as mil_linear_act_tc_f32 + mil_softmax_pool_fwd_f32 launches; passing Wb returns an argument error.
  * keep      nullable uint8[N]: rows with keep[n]==0 are skipped (masked instances).
  * s_out     nullable float[N]: raw attention logits (-inf for skipped rows).
  * t_out     nullable float[N,C]: t_{n,c} = h_n . Wp_c (needs Wp [C,H], C <= 4) -- input of mil_cam_score_f32.

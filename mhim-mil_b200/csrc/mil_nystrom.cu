@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) colmax_kernel(const float* __restrict__ S
   if (j < m) pmax[(int64_t)blockIdx.x * m + j] = mx;
 }
 // pass 2: per chunk, thread j: e = exp(S[r, j] - M[j]); pl[chunk][j] = sum e; pacc[chunk][j][d] = sum e * v[r, d]   (dh <= 64)
-__global__ void __launch_bounds__(256) colsoftmax_pool_kernel(const float* __restrict__ S, const float* __restrict__ V, int64_t ldv, int64_t n, int m, int dh,
+__global__ void __launch_bounds__(256, 2) colsoftmax_pool_kernel(const float* __restrict__ S, const float* __restrict__ V, int64_t ldv, int64_t n, int m, int dh,
                                                               int64_t rows_per_chunk, const float* __restrict__ pmax, int chunks,
                                                               float* __restrict__ colmax_out, float* __restrict__ pl, float* __restrict__ pacc) {
   __shared__ __align__(16) float sv[32][64];
@@ -98,22 +98,32 @@ __global__ void __launch_bounds__(256) colsoftmax_pool_kernel(const float* __res
   for (int64_t rb = r0; rb < r1; rb += 32) {
     const int nr = (int)((r1 - rb) < 32 ? (r1 - rb) : 32);
     __syncthreads();
-    for (int i = threadIdx.x; i < nr * 64; i += 256) {
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
       const int rr = i >> 6, d = i & 63;
-      sv[rr][d] = d < dh ? V[(rb + rr) * ldv + d] : 0.f;
+      sv[rr][d] = (rr < nr && d < dh) ? V[(rb + rr) * ldv + d] : 0.f;
     }
     __syncthreads();
-    if (j < m)
-      for (int rr = 0; rr < nr; ++rr) {
-        const float e = expf(S[(rb + rr) * m + j] - M);
-        l += e;
+    if (j < m) {
+      // the 32 similarity values of this thread's column first (32 independent coalesced loads in flight), then the FMA block: with
+      // the load inside the row loop the kernel sat at 25 % FMA-pipe utilisation waiting on one load per 64 FMAs (ncu, round 2)
+#pragma unroll 1
+      for (int hb = 0; hb < 32; hb += 16) {                     // two batches of 16 rows: 16 loads in flight, <= 128 registers (2 CTAs per SM)
+        float sv_j[16];
 #pragma unroll
-        for (int d = 0; d < 64; d += 4) {                       // broadcast LDS.128: one shared-memory instruction per four FMAs
-          const float4 v4 = *reinterpret_cast<const float4*>(&sv[rr][d]);
-          acc[d] = fmaf(e, v4.x, acc[d]); acc[d + 1] = fmaf(e, v4.y, acc[d + 1]);
-          acc[d + 2] = fmaf(e, v4.z, acc[d + 2]); acc[d + 3] = fmaf(e, v4.w, acc[d + 3]);
+        for (int rr = 0; rr < 16; ++rr) sv_j[rr] = (hb + rr) < nr ? S[(rb + hb + rr) * m + j] : -INFINITY;
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+          const float e = expf(sv_j[rr] - M);                   // rows past the chunk: exp(-inf) = 0
+          l += e;
+#pragma unroll
+          for (int d = 0; d < 64; d += 4) {                     // broadcast LDS.128: one shared-memory instruction per four FMAs
+            const float4 v4 = *reinterpret_cast<const float4*>(&sv[hb + rr][d]);
+            acc[d] = fmaf(e, v4.x, acc[d]); acc[d + 1] = fmaf(e, v4.y, acc[d + 1]);
+            acc[d + 2] = fmaf(e, v4.z, acc[d + 2]); acc[d + 3] = fmaf(e, v4.w, acc[d + 3]);
+          }
         }
       }
+    }
   }
   if (j < m) {
     pl[(int64_t)blockIdx.x * m + j] = l;

@@ -56,8 +56,9 @@ CASES = {"attn_10000": ("attn", 10000, 1024, 151, TOL, TOL), "dsmil_10000": ("ds
 #    N = 1 000; q.2, downstream of the gate, stays at 2.5e-5).  tools/diag_gate_flips.py shows the same passes at <= 2e-6 with every
 #    contraction on the exact-fp32 CUDA-core GEMM.  Any two fp32 implementations differ this way, only ~50x less often (SURVEY 9.9
 #    "seed-dependent gate flips": the fp32 reference vs fp64 reaches 1.5e-4).
-#  * merge.norm.weight: a sum over ~0.2 L rows of g (x) x_hat with heavy cancellation (|result| ~ 1e-6 from terms ~1e-4): 1.5e-4 .. 2.7e-4.
-GRAD_EXCEPTIONS = {"merge.norm.weight": 5e-4, "online_encoder.b_classifier.q.0.weight": 2e-2, "online_encoder.b_classifier.q.0.bias": 2e-2,
+# (merge.norm.weight used to sit at 1.5e-4 .. 2.7e-4 in every case: that was the ORACLE not reproducing the reference's in-forward `.data` write of
+#  global_q_mm, merge.py:127-129, which its LayerNorm backward then sees; fixed in the oracle and pinned against the live reference.)
+GRAD_EXCEPTIONS = {"online_encoder.b_classifier.q.0.weight": 2e-2, "online_encoder.b_classifier.q.0.bias": 2e-2,
                    "online_encoder.b_classifier.v.1.weight": 5e-4, "online_encoder.b_classifier.v.1.bias": 5e-4,
                    "online_encoder.attention.attention.0.weight": 2e-2, "feature.0.weight": 5e-3, "feature.0.bias": 5e-3}
 # the ReLU-gate exceptions apply only to the N = 10 000 cases; everywhere else those tensors are gated at 1e-4
@@ -120,7 +121,7 @@ def test_mhim_full_pass_and_full_gradients(M, name):
     errs = full_grad_errors(stu, sd_ref)
     assert len(errs) >= 6, errs
     print(name, "full-tensor gradient errors:", {k: f"{v:.1e}" for k, v in errs.items()})
-    exc = {k: v for k, v in GRAD_EXCEPTIONS.items() if k == "merge.norm.weight" or name in GATE_FLIP_CASES}
+    exc = GRAD_EXCEPTIONS if name in GATE_FLIP_CASES else {}
     bad = {k: v for k, v in errs.items() if not v < exc.get(k, gtol)}
     assert not bad, (bad, errs)
     stu.eval()

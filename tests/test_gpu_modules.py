@@ -354,3 +354,25 @@ def test_dattention_sincos_and_amp(M):
         b = plain(x.cuda())
     ref = O.abmil_dattention(sd, x, "relu")
     assert cases.rel_err(b, ref) < TOL and cases.rel_err(a, O.abmil_dattention(sd, x.half().float(), "relu")) < TOL
+
+
+def test_mhim_configs_outside_the_fused_kernel_take_the_composed_path(M):
+    """`--act none` (options.py:84), a free-form `--da_act` and n_classes > 4 are legal upstream; the fused kernel is instantiated for
+    act in {relu, gelu}, att_act in {tanh, relu, gelu}, C <= 4 only.  Such models must fall back to the composed path, not raise."""
+    n, d = 700, 1024
+    x = cases.make_bag(5, n, d)
+    for kw, tag in ((dict(act="none"), "act none"), (dict(n_classes=6), "6 classes"), (dict(da_act="sigmoid_like_unknown"), "unknown da_act")):
+        full = dict(cases.MHIM_KW, baseline="attn", input_dim=d, dropout=0.0)
+        full.update(kw)
+        m = M.MHIM(**full).cuda().eval()
+        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        cfg = O.MHIMConfig(**{k: v for k, v in full.items() if k in O.MHIMConfig.__dataclass_fields__})
+        if "da_act" in kw:
+            cfg.da_act = "none"                                     # upstream builds no activation for an unknown name (baseline.py:17-22)
+        with torch.no_grad():
+            got = m.forward_test(x.cuda())
+            cls, score = m.forward_teacher(x.cuda())
+            ref = O.mhim_forward_test(cfg, sd, x)
+            rc, rs = O.mhim_forward_teacher(cfg, sd, x)
+        assert cases.rel_err(got, ref) < TOL, tag
+        assert cases.rel_err(cls, rc) < TOL and cases.rel_err(score, rs) < TOL, tag

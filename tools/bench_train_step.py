@@ -39,6 +39,11 @@ def timed(fn, reps=30):
     return e0.elapsed_time(e1) / reps, (t1 - t0) / reps * 1e3
 
 
+if os.environ.get("T_NCU"):                       # under ncu: two eager steps (the launch list), nothing else
+    for _ in range(2):
+        step(bag)
+    torch.cuda.synchronize()
+    sys.exit(0)
 eager_ms, eager_host = timed(step)
 g = GraphedStep(step)
 graph_ms, graph_host = timed(g)
