@@ -42,11 +42,14 @@ def tensor_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock + throttle reasons through NVML while the timed region runs.  NVML is initialised BEFORE the timed region (the thread
+    signals `ready`): importing / initialising it inside the region held the GIL against the first launches of the loop -- a fixed 0.15 ms (one
+    rank) to 0.3 ms (eight ranks initialising NVML at once), i.e. 5-10 % of a 20-step run and the whole of round 1's "scaling loss"."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.ready, self.active = threading.Event(), False
 
     def run(self):
         try:
@@ -56,15 +59,19 @@ class ClockSampler(threading.Thread):
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                      nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)                  # first query pays the lazy set-up
+            self.ready.set()
             while not self.stop_flag:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                time.sleep(0.02)
+                if self.active:
+                    self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                time.sleep(0.005 if self.active else 0.001)
         except Exception as e:  # NVML missing: report it, do not fail the bench
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+            self.ready.set()
 
     def summary(self):
         sm = sorted(self.sm)
@@ -228,11 +235,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i)
-    sync_all()
     sampler = ClockSampler(local)
     sampler.start()
+    # The FIRST NCCL collective of a process finishes its connection set-up lazily: the kernel launched right after it starts ~0.25 ms
+    # late (tools/probe_step_gaps.py: first step 458 us after the first barrier, 210 us after any later one, 145-150 us otherwise).  One
+    # barrier ahead of the warm-up keeps that one-off out of the timed region (it was most of round 1's 6-7 % "scaling loss" at K = 20).
+    sync_all()
+    for i in range(args.warmup):
+        step(i)
+    sampler.ready.wait(20)                      # NVML is up before anything is timed
+    sync_all()
+    sampler.active = True
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
