@@ -172,8 +172,9 @@ def mhim_attention_pool(sd: SD, h: Tensor, da_act: str = "gelu", prefix: str = "
     """modules/mhim_modules/baseline.py:8-41,88-110.  Bias-free Linear 512->128, act, Linear 128->1,
     softmax over L, A @ h.  h is [L,512].  Returns (p[512], attn[L]) (raw logits if no_norm, :38-41).
     """
-    u = apply_act(affine(h, sd[prefix + "attention.attention.0.weight"]), da_act)
-    s = affine(u, sd[prefix + "attention.attention.2.weight"])[:, 0]
+    known = da_act in ("gelu", "relu", "tanh")                 # any other name builds NO activation module (baseline.py:17-22): the
+    u = apply_act(affine(h, sd[prefix + "attention.attention.0.weight"]), da_act if known else "none")     # second Linear is then index 1
+    s = affine(u, sd[prefix + ("attention.attention.2.weight" if known else "attention.attention.1.weight")])[:, 0]
     p, a = softmax_pool(s, h)
     return p, (s if no_norm else a)
 

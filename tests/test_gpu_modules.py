@@ -367,8 +367,6 @@ def test_mhim_configs_outside_the_fused_kernel_take_the_composed_path(M):
         m = M.MHIM(**full).cuda().eval()
         sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
         cfg = O.MHIMConfig(**{k: v for k, v in full.items() if k in O.MHIMConfig.__dataclass_fields__})
-        if "da_act" in kw:
-            cfg.da_act = "none"                                     # upstream builds no activation for an unknown name (baseline.py:17-22)
         with torch.no_grad():
             got = m.forward_test(x.cuda())
             cls, score = m.forward_teacher(x.cuda())
