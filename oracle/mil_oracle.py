@@ -684,6 +684,45 @@ def mhim_forward(cfg: MHIMConfig, sd: SD, x: Tensor, attn: Tensor, teacher_cls_f
 
 
 # ----------------------------------------------------------------------------------------------
+# f-3 : DTFD-MIL (modules/dtfd.py)
+# ----------------------------------------------------------------------------------------------
+def dtfd_gated_logits(sd: SD, x: Tensor, prefix: str) -> Tensor:
+    """dtfd.py:135-139 (Attention.forward before the softmax): w . (tanh(V x) * sigmoid(U x)) + b -> [N]"""
+    av = torch.tanh(affine(x, sd[prefix + "attention_V.0.weight"], sd[prefix + "attention_V.0.bias"]))
+    au = torch.sigmoid(affine(x, sd[prefix + "attention_U.0.weight"], sd[prefix + "attention_U.0.bias"]))
+    return affine(av * au, sd[prefix + "attention_weights.weight"], sd[prefix + "attention_weights.bias"])[:, 0]
+
+
+def dtfd_forward(sd: SD, x: Tensor, training: bool, group: int = 5, distill: str = "AFS", act: str = "relu",
+                 test_ids: Optional[Sequence[int]] = None) -> Tensor:
+    """dtfd.py:168-272 (DTFD.train_forward / test_forward) with every dropout off.  x [N, D] -> slide prediction [1, C].
+    training: contiguous pseudo-bags (np.array_split of range(N), :176-178); eval: pseudo-bags from the shuffled ids `test_ids`
+    (:232-235; pass the permutation python's `random.shuffle` produced).  distill in ('AFS', 'MaxS', 'MaxMinS')."""
+    import numpy as np
+    n = x.shape[0]
+    mid = apply_act(affine(x, sd["dimReduction.fc1.weight"]), act)                               # :81-83
+    ids = list(range(n)) if training else list(test_ids)
+    chunks = [torch.as_tensor(c, dtype=torch.long) for c in np.array_split(np.array(ids), group)]
+    s_all = dtfd_gated_logits(sd, mid, "attention.")
+    feats = []
+    for idx in chunks:
+        h = mid[idx]
+        a = torch.softmax(s_all[idx], 0)                                                         # :191 / :239-240
+        att = h * a[:, None]                                                                     # :193 tattFeats
+        pooled = att.sum(0, keepdim=True)
+        if distill == "AFS":
+            feats.append(pooled)
+            continue
+        cam = att @ sd["classifier.fc.weight"].t()                                               # get_cam_1d: no bias (:29-32)
+        order = torch.sort(torch.softmax(cam, 1)[:, -1], descending=True).indices                # :200-202
+        sel = order[:1] if distill == "MaxS" else torch.cat([order[:1], order[-1:]])
+        feats.append(h[sel])
+    pseudo = torch.cat(feats, 0)
+    a2 = torch.softmax(dtfd_gated_logits(sd, pseudo, "UClassifier.attention."), 0)
+    return affine((a2[None] @ pseudo), sd["UClassifier.classifier.fc.weight"], sd["UClassifier.classifier.fc.bias"])
+
+
+# ----------------------------------------------------------------------------------------------
 # Analytic ABMIL backward (SURVEY §9.2) -- what the streaming backward kernel implements.
 # ----------------------------------------------------------------------------------------------
 def abmil_backward_analytic(x: Tensor, W1: Tensor, b1: Tensor, Wa: Tensor, ba: Optional[Tensor], wc: Tensor,

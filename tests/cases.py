@@ -83,6 +83,19 @@ def sincos_pos(seed, N, W=97, H=61):
     return torch.cat([torch.tensor([[W, H]]), xy])[None]
 
 
+def dtfd_state(seed, D=1024, H=512, Da=128, C=2):
+    """modules/dtfd.py:149-153: the keys of DTFD(device, lr, wd, steps)."""
+    g, sd = _g(seed), {}
+    _lin(sd, g, "classifier.fc", C, H)
+    for p in ("attention.", "UClassifier.attention."):
+        _lin(sd, g, p + "attention_V.0", Da, H)
+        _lin(sd, g, p + "attention_U.0", Da, H)
+        _lin(sd, g, p + "attention_weights", 1, Da)
+    sd["dimReduction.fc1.weight"] = _mat(g, H, D)
+    _lin(sd, g, "UClassifier.classifier.fc", C, H)
+    return sd
+
+
 def gated_state(seed, D=1024, H=512, Da=384, C=2):
     g, sd = _g(seed), {}
     _lin(sd, g, "feature.0", H, D)

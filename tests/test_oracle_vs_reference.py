@@ -194,3 +194,24 @@ def test_dattention_mil_norm_and_sincos(R, mil_norm, pos_):
         ms = R.abmil.DAttention(1024, 2, dropout=0.0, act="relu", pos="sincos").eval()
         ms.load_state_dict(sd0, strict=True)
         assert cases.rel_err(O.abmil_dattention(sd0, x, "relu", pos=pos), ms(x.clone(), pos=pos)) <= 2e-6
+
+
+@pytest.mark.parametrize("distill", ["AFS", "MaxS", "MaxMinS"])
+@pytest.mark.parametrize("N", [7, 333, 2000])
+def test_dtfd_train_and_test_forward(R, distill, N):
+    """DTFD-MIL (modules/dtfd.py:148-272), both forwards, all three distillations, dropout neutralised; eval mode shuffles with python's RNG."""
+    import importlib
+    import random
+    D = importlib.import_module("modules.dtfd")
+    sd, x = cases.dtfd_state(N), cases.make_bag(N + 3, N, 1024)[0]
+    m = zero_dropout(D.DTFD(torch.device("cpu"), 1e-4, 1e-5, 10, distill=distill))
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    assert cases.rel_err(O.dtfd_forward(sd, x, True, distill=distill), m(x[None])) <= 2e-6
+    m.eval()
+    random.seed(5)
+    ref = m(x[None])
+    random.seed(5)
+    ids = list(range(N))
+    random.shuffle(ids)
+    assert cases.rel_err(O.dtfd_forward(sd, x, False, distill=distill, test_ids=ids), ref) <= 2e-6
