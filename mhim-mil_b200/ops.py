@@ -243,18 +243,14 @@ def linear_forward(x, W, b, act, pre=None, precision=None, volatile=False, dropo
         return y
     if dropout:
         raise RuntimeError("mhimk: fused dropout on a Linear wider than 512 columns is not provided")
-    ys, o = [], 0
-    pres = []
+    # wider than 512 columns: column blocks of ONE output buffer (the kernel takes a leading dimension), no concatenation afterwards
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    o = 0
     for i, wdt in enumerate(widths):
-        y_b = torch.empty((M, wdt), dtype=torch.float32, device=x.device)
-        p_b = torch.empty((M, wdt), dtype=torch.float32, device=x.device) if pre is not None else None
-        _tc_block(x, W[o:o + wdt], None if b is None else b[o:o + wdt], act, p_b, y_b, W, i, precision, volatile)
-        ys.append(y_b)
-        pres.append(p_b)
+        _tc_block(x, W[o:o + wdt], None if b is None else b[o:o + wdt], act, None if pre is None else pre[:, o:o + wdt], y[:, o:o + wdt], W, i, precision,
+                  volatile)
         o += wdt
-    if pre is not None:
-        pre.copy_(torch.cat(pres, dim=1))
-    return torch.cat(ys, dim=1)
+    return y
 
 
 class _LinearAct(torch.autograd.Function):

@@ -1,1 +1,2 @@
-python -m pytest tests/test_gpu_dtfd.py -m gpu -q -p no:cacheprovider 2>&1 | grep -E "passed|failed|^E   .*(assert|Error)|^tests/test_gpu_dtfd.py:[0-9]+" | cut -c1-260 | head -30
+# scratch probe used during round 2 (see profiles/round2_summary.md "Multi-GPU"): the GPU suite tail
+python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | grep -E "passed|failed|^FAILED|^E   .*(assert|Error)" | cut -c1-300 | tail -15
