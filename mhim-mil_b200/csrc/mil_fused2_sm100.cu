@@ -140,7 +140,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       // tiles are first pulled into L2 PF sub-steps ahead (cp.async.bulk.prefetch.tensor); the staged load then sees L2 latency.
       uint32_t s = 0, ph = 1, xit = 0;
       const uint32_t sx0 = smem_u32(sX);
-      constexpr int PF = 24;
+      const int PF = ((p.dbg >> 16) & 0xFF) ? ((p.dbg >> 16) & 0xFF) : 24;       // MHIMK_DEBUG bits 16..23 override the L2 prefetch distance (tuning probe)
       int64_t ptile = pair_id;
       int pks = 0;
       auto prefetch_next = [&]() {                                               // one box further down this CTA's stream

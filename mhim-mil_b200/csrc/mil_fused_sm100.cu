@@ -596,8 +596,10 @@ int make_map_2d_ld(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const
   cuuint64_t gstr[1] = {ld * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  static const int promo_env = getenv("MHIMK_L2PROMO") ? atoi(getenv("MHIMK_L2PROMO")) : 128;     // tuning probe: 0 / 64 / 128 / 256
+  const CUtensorMapL2promotion promo = promo_env == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo_env == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                       : promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  CUresult r = enc(m, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)", (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols); return -3; }
   return 0;
 }

@@ -345,6 +345,9 @@ def linear_act(x: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor] = Non
     """drop(act(x @ W.T + b)) for x [M,K]; differentiable (CUDA backward).  volatile=True: do not trust a cached weight image
     (see weights_touched).  dropout: a DropSpec (next_dropout(p)) applied inside the GEMM's epilogue; the backward regenerates
     the same mask."""
+    if not (torch.is_grad_enabled() and (x.requires_grad or W.requires_grad or (b is not None and b.requires_grad))):
+        # no autograd wanted: skip the autograd.Function machinery (≈ 10 us of host time per call; the eval paths are launch-bound)
+        return linear_forward(_need(x, "x"), _need(W, "weight"), _need(b, "bias") if b is not None else None, act, None, volatile=volatile, dropout=dropout)
     return _LinearAct.apply(x, W, b, act, volatile, dropout)
 
 
@@ -399,6 +402,11 @@ class _SoftmaxPool(torch.autograd.Function):
 
 def softmax_pool(s: torch.Tensor, h: torch.Tensor, keep: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """(pooled[H], attn[L]) = (softmax(s) @ h, softmax(s)); s [L] may be a strided column view.  attn is not differentiable."""
+    if not (torch.is_grad_enabled() and (s.requires_grad or h.requires_grad)):
+        if not s.is_cuda or s.dtype != torch.float32 or s.dim() != 1:
+            raise RuntimeError("mhimk: `s` must be a 1-D float32 CUDA tensor")
+        pooled, _, attn = _pool_fwd(s, _need(h, "h"), keep, True)
+        return pooled, attn
     return _SoftmaxPool.apply(s, h, keep)
 
 

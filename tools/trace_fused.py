@@ -19,7 +19,7 @@ for prec in os.environ.get("PROF_PREC", "bf16x3,fp16").split(","):
         ops.abmil_fused_forward(x, sd["feature.0.weight"], sd["feature.0.bias"], os.environ.get("PROF_ACT", "relu"), sd["attention.0.weight"],
                                 sd["attention.0.bias"], sd["attention.2.weight"], sd["attention.2.bias"], "tanh", precision=prec)
     torch.cuda.synchronize()
-    ws, _ = ops._fused_workspace(sd["feature.0.weight"], sd["attention.0.weight"], prec, ops._pipeline(None, prec))
+    ws = ops._fused_workspace(sd["feature.0.weight"], sd["attention.0.weight"], prec, ops._pipeline(None, prec))[0]
     L = mhimk._lib.lib()
     total = L.mil_fused_workspace_bytes(1024, 512, 128, 0)
     base = ws.data_ptr()
@@ -43,6 +43,7 @@ for prec in os.environ.get("PROF_PREC", "bf16x3,fp16").split(","):
     print("   end-time percentiles us: " + ", ".join(f"p{q}={float(ends[int(q / 100 * (len(ends) - 1))]):.1f}" for q in (0, 10, 50, 90, 100)))
     print(f"== {prec}: per-tile phase stamps of CTA 0, cycles relative to g1_start of tile 0")
     t0 = int(t[0, 0])
+    print(f"   CTA 0: kernel entry -> g1_start of tile 0: {t0 - int(fl[238])} cycles; e4_done of the last tile -> kernel exit: {int(fl[239]) - max(int(t[i, 9]) for i in range(16))} cycles")
     for tl in range(4):
         if int(t[tl, 0]) == 0:
             break
