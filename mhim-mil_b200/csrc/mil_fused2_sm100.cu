@@ -317,6 +317,13 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           const uint32_t st = it / KSUB, sub = it % KSUB, s = st % NST, ph = (st / NST) & 1;
           mbar_wait(BAR(B_XFULL + xs), xph, p.err, 10);
           if (tid == 0) kstamp(p, 5, it);
+          if (p.dbg & 8) {                                      // timing attribution: hand-shakes only, no conversion work
+            mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 11);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { ARRIVE_LEADER(B_FULL + s); mbar_arrive(BAR(B_XEMPTY + xs)); }
+            continue;
+          }
           float x[16];
           const uint32_t src = smem_u32(sX + xs * X_SLOT) + (uint32_t)row * 128u;
 #pragma unroll
