@@ -66,6 +66,15 @@ class GraphedStep:
         self._graphs[key] = (graph, static_in, static_out)
         return self._graphs[key]
 
+    def buffers(self, *args):
+        """The static input buffers of the graph for these shapes (captured on first use): fill them in place (e.g. the H2D copy of the
+        next bag) and call the step with them to skip the per-replay input copy."""
+        key = self._key(args)
+        hit = self._graphs.get(key)
+        if hit is None:
+            hit = self._capture(key, args)
+        return hit[1]
+
     @property
     def n_graphs(self) -> int:
         return len(self._graphs)

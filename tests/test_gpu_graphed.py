@@ -90,3 +90,23 @@ def test_graphed_step_draws_fresh_dropout_masks(M):
     assert abs(float(a.mean()) - float(b.mean())) < 1e-3
     tea.eval()
     assert torch.equal(tea.forward_teacher(x)[1], tea.forward_teacher(x)[1])
+
+
+@pytest.mark.parametrize("base,D", [("dsmil", 1536), ("attn", 1024)])
+def test_graphed_inference_in_place_buffers(M, base, D):
+    """Inference replayed from a graph: `buffers()` hands out the static input so a loader can fill it in place; the replay equals the
+    eager call bit for bit (same kernels, same order) and follows new bag contents."""
+    from mhimk.engines import GraphedStep
+    tea = build(M, base, D, 7, 0.0).eval()
+    x1, x2 = cases.make_bag(4, 1500, D).cuda(), cases.make_bag(5, 1500, D).cuda()
+    with torch.no_grad():
+        g = GraphedStep(lambda bag: tea.forward_test(bag))
+        buf = g.buffers(x1)[0]
+        assert buf.data_ptr() != x1.data_ptr() and g.n_graphs == 1
+        for x in (x1, x2):
+            buf.copy_(x)
+            out = g(buf)
+            ref = tea.forward_test(x)
+            out, ref = (out[0], ref[0]) if isinstance(out, (tuple, list)) else (out, ref)
+            assert torch.equal(out, ref)
+    assert g.n_graphs == 1

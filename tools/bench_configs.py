@@ -83,8 +83,17 @@ def mhim_cfg(base, N, D, tag, do_cpu=True, student=True):
         from mhimk.engines import GraphedStep
         gfull = GraphedStep(lambda bag: full())
         res["train_step_graphed_ms"] = gpu_time(lambda: gfull(xb))
+    from mhimk.engines import GraphedStep
+    with torch.no_grad():                                   # inference replayed from a CUDA graph (input filled in place: no copy per replay)
+        gt = GraphedStep(lambda bag: tea.forward_teacher(bag))
+        buf = gt.buffers(xb)[0]
+        res["teacher_graphed_ms"] = gpu_time(lambda: gt(buf))
     stu.eval()
     res["forward_test_ms"] = gpu_time(lambda: stu.forward_test(xb))
+    with torch.no_grad():
+        gf = GraphedStep(lambda bag: stu.forward_test(bag))
+        buf2 = gf.buffers(xb)[0]
+        res["forward_test_graphed_ms"] = gpu_time(lambda: gf(buf2))
     # informational: the oracle's torch ops on the same GPU (eager PyTorch CUDA: aten / cuBLAS / cuDNN kernels)
     cfg_ = O.MHIMConfig(**dict(cases.MHIM_KW, baseline=base, input_dim=D))
     sds_g = {k: v.to(dev) for k, v in cases.mhim_state(1, base, D=D).items()}
@@ -135,6 +144,10 @@ def transmil():
     sd_g = {k: v.detach() for k, v in t.state_dict().items()}
     with torch.no_grad():
         out["transmil_eval_fwd_N50000_ms"] = gpu_time(lambda: t(xb), 5)
+        from mhimk.engines import GraphedStep
+        gtm = GraphedStep(lambda bag: t(bag))
+        bufm = gtm.buffers(xb)[0]
+        out["transmil_eval_fwd_graphed_N50000_ms"] = gpu_time(lambda: gtm(bufm), 5)
         out["transmil_eager_torch_cuda_N50000_ms"] = gpu_time(lambda: O.transmil_forward(sd_g, xb, "relu"), 3)
     # the headline module next to eager torch
     a = M.DAttention(1024, 2, dropout=0.0, act="relu").to(dev).eval()

@@ -22,7 +22,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 T_REPS=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/launches_train_step_attn.csv env T_NCU=1 python tools/bench_train_step.py > $O/train_under_ncu.log 2>&1
 # ... and one full capture each of the fused forward, the tensor-core weight gradient and the streaming softmax-over-N pool
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:mil_fused2 -s 2 -c 1 -o $O/fused2_full -f env PROF_MODES=fused PROF_PREC=bf16x3 PROF_REPS=1 python tools/prof_fused.py > $O/ncu_fused2.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:wgrad_kernel -s 1 -c 1 -o $O/wgrad_full -f env T_NCU=1 python tools/bench_train_step.py > $O/ncu_wgrad.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^wgrad_kernel" -s 1 -c 1 -o $O/wgrad_full -f env T_NCU=1 python tools/bench_train_step.py > $O/ncu_wgrad.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:colsoftmax_pool_kernel -s 2 -c 1 -o $O/colpool_full -f env T_N=50000 python tools/prof_transmil.py > $O/ncu_colpool.log 2>&1
 for r in fused2_full wgrad_full colpool_full; do
   [ -f $O/$r.ncu-rep ] && ncu -i $O/$r.ncu-rep --page raw --csv > $O/$r.raw.csv 2>/dev/null
