@@ -11,7 +11,7 @@ pids=()
 SRCS="mil_api mil_simt mil_topk mil_fused_sm100 mil_fused2_sm100 mil_wgrad_sm100 mil_skinny mil_rows mil_nystrom"
 for f in $SRCS; do
   if [ ! -f "$HERE/build/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/build/$f.o" ] || [ "$HERE/mil_common.cuh" -nt "$HERE/build/$f.o" ] || [ "$HERE/mil_umma.cuh" -nt "$HERE/build/$f.o" ] || [ "$ROOT/include/mhimk.h" -nt "$HERE/build/$f.o" ]; then
-    "$NVCC" "${FLAGS[@]}" ${PTXAS_V:+-Xptxas -v} ${KSTAMP:+-DMIL_KSTAMP} -c "$HERE/$f.cu" -o "$HERE/build/$f.o" &
+    "$NVCC" "${FLAGS[@]}" ${PTXAS_V:+-Xptxas -v} ${KSTAMP:+-DMIL_KSTAMP} ${PROBE:+-DMIL_PROBE} -c "$HERE/$f.cu" -o "$HERE/build/$f.o" &
     pids+=($!)
   fi
 done

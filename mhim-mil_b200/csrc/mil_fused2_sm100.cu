@@ -140,7 +140,11 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       // tiles are first pulled into L2 PF sub-steps ahead (cp.async.bulk.prefetch.tensor); the staged load then sees L2 latency.
       uint32_t s = 0, ph = 1, xit = 0;
       const uint32_t sx0 = smem_u32(sX);
-      const int PF = ((p.dbg >> 16) & 0xFF) ? ((p.dbg >> 16) & 0xFF) : 24;       // MHIMK_DEBUG bits 16..23 override the L2 prefetch distance (tuning probe)
+#ifdef MIL_PROBE
+      const int PF = ((p.dbg >> 16) & 0xFF) ? ((p.dbg >> 16) & 0xFF) : 24;       // MHIMK_DEBUG bits 16..23 override the L2 prefetch distance (PROBE=1 builds only)
+#else
+      constexpr int PF = 24;                                                     // 8 ... 96 measured: no sensitivity (profiles/round2_summary.md)
+#endif
       int64_t ptile = pair_id;
       int pks = 0;
       auto prefetch_next = [&]() {                                               // one box further down this CTA's stream
@@ -317,13 +321,15 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           const uint32_t st = it / KSUB, sub = it % KSUB, s = st % NST, ph = (st / NST) & 1;
           mbar_wait(BAR(B_XFULL + xs), xph, p.err, 10);
           if (tid == 0) kstamp(p, 5, it);
-          if (p.dbg & 8) {                                      // timing attribution: hand-shakes only, no conversion work
+#ifdef MIL_PROBE
+          if (p.dbg & 8) {                                      // timing attribution (PROBE=1 builds only): hand-shakes only, no conversion work
             mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 11);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) { ARRIVE_LEADER(B_FULL + s); mbar_arrive(BAR(B_XEMPTY + xs)); }
             continue;
           }
+#endif
           float x[16];
           const uint32_t src = smem_u32(sX + xs * X_SLOT) + (uint32_t)row * 128u;
 #pragma unroll

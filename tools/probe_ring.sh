@@ -1,4 +1,5 @@
-# What sets the ~1000-cycle operand-ring stage of the pair kernel (768 GEMM1 MMA cycles)?  Run on a B200; output = profiles/round2_ring_attribution.txt.
+# What sets the ~1000-cycle operand-ring stage of the pair kernel (768 GEMM1 MMA cycles)?  Needs a probe build (touch csrc/mil_fused2_sm100.cu; PROBE=1 csrc/build.sh):
+# the no-conversion and prefetch-distance switches are compiled out of the shipped kernel.  Run on a B200; output = profiles/round2_ring_attribution.txt.
 # Part 1: fewer CTAs (MHIMK_GRID) -> same GEMM1 window  => not chip-wide L2 / HBM contention.
 for g in 148 74 38 2; do
   n=$(( g / 2 * 4 * 128 ))

@@ -1,6 +1,6 @@
 """Where one MHIM training step (teacher + student forward + backward) spends its time: GPU-busy time per kernel
 (torch.profiler / CUPTI), host issue time (wall clock without waiting for the GPU) and the event-timed step.
-T_BASE=attn|dsmil|selfattn, T_N, T_D."""
+T_BASE=attn|dsmil|selfattn, T_N, T_D; T_MODE=step|teacher|test profiles the whole step / the teacher pass / `forward_test` alone."""
 import os, sys, time
 import torch, torch.nn.functional as F
 from torch.profiler import profile, ProfilerActivity
@@ -24,6 +24,15 @@ def full():
     lt = 0.5 * lg[0].view(1, -1) + 0.5 * lg[1].view(1, -1) if base == "dsmil" else lg
     (F.cross_entropy(lt, LABEL) + 0.5 * loss).backward()
 
+
+mode = os.environ.get("T_MODE", "step")
+if mode != "step":
+    step_fn = full
+    stu.eval()
+
+    def full():                                            # noqa: F811 - the profiled callable
+        with torch.no_grad():
+            return tea.forward_teacher(xb) if mode == "teacher" else stu.forward_test(xb)
 
 for _ in range(5):
     full()

@@ -1,2 +1,2 @@
-# scratch probe used during round 2 (see profiles/round2_summary.md "Multi-GPU"): the GPU suite tail
-python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | grep -E "passed|failed|^FAILED|^E   .*(assert|Error)" | cut -c1-300 | tail -15
+for i in 1 2; do python bench.py --steps 50 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; b=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(b['ms_per_step'], b['roofline']['kernel_ms'], b['roofline']['frac'])"; done
+python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
