@@ -100,7 +100,11 @@ int         mil_device_supported(void);
  * logits    nullable float[n_cls] = Wcls pooled + bcls (classifier fused into the same tail; replaces abmil.py:238 /
  *           mhim.py:267); Wcls [n_cls, H], bcls nullable.
  * ws / ws_bytes: scratch of at least mil_fused_workspace_bytes(D, H, Da, gated) bytes; it holds the 16-bit hi/lo images of
- *           W1 and Wa.  ws_ready = 0: the images are (re)built by this call; ws_ready = 1: the caller guarantees `ws` was
+ *           W1 and Wa, the finalisation counter and (pair pipeline) the exchange area of the tail split: when the last wave of
+ *           128-row tiles fills at most half of the CTA pairs, each of its tiles is shared by K range between two pairs, one of
+ *           which hands its partial accumulator (128 x 512 fp32) to the other through this area (~19 MB on a 148-SM part;
+ *           MHIMK_NOSPLIT=1 switches the split off).  Deterministic: one partial, added in a fixed place.
+ *           ws_ready = 0: the images are (re)built by this call; ws_ready = 1: the caller guarantees `ws` was
  *           filled by an earlier call with the same weights, precision AND pipeline (skips two small kernels per bag).
  * precision MIL_PREC_* | (MIL_PIPE_* << 8).
  */

@@ -53,6 +53,41 @@ __device__ __forceinline__ void kstamp(const FusedParams& p, int series, uint32_
 #endif
 }
 
+// Work items of one pair.  Whole waves of tiles go round-robin over the pairs (tile = pair + i * n_pairs); the tiles of a partly filled wave
+// are split by K range over otherwise idle pairs (FusedParams::split_*): the pairs S g .. S g + S - 1 share tile split_full * n_pairs + g, pair
+// S g ("owner") runs the tile's epilogue after adding the helper's dumped accumulator (S = 2: one partial, deterministic).
+// The helper does its part FIRST and the owner its part LAST: the exchange (dump 128 KB per CTA through L2 at ~32 B/clk, barrier, release flag:
+// 6.5-10 k cycles, measured) is then long over when the owner's last epilogue asks for the partial.  (Both last: the dump sits on the kernel's
+// tail.  Both first: the owner's wait delays the release of its TMEM buffer and stalls GEMM1 two items later; both measured, both gain nothing.)
+// A helper's item has no GEMM2: the GEMM2-side barriers count GEMM2 tiles (item index - 1 on a helper pair), the accumulator barriers count items.
+struct WorkItem {
+  int64_t tile;
+  int kb, ke;       // pipeline stages [kb, ke) of the tile's K loop
+  int kind;         // 0 whole tile, 1 owner of a split tile, 2 helper
+  int pidx;         // helper: index of its partial; owner: index of its first helper's partial (S - 1 consecutive)
+};
+__device__ __forceinline__ int work_count(const FusedParams& p, int64_t pair_id, int64_t n_pairs, int64_t n_tiles) {
+  if (p.split_s <= 1) return pair_id < n_tiles ? (int)((n_tiles - pair_id + n_pairs - 1) / n_pairs) : 0;
+  return p.split_full + (pair_id < (int64_t)p.split_rem * p.split_s ? 1 : 0);
+}
+__device__ __forceinline__ WorkItem work_item(const FusedParams& p, int i, int64_t pair_id, int64_t n_pairs, int KST) {
+  WorkItem w;
+  const bool has_split = p.split_s > 1 && pair_id < (int64_t)p.split_rem * p.split_s;
+  const int part = has_split ? (int)pair_id % p.split_s : 0;
+  const int split_pos = part ? 0 : p.split_full;           // helper: its first item; owner: its last
+  if (!has_split || i != split_pos) {
+    w.tile = pair_id + (int64_t)(i - (part ? 1 : 0)) * n_pairs; w.kb = 0; w.ke = KST; w.kind = 0; w.pidx = 0;
+    return w;
+  }
+  const int grp = (int)pair_id / p.split_s;
+  w.tile = (int64_t)p.split_full * n_pairs + grp;
+  w.kb = KST * part / p.split_s;
+  w.ke = KST * (part + 1) / p.split_s;
+  w.kind = part ? 2 : 1;
+  w.pidx = grp * (p.split_s - 1) + (part ? part - 1 : 0);
+  return w;
+}
+
 template <int NPROD, bool FP16, int NST, int XS, int KSUB, int ACT, int ATT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW1,
@@ -103,13 +138,14 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     p.trace[256 + 2 * blockIdx.x] = (long long)gt;
-    if (blockIdx.x == 0) p.trace[238] = clock64();
+    if (blockIdx.x == (unsigned)p.trace_cta) p.trace[238] = clock64();
   }
   const int KS = p.D / BK;                                     // GEMM1 32-wide k sub-steps per tile
   const int KST = KS / KSUB;                                   // pipeline stages per tile
   constexpr int NCH2 = HMAX / BK;                              // GEMM2 k-steps per tile (16)
   const int64_t n_tiles = (p.N + BMP - 1) / BMP;
   const int64_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_it = work_count(p, pair_id, n_pairs, n_tiles);    // work items of this pair (whole tiles, then at most one split item)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < XS; ++i) { mbar_init(BAR(B_XFULL + i), 1); mbar_init(BAR(B_XEMPTY + i), LO ? 4 : 2); }
@@ -145,20 +181,22 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #else
       constexpr int PF = 24;                                                     // 8 ... 96 measured: no sensitivity (profiles/round2_summary.md)
 #endif
-      int64_t ptile = pair_id;
-      int pks = 0;
+      int pi = 0;
+      WorkItem pw = work_item(p, 0, pair_id, n_pairs, KST);
+      int pks = pw.kb * KSUB;
       auto prefetch_next = [&]() {                                               // one box further down this CTA's stream
-        if (ptile < n_tiles) {
-          if (elect_one()) tma_prefetch_2d(&mapX, pks * BK, (int)(ptile * BMP + rank * BMC));
+        if (pi < n_it) {
+          if (elect_one()) tma_prefetch_2d(&mapX, pks * BK, (int)(pw.tile * BMP + rank * BMC));
           __syncwarp();
-          if (++pks == KS) { pks = 0; ptile += n_pairs; }
+          if (++pks == pw.ke * KSUB && ++pi < n_it) { pw = work_item(p, pi, pair_id, n_pairs, KST); pks = pw.kb * KSUB; }
         }
       };
       if (!(p.dbg & 2))
         for (int i = 0; i < PF; ++i) prefetch_next();
-      for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) {
-        const int row0 = (int)(tile * BMP + rank * BMC);
-        for (int ks = 0; ks < KS; ++ks) {
+      for (int wi = 0; wi < n_it; ++wi) {
+        const WorkItem w = work_item(p, wi, pair_id, n_pairs, KST);
+        const int row0 = (int)(w.tile * BMP + rank * BMC);
+        for (int ks = w.kb * KSUB; ks < w.ke * KSUB; ++ks) {
           if (!(p.dbg & 2)) prefetch_next();
           mbar_wait(BAR(B_XEMPTY + s), ph, p.err, 1);
           if (lane == 0) kstamp(p, 6, xit++);
@@ -178,8 +216,9 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       // Image rows are 256 B; one stage of one CTA is KSUB x NOP x 16 KB contiguous: per sub-step [hi: N block 0 | N block 1][lo: ...].
       uint32_t s = 0, ph = 1, wit = 0;
       const uint32_t full0 = LEADER(B_FULL), sb0 = smem_u32(sB);
-      for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) {
-        for (int kst = 0; kst < KST; ++kst) {
+      for (int wi = 0; wi < n_it; ++wi) {
+        const WorkItem w = work_item(p, wi, pair_id, n_pairs, KST);
+        for (int kst = w.kb; kst < w.ke; ++kst) {
           mbar_wait(BAR(B_EMPTY + s), ph, p.err, 2);
           if (lane == 0) kstamp(p, 0, wit++);
           if (elect_one()) {
@@ -199,13 +238,14 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       const uint32_t sa0 = smem_u32(sA), sb0 = smem_u32(sB);
       uint32_t s = 0, ph = 0, tl = 0, iit = 0, sq = 0, phq = 0, gi = 0;
       const uint32_t qd = ((uint32_t)p.dbg >> 12) & 15u;
-      for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs, ++tl) {
+      for (int wi = 0; wi < n_it; ++wi, ++tl) {
+        const WorkItem w = work_item(p, wi, pair_id, n_pairs, KST);
         const uint32_t b1 = tl & 1;
         mbar_wait(BAR(B_ACCEMPTY + b1), ((tl >> 1) & 1) ^ 1, p.err, 4);
         tc_fence_after();
         if (lane == 0) trace_stamp(p, tl, 0);
         const uint32_t d0 = tmem + b1 * 256;
-        for (int kst = 0; kst < KST; ++kst) {
+        for (int kst = w.kb; kst < w.ke; ++kst) {
           if (lane == 0) kstamp(p, 2, iit);
           // optional queue-depth limit (MHIMK_DEBUG bits 12..15 = qd): at most qd stages queued in the tensor pipe, so that GEMM2's
           // short MMAs of the previous tile (other warp) do not wait behind a full ring of GEMM1 work
@@ -229,7 +269,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 for (int blk = 0; blk < 2; ++blk) {
                   // descriptor start addresses are in 16-byte units: +2 per K = 16 step (32 B), +512 per N block (8 KB)
                   const uint64_t oa = (uint64_t)(sub * (A_SUB / 16) + k16 * 2), ob = (uint64_t)(sub * (B_SUB / 16) + blk * 512 + k16 * 2);
-                  const uint32_t acc = (kst | sub | k16) ? 1u : 0u;
+                  const uint32_t acc = ((kst - w.kb) | sub | k16) ? 1u : 0u;
                   umma_f16_pair(d0 + blk * 128, ah0 + oa, bh0 + ob, idesc1, acc);
                   if (LO) {
                     umma_f16_pair(d0 + blk * 128, al0 + oa, bh0 + ob, idesc1, 1u);
@@ -239,7 +279,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
               }
             }
             umma_commit_pair(BAR(B_EMPTY + s));
-            if (kst == KST - 1) umma_commit_pair(BAR(B_ACCFULL + b1));
+            if (kst == w.ke - 1) umma_commit_pair(BAR(B_ACCFULL + b1));
           }
           __syncwarp();
           if (++s == (uint32_t)NST) { s = 0; ph ^= 1; }
@@ -252,8 +292,8 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       // (16 KB per CTA: this CTA's 64 rows of each chunk), double-buffered; group G+1 is requested when group G starts.
       const uint32_t idesc2 = make_idesc(FP16, 128, BMP);
       const uint32_t bfull0 = LEADER(B_G2BFULL), sa20 = smem_u32(sA2), sb20 = smem_u32(sB2);
-      uint32_t T = 0;
-      for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) ++T;
+      const uint32_t skip = (n_it && work_item(p, 0, pair_id, n_pairs, KST).kind == 2) ? 1u : 0u;   // a helper's split item (its first) has no GEMM2
+      const uint32_t T = (uint32_t)n_it - skip;
       const uint32_t total = T * NG;
       auto load_group = [&](uint32_t G) {                      // G-th group of this CTA's sequence (groups repeat every NG)
         const uint32_t bf = G & 1;
@@ -264,14 +304,15 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
         __syncwarp();
       };
-      load_group(0);
+      if (total) load_group(0);
       uint32_t G = 0;
-      for (uint32_t tl = 0; tl < T; ++tl) {
-        const uint32_t b2 = tl & 1;
+      for (uint32_t tl = 0; tl < T; ++tl) {                  // tl: GEMM2 tile index; its accumulator buffer follows the ITEM index tl + skip
+        const uint32_t b2 = (tl + skip) & 1;
         if (rank == 0) {
+          // (tl >> 1) = earlier GEMM2 tiles on the same buffer, with or without a skipped first item
           mbar_wait(BAR(B_TAILFREE + b2), (tl >> 1) & 1, p.err, 7);             // u's columns are vacated (implies GEMM1 of the tile is complete)
           tc_fence_after();
-          if (lane == 0) trace_stamp(p, tl, 2);
+          if (lane == 0) trace_stamp(p, tl + skip, 2);
         }
         const uint32_t d = tmem + b2 * 256;
         for (int g = 0; g < NG; ++g, ++G) {
@@ -303,7 +344,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             __syncwarp();
           }
         }
-        if (rank == 0 && lane == 0) trace_stamp(p, tl, 3);
+        if (rank == 0 && lane == 0) trace_stamp(p, tl + skip, 3);
       }
     }
   } else if (warp >= CONV_WARP0) {
@@ -315,8 +356,9 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       const int tid = threadIdx.x - CONV_WARP0 * 32, row = tid >> 1, hf = tid & 1;
       const uint32_t row_off = (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 64u, sw = (uint32_t)(row >> 1) & 3u;
       uint32_t it = 0;
-      for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) {
-        for (int ks = 0; ks < KS; ++ks, ++it) {
+      for (int wi = 0; wi < n_it; ++wi) {
+        const WorkItem w = work_item(p, wi, pair_id, n_pairs, KST);
+        for (int ks = w.kb * KSUB; ks < w.ke * KSUB; ++ks, ++it) {
           const uint32_t xs = it % XS, xph = (it / XS) & 1;
           const uint32_t st = it / KSUB, sub = it % KSUB, s = st % NST, ph = (st / NST) & 1;
           mbar_wait(BAR(B_XFULL + xs), xph, p.err, 10);
@@ -364,8 +406,9 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     const int grp = (warp - CONV_WARP0) >> 1;
     const int row = ((warp - CONV_WARP0) & 1) * 32 + lane;
     uint32_t it = 0;
-    for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs) {
-      for (int ks = 0; ks < KS; ++ks, ++it) {
+    for (int wi = 0; wi < n_it; ++wi) {
+      const WorkItem w = work_item(p, wi, pair_id, n_pairs, KST);
+      for (int ks = w.kb * KSUB; ks < w.ke * KSUB; ++ks, ++it) {
         if ((int)(it & 1) != grp) continue;
         // Parity waits are only sound if the waiter sees every phase of its barrier: the rings are even (XS) or shared by both groups
         // within every stage (KSUB == 2), so a staging slot / stage always belongs to the same group.
@@ -404,6 +447,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
     const int et = threadIdx.x - EPI_WARP0 * 32;             // 0..255
     uint32_t tl = 0;
+    const uint32_t gskip = (n_it && work_item(p, 0, pair_id, n_pairs, KST).kind == 2) ? 1u : 0u;   // GEMM2 tiles = items - gskip (see WorkItem)
 
     for (int i = et; i < HMAX; i += 256) c_b1[i] = p.b1 ? p.b1[i] : 0.f;
     for (int i = et; i < 128; i += 256) { c_ba[i] = p.ba ? p.ba[i] : 0.f; c_wc[i] = p.wc[i]; }
@@ -414,13 +458,72 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     const float bc = p.bc ? p.bc[0] : 0.f;
     const uint32_t a2_hi = smem_u32(sA2 + strip * G2A_STAGE);
 
-    for (int64_t tile = pair_id; tile < n_tiles; tile += n_pairs, ++tl) {
+    for (int wi = 0; wi < n_it; ++wi, ++tl) {
+      const WorkItem wk = work_item(p, wi, pair_id, n_pairs, KST);
+      const int64_t tile = wk.tile;
       const uint32_t b = tl & 1;
       const int64_t grow = tile * BMP + rank * BMC + row;
       const uint32_t tb = tq + b * 256 + (uint32_t)(half * 128);        // this warp's strip in the tile's accumulator buffer
+      if (wi == n_it - 2) {
+        // the owner's split item comes next (last): pull this warp's 16 KB of the helper's partial (dumped long ago, possibly evicted by the bag
+        // stream) back into L2 while this tile's epilogue runs.  A hint only: the flag is still checked before the loads.
+        const WorkItem nx = work_item(p, wi + 1, pair_id, n_pairs, KST);
+        if (nx.kind == 1) {
+          const char* base = reinterpret_cast<const char*>(p.split_buf) + ((size_t)(nx.pidx * 2 + rank) * 8 + (warp - EPI_WARP0)) * (4 * 8 * 32 * 16);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)(lane + 32 * k) * 128));
+        }
+      }
       mbar_wait(BAR(B_ACCFULL + b), (tl >> 1) & 1, p.err, 13);
       tc_fence_after();
       if (et == 0) trace_stamp(p, tl, 4);
+      if (wk.kind == 2) {
+        // helper of a split tile: dump the raw partial accumulator (its K range) for the owner pair and raise this CTA's flag
+        // layout [partial][CTA rank][warp][chunk j][4-column group][lane] float4: every store / load instruction of a warp covers 512 contiguous bytes
+        float4* dst = reinterpret_cast<float4*>(p.split_buf) + ((size_t)(wk.pidx * 2 + rank) * 8 + (warp - EPI_WARP0)) * (4 * 8 * 32) + lane;
+#pragma unroll 1
+        for (int j = 0; j < 4; j += 2) {                      // two chunks in flight: the second TMEM load overlaps the first chunk's stores
+          uint32_t va[32], vb[32];
+          tmem_ld32(tb + (uint32_t)(j * 32), va);
+          tmem_ld32(tb + (uint32_t)((j + 1) * 32), vb);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            __stcg(dst + (j * 8 + i) * 32, make_float4(__uint_as_float(va[4 * i]), __uint_as_float(va[4 * i + 1]), __uint_as_float(va[4 * i + 2]), __uint_as_float(va[4 * i + 3])));
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            __stcg(dst + ((j + 1) * 8 + i) * 32, make_float4(__uint_as_float(vb[4 * i]), __uint_as_float(vb[4 * i + 1]), __uint_as_float(vb[4 * i + 2]), __uint_as_float(vb[4 * i + 3])));
+        }
+        if (et == 0) trace_stamp(p, tl, 5);
+        tc_fence_before();
+        named_bar_sync(1, 256);                               // every epilogue thread's stores are ordered before thread 0's release below (cumulativity)
+        if (et == 0) trace_stamp(p, tl, 7);
+        if (et == 0) flag_raise(p.split_flags + wk.pidx * 2 + rank);   // st.release.gpu = fence + store, the grid-sync pattern
+        if (et == 0) trace_stamp(p, tl, 8);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(LEADER(B_ACCEMPTY + b));
+        if (et == 0) trace_stamp(p, tl, 9);
+        continue;
+      }
+      // owner: accumulator chunk j of this warp's strip += the helper's partial sum.  The partial of chunk j + 1 is fetched (L2 loads: another
+      // SM wrote it) while chunk j is processed, so one L2 latency is exposed per tile instead of one per chunk.
+      float4 pf[8];
+      const float4* pf_src = reinterpret_cast<const float4*>(p.split_buf) + ((size_t)(wk.pidx * 2 + rank) * 8 + (warp - EPI_WARP0)) * (4 * 8 * 32) + lane;
+      auto pf_load = [&](int j) {
+        if (wk.kind != 1) return;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pf[i] = __ldcg(pf_src + (j * 8 + i) * 32);
+      };
+      auto pf_add = [&](float (&hv)[32]) {
+        if (wk.kind != 1) return;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { hv[4 * i] += pf[i].x; hv[4 * i + 1] += pf[i].y; hv[4 * i + 2] += pf[i].z; hv[4 * i + 3] += pf[i].w; }
+      };
+      if (wk.kind == 1) {                                     // the helper's partial of this CTA's 64 rows must have landed
+        if (lane == 0) flag_wait(p.split_flags + wk.pidx * 2 + rank, p.err, 30);
+        __syncwarp();
+        pf_load(0);
+      }
       if (p.dbg & 512) {                                    // timing attribution: handshakes only, no epilogue work
         if (half == 0) { __syncwarp(); if (lane == 0) mbar_arrive_cluster(LEADER(B_TAILFREE + b)); }
         for (int j = 0; j < 4; ++j) {
@@ -428,7 +531,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(LEADER(B_G2AFULL + strip));
         }
-        mbar_wait(BAR(B_UFULL), tl & 1, p.err, 15);
+        mbar_wait(BAR(B_UFULL), (tl - gskip) & 1, p.err, 15);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(LEADER(B_ACCEMPTY + b));
@@ -441,6 +544,8 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           tmem_ld32f(tb + (uint32_t)(j * 32), keep_h[j]);
+          pf_add(keep_h[j]);
+          pf_load(j + 1);
           bias_act32<ACT>(keep_h[j], c_b1 + f0 + j * 32, p.act, p.w1_inv);
           if (p.drop_mode) drop_apply32(keep_h[j], drop_keep_word(p, grow, (f0 >> 5) + j, HMAX / 32), p.drop_scale);
         }
@@ -487,6 +592,8 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       for (int j = (half == 0 ? 2 : 0); j < 4; ++j) {
         float hv[32];
         tmem_ld32f(tb + (uint32_t)(j * 32), hv);
+        pf_add(hv);
+        if (j < 3) pf_load(j + 1);
         bias_act32<ACT>(hv, c_b1 + f0 + j * 32, p.act, p.w1_inv);
         if (p.drop_mode) drop_apply32(hv, drop_keep_word(p, grow, (f0 >> 5) + j, HMAX / 32), p.drop_scale);
         tmem_st32f(tb + (uint32_t)(j * 32), hv);
@@ -497,7 +604,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 
       // E3: attention logit of every row: s = wc . f(u + ba) + bc.  u (N = 128) sits in the buffer's first 64 columns:
       // lanes 0..63 hold Da 0..63, lanes 64..127 hold Da 64..127; this warp takes 32 of its 64 columns.
-      mbar_wait(BAR(B_UFULL), tl & 1, p.err, 15);
+      mbar_wait(BAR(B_UFULL), (tl - gskip) & 1, p.err, 15);
       tc_fence_after();
       if (et == 0) trace_stamp(p, tl, 7);
       {
@@ -527,6 +634,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             p.t_out[grow * p.C + cc] = (t_part[row * 4 + cc] + t_part[(64 + row) * 4 + cc]) + (t_part[(128 + row) * 4 + cc] + t_part[(192 + row) * 4 + cc]);
       }
       named_bar_sync(1, 256);                               // s_part / t_part may be overwritten by the next tile after this
+      if (wk.kind == 1 && et == 0) p.split_flags[wk.pidx * 2 + rank] = 0;   // every warp is past E2: the partial was consumed; re-arm for the next launch
       if (et == 0) trace_stamp(p, tl, 8);
 
       // online softmax over the 32 rows of this warp (the four warps that share these rows compute identical m, l)
@@ -599,7 +707,7 @@ mil_fused2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     p.trace[256 + 2 * blockIdx.x + 1] = (long long)gt;
-    if (blockIdx.x == 0) p.trace[239] = clock64();
+    if (blockIdx.x == (unsigned)p.trace_cta) p.trace[239] = clock64();
   }
   if (warp == W_W1) { tc_fence_after(); tmem_dealloc_pair(tmem, 512); }
 }
@@ -736,10 +844,27 @@ int pair_fused_launch(const float* X, FusedParams p, int precision, cudaStream_t
   if ((rc = make_map_2d(&mw1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, p.w1_img, w1_rows, 256, (uint32_t)(pair_ksub(precision, p.D) * NOP * B_OP / 256), 256, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   if ((rc = make_map_2d(&mwa, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, p.wa_img, wa_rows, 256, (uint32_t)(G2B_BUF / 256), 256, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   const int64_t n_tiles = (p.N + BMP - 1) / BMP;
-  int pairs = num_sms() / 2;
-  if (n_tiles < pairs) pairs = (int)n_tiles;
+  int pmax = num_sms() / 2;
   const char* e = getenv("MHIMK_GRID");
-  if (e && atoi(e) >= 2 && atoi(e) / 2 < pairs) pairs = atoi(e) / 2;
+  if (e && atoi(e) >= 2 && atoi(e) / 2 < pmax) pmax = atoi(e) / 2;
+  int pairs = n_tiles < pmax ? (int)n_tiles : pmax;
+  // Tail split: the tiles of a last wave that fills at most half of the pairs are shared by K range between two pairs each (the owner adds one
+  // partial accumulator of 128 KB per CTA; >= 4 pipeline stages per part).  More parts do not pay: the split item's epilogue cannot start
+  // before the previous tile's (~25 k cycles) has finished, and half a GEMM1 (~16 k) already fits under it; every extra partial costs the owner
+  // an L2 round trip per chunk.  391 tiles on 74 pairs: 5 waves + 21 tiles x 2 halves instead of a 6th tile period for 21 pairs.
+  p.split_s = 1; p.split_full = 0; p.split_rem = 0;
+  static const bool nosplit = getenv("MHIMK_NOSPLIT") && atoi(getenv("MHIMK_NOSPLIT"));
+  if (!nosplit && p.split_buf && p.split_flags) {
+    const int kst = p.D / BK / pair_ksub(precision, p.D);
+    const int rem = (int)(n_tiles % pmax);                  // == n_tiles when the bag has fewer tiles than pairs
+    int S = rem ? pmax / rem : 1;
+    if (S > 2) S = 2;
+    while (S > 1 && kst / S < 4) --S;
+    if (S >= 2) {
+      p.split_s = S; p.split_full = (int)(n_tiles / pmax); p.split_rem = rem;
+      pairs = p.split_full ? pmax : rem * S;
+    }
+  }
   const int grid = 2 * pairs;
 #define MIL_CASE(A, T) if (p.act == A && p.att_act == T) return dispatch_prec<A, T>(precision, mx, mw1, mwa, p, grid, stream);
   MIL_CASE(MIL_ACT_RELU, MIL_ACT_TANH) MIL_CASE(MIL_ACT_GELU, MIL_ACT_TANH)

@@ -754,9 +754,15 @@ extern "C" int mil_dropout_bits(int64_t rows, int ncols, const mil_dropout_t* dr
   return 0;
 }
 
+// workspace: [weight images][err, counter][trace stamps][tail-split flags (1 KB) | partial accumulators of the pair pipeline's tail split:
+// fewer than num_sms / 2 partials of 128 x 512 fp32 (mil_fused2_sm100.cu)]
+static size_t fused_ws_base_bytes(int D, int H, int Da) {
+  return ((size_t)H * D + (size_t)Da * H) * 2 /*hi+lo*/ * sizeof(uint16_t) + 1024 + sizeof(int) * 4 + 64 + (16 * 16 + 2 * 1024) * sizeof(long long);
+}
+static size_t fused_ws_split_bytes() { return 256 + 1024 + (size_t)(num_sms() / 2) * 128 * HMAX * sizeof(float); }
 extern "C" size_t mil_fused_workspace_bytes(int D, int H, int Da, int gated) {
   (void)gated;
-  return ((size_t)H * D + (size_t)Da * H) * 2 /*hi+lo*/ * sizeof(uint16_t) + 1024 + sizeof(int) * 4 + 64 + (16 * 16 + 2 * 1024) * sizeof(long long);
+  return fused_ws_base_bytes(D, H, Da) + fused_ws_split_bytes();
 }
 
 extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, const float* W1, const float* b1, int act, const float* Wa,
@@ -802,6 +808,9 @@ extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, 
     }
     MIL_CUDA(cudaMemsetAsync(err, 0, 4 * sizeof(int), stream));
   }
+  long long* trace_base = (long long*)(((uintptr_t)(err + 4) + 63) & ~(uintptr_t)63);
+  int* split_flags = (int*)(((uintptr_t)(trace_base + 16 * 16 + 2 * 1024) + 255) & ~(uintptr_t)255);
+  if (!ws_ready) MIL_CUDA(cudaMemsetAsync(split_flags, 0, 1024, stream));
   CUtensorMap mx;
   if (pipeline == 1 && (rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)N, (uint64_t)D, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
 
@@ -810,7 +819,9 @@ extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, 
   p.b1 = b1; p.ba = ba; p.wc = wc; p.bc = bc; p.keep = keep; p.Wp = Wp; p.C = t_out ? C : 0;
   p.s_out = s_out; p.t_out = t_out; p.h_out = h_out; p.part = part; p.c_out = nullptr; p.ldc = 0; p.err = err; p.dbg = debug_mask(); p.w1_img = w1_img; p.wa_img = wa_img;
   p.stats = stats; p.pooled = pooled; p.rec_out = rec_out; p.counter = (unsigned int*)(err + 1); p.Wcls = Wcls; p.bcls = bcls; p.n_cls = n_cls; p.logits = logits;
-  p.trace = getenv("MHIMK_TRACE") ? (long long*)(((uintptr_t)(err + 4) + 63) & ~(uintptr_t)63) : nullptr;
+  p.trace = getenv("MHIMK_TRACE") ? trace_base : nullptr;
+  p.trace_cta = getenv("MHIMK_TRACE_CTA") ? atoi(getenv("MHIMK_TRACE_CTA")) : 0;
+  p.split_flags = split_flags; p.split_buf = (float*)((uint8_t*)split_flags + 1024);
   p.w1_inv = p.wa_inv = 1.f / prec_wscale(precision);
   if ((rc = set_dropout(p, drop, H))) return rc;
   if (pipeline == 2) return pair_fused_launch(X, p, precision, stream);

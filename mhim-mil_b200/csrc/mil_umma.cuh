@@ -30,10 +30,16 @@ struct FusedParams {
   float* rec_out;       // nullable [2 + H]: (m, l, P = sum e^{s-m} h) = the exchange record of an instance-sharded bag
   const float* Wcls; const float* bcls; int n_cls; float* logits;
   int* err;
-  long long* trace;     // optional [16 tiles][16 slots] clock64 stamps of CTA 0 (MHIMK_TRACE=1), see tools/trace_fused.py
+  long long* trace;     // optional [16 tiles][16 slots] clock64 stamps of CTA trace_cta (MHIMK_TRACE=1, MHIMK_TRACE_CTA=<block>), see tools/trace_fused.py
+  int trace_cta = 0;
   // dropout on h (mhim.py:193-194, abmil.py:188-189): 0 = none, 1 = caller-supplied keep bits, 2 = in-kernel Philox4x32-10
   int drop_mode; const uint32_t* drop_bits; uint32_t drop_thresh; float drop_scale; uint32_t drop_seed[2]; uint32_t drop_off[2];
   float w1_inv, wa_inv; // 1 / (power-of-two scale of the W1 / Wa image): MIL_W_SCALE_FP16X3 in the fp16x3 arithmetic, else 1
+  // tail split of the pair pipeline (mil_fused2_sm100.cu): the last, partly filled wave of tiles is split over idle pairs by K range.
+  // split_s = parts per tile (1 = off), split_full = whole-tile waves, split_rem = tiles of the split wave; helpers dump their
+  // accumulators to split_buf ([partial][CTA rank][epilogue warp][...] in the warps' own register order, 128 KB per CTA) and raise
+  // split_flags [partial][2 CTA ranks]; the owner adds them before the bias.
+  int split_s = 1, split_full = 0, split_rem = 0; float* split_buf = nullptr; int* split_flags = nullptr;
   int dbg;              // MHIMK_DEBUG bitmask (timing attribution only): 1 skip W1 TMA, 2 skip X TMA, 4 skip GEMM1 MMA, 8 skip convert, 16 skip Wa TMA, 32 skip pooling, 64 skip GEMM2 MMA
 };
 
@@ -76,6 +82,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
   }
 }
+// acquire-spin on a global flag raised by another CTA of the same launch (st.release.gpu); same time-out policy as mbar_wait
+__device__ __forceinline__ void flag_wait(const int* f, int* err, int code) {
+  const long long t0 = clock64();
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (v) return;
+    const uint64_t dt = (uint64_t)(clock64() - t0);
+    if (g_mil_notrap && dt > 100000000ull) {
+      if (err) atomicCAS(err, 0, code | ((int)blockIdx.x << 8) | ((int)(threadIdx.x >> 5) << 20));
+      return;
+    }
+    if (dt > WAIT_TIMEOUT_CYCLES) {
+      if (err) atomicExch(err, code);
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ void flag_raise(int* f) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(1) : "memory"); }
 static void mil_set_notrap() {
   static bool done_dev[64] = {false};           // the symbol lives per device
   int dev = 0;
@@ -222,7 +248,7 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 __device__ __forceinline__ void trace_stamp(const FusedParams& p, uint32_t tl, int slot) {
-  if (p.trace && blockIdx.x == 0 && tl < 16) p.trace[tl * 16 + slot] = clock64();
+  if (p.trace && blockIdx.x == (unsigned)p.trace_cta && tl < 16) p.trace[tl * 16 + slot] = clock64();
 }
 
 // K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows are 64 B, 8-row groups are 512 B apart.

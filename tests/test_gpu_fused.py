@@ -130,3 +130,38 @@ def test_fused_matches_golden_logits(K):
     assert cases.rel_err(out["pooled"], G["pooled"][0]) < 1e-4
     logits = out["pooled"].cpu() @ sd["classifier.weight"].t() + sd["classifier.bias"]
     assert cases.rel_err(logits, G["logits"][0]) < 1e-4
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16"])
+def test_pair_tail_split_shapes_and_rearm(K, prec):
+    """Tail split of the pair pipeline (the tiles of a last wave that fills at most half of the pairs are shared by K range between two pairs
+    each; the owner adds the helper's dumped accumulator): split and unsplit shapes, with and without whole waves before the split one, on ONE
+    workspace (same weights) in an interleaved order so the flags raised by one launch must have been re-armed for the next, each launch
+    twice and bit-identical."""
+    sd = cases.abmil_state(41)
+    c = {k: v.cuda() for k, v in sd.items()}
+    Wp = (torch.randn(2, 512, generator=torch.Generator().manual_seed(2)) * 0.05).cuda()
+    # tiles: 1 | 19 | 37 (all split) | 38 (more than half of the 74 pairs: no split) | 74 + 1 | 74 + 30 | 2 x 74 + 21 (split after whole waves)
+    sizes = [100, 19 * 128, 37 * 128 - 5, 38 * 128, 75 * 128 - 60, 104 * 128, 169 * 128 + 1, 100, 75 * 128 - 60]
+    seen = {}
+    for N in sizes:
+        x = cases.make_bag(500 + N, N, 1024)
+        h_ref, s_ref, p_ref = run_oracle(sd, x, "gelu")
+        xg = x[0].cuda()
+        outs = []
+        for _ in range(2):
+            o = K.abmil_fused_forward(xg, c["feature.0.weight"], c["feature.0.bias"], "gelu", c["attention.0.weight"], c["attention.0.bias"],
+                                      c["attention.2.weight"], c["attention.2.bias"], "tanh", Wp=Wp, want_scores=True, want_h=True, precision=prec,
+                                      pipeline="pair", Wcls=c["classifier.weight"], bcls=c["classifier.bias"])
+            outs.append({k: o[k].clone() for k in ("pooled", "s", "h", "t", "logits")})
+        torch.cuda.synchronize()
+        for k in outs[0]:
+            assert torch.equal(outs[0][k], outs[1][k]), (N, k)
+        o = outs[0]
+        assert cases.rel_err(o["h"], h_ref) < TOL[prec], N
+        assert cases.rel_err(o["s"], s_ref) < TOL[prec] * 3, N
+        assert cases.rel_err(o["t"], h_ref @ Wp.cpu().double().t()) < TOL[prec] * 3, N
+        assert cases.rel_err(o["pooled"], p_ref) < TOL[prec], N
+        if N in seen:                                                          # the same bag later in the sequence: same bits
+            assert torch.equal(seen[N], o["pooled"])
+        seen[N] = o["pooled"]

@@ -44,7 +44,7 @@ for prec in os.environ.get("PROF_PREC", "bf16x3,fp16").split(","):
     print(f"== {prec}: per-tile phase stamps of CTA 0, cycles relative to g1_start of tile 0")
     t0 = int(t[0, 0])
     print(f"   CTA 0: kernel entry -> g1_start of tile 0: {t0 - int(fl[238])} cycles; e4_done of the last tile -> kernel exit: {int(fl[239]) - max(int(t[i, 9]) for i in range(16))} cycles")
-    for tl in range(4):
+    for tl in range(int(os.environ.get("PROF_TILES", 4))):
         if int(t[tl, 0]) == 0:
             break
         row = {n: int(t[tl, i]) - t0 for i, n in enumerate(names)}
