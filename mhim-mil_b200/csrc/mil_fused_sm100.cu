@@ -98,6 +98,9 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
   const int KS = p.D / BK;                                 // GEMM1 k-steps per tile
   const int NCH2 = (MODE == MODE_FUSED) ? HMAX / BK : 0;   // GEMM2 k-steps per tile (16)
   const int64_t n_tiles = (p.N + BM - 1) / BM;
+  // store mode, column-split launch: virtual tile v = (row tile v / nblk, 256-column block v % nblk); p.nout = columns per virtual tile
+  const int nblk = (MODE == MODE_STORE) ? p.nblk : 1;
+  const int64_t n_vt = n_tiles * nblk;
 
   if (threadIdx.x == 0) {
     // FULL[s]: the converter warps of the k-step + the weight producer's expect_tx arrival (+ its bytes)
@@ -134,13 +137,13 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
       int64_t ptile = blockIdx.x;
       int pks = 0;
       auto prefetch_next = [&]() {
-        if (ptile < n_tiles && !(p.dbg & 2)) {
-          tma_prefetch_2d(&mapX, pks * BK, (int)(ptile * BM));
+        if (ptile < n_vt && !(p.dbg & 2)) {
+          tma_prefetch_2d(&mapX, pks * BK, (int)((ptile / nblk) * BM));
           if (++pks == KS) { pks = 0; ptile += gridDim.x; }
         }
       };
       for (int i = 0; i < PF; ++i) prefetch_next();
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int64_t tile = blockIdx.x; tile < n_vt; tile += gridDim.x) {
         for (int ks = 0; ks < KS; ++ks, ++it) {
           prefetch_next();
           const uint32_t s = it % XS, m = it / XS;
@@ -153,7 +156,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
           const uint32_t full = BAR(B_XFULL + (XG == 1 ? 0 : (it & 1) * XS) + s);
           if (p.dbg & 2) { mbar_arrive(full); continue; }
           mbar_expect_tx(full, X_SLOT_BYTES);
-          tma_load_2d(smem_u32(sX + s * X_SLOT_BYTES), &mapX, full, ks * BK, (int)(tile * BM));
+          tma_load_2d(smem_u32(sX + s * X_SLOT_BYTES), &mapX, full, ks * BK, (int)((tile / nblk) * BM));
         }
       }
     }
@@ -163,19 +166,24 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
     // (UMMA K-major SWIZZLE_64B), so each stage is ONE contiguous bulk copy per operand instead of 256-512 64-byte TMA rows.
     if (lane == 0) {
       uint32_t it = 0, tl = 0;
-      const uint32_t w1_tile = (uint32_t)p.nout * BK * 2, wa_tile = (uint32_t)p.Da * BK * 2;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      // W1 image: 256-row blocks (split_weights_kernel); this CTA consumes nimg of them per stage, starting at block blk0 of its virtual tile
+      const uint32_t w1_tile = (uint32_t)(p.nout < 256 ? p.nout : 256) * BK * 2, wa_tile = (uint32_t)p.Da * BK * 2;
+      const int nimg = (p.nout + 255) / 256;
+      for (int64_t tile = blockIdx.x; tile < n_vt; tile += gridDim.x, ++tl) {
+        const int blk0 = (int)(tile % nblk);
         // the GEMM1 stage slots host GEMM2's ring between ACC_FULL and U_FULL of the previous tile
         if (MODE == MODE_FUSED && tl > 0) mbar_wait(BAR(B_UFULL), (tl - 1) & 1, p.err, 17);
         for (int ks = 0; ks < KS; ++ks, ++it) {
           const uint32_t s = it % NST, ph = (it / NST) & 1;
           mbar_wait(BAR(B_EMPTY + s), ph ^ 1, p.err, 2);
           if (p.dbg & 1) { mbar_arrive(BAR(B_FULL + s)); continue; }
-          mbar_expect_tx(BAR(B_FULL + s), NOP * w1_tile);
+          mbar_expect_tx(BAR(B_FULL + s), NOP * nimg * w1_tile);
           const uint32_t dst = smem_u32(sB + s * B_STAGE);
-          const uint8_t* src = p.w1_img + (size_t)ks * NOP * w1_tile;
-          bulk_load(dst, src, w1_tile, BAR(B_FULL + s));
-          if (LO) bulk_load(dst + B_OP_BYTES, src + w1_tile, w1_tile, BAR(B_FULL + s));
+          for (int hf = 0; hf < nimg; ++hf) {
+            const uint8_t* src = p.w1_img + ((size_t)(blk0 + hf) * KS + ks) * NOP * w1_tile;
+            bulk_load(dst + hf * w1_tile, src, w1_tile, BAR(B_FULL + s));
+            if (LO) bulk_load(dst + B_OP_BYTES + hf * w1_tile, src + w1_tile, w1_tile, BAR(B_FULL + s));
+          }
         }
         if (NCH2 > 0) mbar_wait(BAR(B_ACCFULL), tl & 1, p.err, 18);
         for (int c = 0; c < NCH2; ++c) {
@@ -199,7 +207,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
       const int n1 = p.nout < 256 ? p.nout : 256, nhalf = (p.nout + 255) / 256;
       const uint32_t idesc1 = make_idesc(FP16, n1), idesc2 = make_idesc(FP16, p.Da);
       const uint32_t sa0 = smem_u32(sA), sb0 = smem_u32(sB);
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      for (int64_t tile = blockIdx.x; tile < n_vt; tile += gridDim.x, ++tl) {
         mbar_wait(BAR(B_ACCEMPTY), (tl & 1) ^ 1, p.err, 4);
         tc_fence_after();
         if (lane == 0) trace_stamp(p, tl, 0);                // GEMM1 may start
@@ -269,7 +277,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
     const int grp = LO ? 0 : (warp - 4) >> 1;                 // 1-product modes: group 0 = warps 4, 5 (even k-steps), group 1 = warps 6, 7 (odd)
     const int row0 = LO ? (warp - 4) * 32 + lane : ((warp - 4) & 1) * 32 + lane;   // rows row0 and (RPT == 2) row0 + 64
     uint32_t itx = 0, ita = 0, tl = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+    for (int64_t tile = blockIdx.x; tile < n_vt; tile += gridDim.x, ++tl) {
       // The stage slots host GEMM2's operand ring until U_FULL of the previous tile: do not overwrite them earlier.
       if (MODE == MODE_FUSED && tl > 0) mbar_wait(BAR(B_UFULL), (tl - 1) & 1, p.err, 16);
       for (int ks = 0; ks < KS; ++ks, ++itx, ++ita) {
@@ -315,7 +323,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
     uint32_t tl = 0;
 
     // per-column constants -> shared memory (broadcast reads in the hot loops)
-    for (int i = et; i < HMAX; i += 256) c_b1[i] = (p.b1 && i < p.nout) ? p.b1[i] : 0.f;   // the bias has nout entries (store mode: nout <= 512)
+    for (int i = et; i < HMAX; i += 256) c_b1[i] = (p.b1 && i < p.nout * nblk) ? p.b1[i] : 0.f;   // the bias has nout * nblk entries (<= 512)
     if (MODE == MODE_FUSED) {
       for (int i = et; i < 128; i += 256) { c_ba[i] = p.ba ? p.ba[i] : 0.f; c_wc[i] = p.wc[i]; }
     } else {
@@ -326,14 +334,16 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
 
     if (MODE == MODE_STORE) {
       const int nch = p.nout / 32;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      for (int64_t tile = blockIdx.x; tile < n_vt; tile += gridDim.x, ++tl) {
         mbar_wait(BAR(B_ACCFULL), tl & 1, p.err, 12);
         tc_fence_after();
-        const int64_t grow = tile * BM + row;
+        const int64_t grow = (tile / nblk) * BM + row;
+        const int cb = (int)(tile % nblk) * nch;              // first 32-column chunk of this virtual tile's column block
 #pragma unroll 1
-        for (int c = half; c < nch; c += 2) {
+        for (int cc = half; cc < nch; cc += 2) {
+          const int c = cb + cc;                              // chunk index in the full output row
           float hv[32];
-          tmem_ld32f(tq + (uint32_t)(c * 32), hv);
+          tmem_ld32f(tq + (uint32_t)(cc * 32), hv);
           if (p.h_out) {                                      // pre-activation (needed by the GELU backward)
             bias_act32<MIL_ACT_NONE>(hv, c_b1 + c * 32, 0, p.w1_inv);
             if (grow < p.N) {
@@ -345,7 +355,7 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
           } else {
             bias_act32<-1>(hv, c_b1 + c * 32, p.act, p.w1_inv);
           }
-          if (p.drop_mode) drop_apply32(hv, drop_keep_word(p, grow, c, nch), p.drop_scale);
+          if (p.drop_mode) drop_apply32(hv, drop_keep_word(p, grow, c, nch * nblk), p.drop_scale);
           if (grow < p.N) {
             float* dst = p.c_out + grow * p.ldc + c * 32;
 #pragma unroll
@@ -544,7 +554,8 @@ mil_fused_kernel(const __grid_constant__ CUtensorMap mapX, const FusedParams p) 
 
 // ------------------------------------------------------------------------------------------------------------
 // fp32 weights W[R, K] -> pre-swizzled 16-bit operand image (once per weight version; 2.4 MB of weights vs 205 MB of bag)
-//   image = for every k-step ks (32 elements): [hi tile | lo tile], each tile = R rows x 64 B laid out exactly as the
+//   image = for every 256-row block of W (one block if R <= 256), for every k-step ks (32 elements): [hi tile | lo tile], each tile =
+//   min(R, 256) rows x 64 B laid out exactly as the
 //   UMMA K-major SWIZZLE_64B shared-memory tile: byte(r, c, e) = (r/8)*512 + (r%8)*64 + ((c ^ ((r>>1)&3))*16) + 2e,
 //   c = 16-byte chunk (8 elements) inside the 64-byte row.  One thread converts one (row, chunk).
 // ------------------------------------------------------------------------------------------------------------
@@ -561,9 +572,12 @@ __global__ void split_weights_kernel(const float* __restrict__ w, int R, int K, 
   uint32_t h[4], l[4];
   h[0] = pack_hi<FP16>(a.x, a.y); h[1] = pack_hi<FP16>(a.z, a.w); h[2] = pack_hi<FP16>(b.x, b.y); h[3] = pack_hi<FP16>(b.z, b.w);
   constexpr int NOPK = LO ? 2 : 1;
-  const size_t tile = (size_t)R * 64;
-  const size_t off = (size_t)(r >> 3) * 512 + (size_t)(r & 7) * 64 + (size_t)((c ^ ((r >> 1) & 3)) << 4);
-  uint8_t* dst = img + (size_t)ks * NOPK * tile + off;
+  // R > 256: one image per 256-row block, block after block, so that a CTA can take either the whole width (two block tiles per stage) or
+  // one 256-column block of it (store mode, column-split launches) from the SAME image
+  const int rb = R > 256 ? (r & 255) : r, blk = R > 256 ? (r >> 8) : 0;
+  const size_t tile = (size_t)(R > 256 ? 256 : R) * 64;
+  const size_t off = (size_t)(rb >> 3) * 512 + (size_t)(rb & 7) * 64 + (size_t)((c ^ ((rb >> 1) & 3)) << 4);
+  uint8_t* dst = img + ((size_t)blk * (K / 32) + ks) * NOPK * tile + off;
   *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
   if (LO) {
     l[0] = pack_lo<FP16>(a.x, a.y, h[0]); l[1] = pack_lo<FP16>(a.z, a.w, h[1]); l[2] = pack_lo<FP16>(b.x, b.y, h[2]); l[3] = pack_lo<FP16>(b.z, b.w, h[3]);
@@ -892,7 +906,11 @@ extern "C" int mil_linear_act_tc_ld_f32(const float* X, int64_t ldx, int64_t M, 
   if ((rc = set_dropout(p, drop, N))) return rc;
   p.w1_inv = p.wa_inv = 1.f / prec_wscale(precision);
   const int64_t n_tiles = (M + BM - 1) / BM;
-  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+  int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+  // Column split: with at most half of the SMs' worth of row tiles a 512-wide output is computed as two 256-column blocks by separate CTAs
+  // (half the MMA time and weight traffic per CTA; the bag tile is read and converted twice, the second read is an L2 hit).
+  static const bool nocolsplit = getenv("MHIMK_NOCOLSPLIT") && atoi(getenv("MHIMK_NOCOLSPLIT"));
+  if (N == 512 && 2 * n_tiles <= num_sms() && !nocolsplit) { p.nout = 256; p.nblk = 2; grid = (int)(2 * n_tiles); }
   return dispatch_fused(precision, MODE_STORE, mx, p, grid, stream);
 }
 

@@ -40,6 +40,7 @@ struct FusedParams {
   // accumulators to split_buf ([partial][CTA rank][epilogue warp][...] in the warps' own register order, 128 KB per CTA) and raise
   // split_flags [partial][2 CTA ranks]; the owner adds them before the bias.
   int split_s = 1, split_full = 0, split_rem = 0; float* split_buf = nullptr; int* split_flags = nullptr;
+  int nblk = 1;         // store mode of the single pipeline: 256-column blocks per row tile handled by separate CTAs (nout = columns per CTA)
   int dbg;              // MHIMK_DEBUG bitmask (timing attribution only): 1 skip W1 TMA, 2 skip X TMA, 4 skip GEMM1 MMA, 8 skip convert, 16 skip Wa TMA, 32 skip pooling, 64 skip GEMM2 MMA
 };
 

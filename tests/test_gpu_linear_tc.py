@@ -54,3 +54,26 @@ def test_linear_act_autograd_through_tc(K):
             Wd.mul_(1.5)
         y = K.linear_act(x.cuda(), Wd, bd, act)
         assert cases.rel_err(y, O.apply_act(x.double() @ (1.5 * W.double()).t() + b.double(), act)) < 2e-5
+
+
+def test_column_split_and_whole_width_share_one_weight_image(K):
+    """A 512-wide Linear over <= 74 row tiles runs as two 256-column blocks on separate CTAs, over more rows as whole-width tiles; both read
+    the SAME cached weight image (256-row blocks), so alternating bag sizes on one weight must stay correct; dropout bits and the
+    pre-activation output follow the column block."""
+    g = torch.Generator().manual_seed(12)
+    N, Kd = 512, 1024
+    W, b = (torch.randn(N, Kd, generator=g) * 0.05).cuda(), (torch.randn(N, generator=g) * 0.1).cuda()
+    for M in (3000, 20000, 129, 9472, 9473, 3000):
+        x = torch.randn(M, Kd, generator=g)
+        pre = torch.empty(M, N, device="cuda")
+        y = K.linear_forward(x.cuda(), W, b, "gelu", pre)
+        ref_pre = x.double() @ W.cpu().double().t() + b.cpu().double()
+        assert cases.rel_err(pre, ref_pre) < 2e-5, M
+        assert cases.rel_err(y, O.apply_act(ref_pre, "gelu")) < 5e-5, M
+    M = 2500
+    x = torch.randn(M, Kd, generator=g)
+    keep = torch.rand(M, N, generator=g) > 0.25
+    spec = K.DropSpec(p=0.25, keep_bits=K.pack_keep_bits(keep.cuda()))
+    y = K.linear_forward(x.cuda(), W, b, "gelu", None, dropout=spec)
+    ref = O.apply_act(x.double() @ W.cpu().double().t() + b.cpu().double(), "gelu") * keep.double() / 0.75
+    assert cases.rel_err(y, ref) < 5e-5

@@ -1,4 +1,3 @@
-timeout 900 python -m pytest tests/test_gpu_fused.py -x -q -p no:cacheprovider 2>&1 | tail -2
-for c in 0; do echo "CTA $c"; PROF_TILES=7 MHIMK_TRACE_CTA=$c PROF_N=50000 PROF_PREC=bf16x3 timeout 120 python tools/trace_fused.py 2>&1 | grep -E "kernel span|tile [45]" | cut -c1-330; done
-for i in 1 2; do python bench.py --steps 50 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; b=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('split', b['ms_per_step'], b['roofline']['kernel_ms'], b['roofline']['frac'])"; done
-MHIMK_NOSPLIT=1 python bench.py --steps 50 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; b=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('nosplit', b['ms_per_step'], b['roofline']['kernel_ms'], b['roofline']['frac'])"
+python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -3
+CFG_REPS=6 CFG_CPU=0 python tools/bench_configs.py 2>/dev/null | tail -n 48 | grep -E "\"teacher|forward_test|graphed|train_step_ms|cfg0" | head -24
+for b in attn dsmil; do d=1024; [ $b = dsmil ] && d=1536; T_BASE=$b T_D=$d timeout 300 python tools/bench_train_step.py 2>/dev/null | tail -1; done
