@@ -15,7 +15,10 @@ DST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 FILES = ["modules/abmil.py", "modules/emb_position.py", "modules/mhim.py", "modules/dsmil.py", "modules/transmil.py",
          "modules/nystrom_attention.py", "modules/mhim_modules/__init__.py", "modules/mhim_modules/baseline.py",
          "modules/mhim_modules/masking.py", "modules/mhim_modules/scoring.py", "modules/mhim_modules/merge.py",
-         "modules/mhim_modules/losses.py", "modules/mhim_modules/utils.py", "engines/common_mil.py"]
+         "modules/mhim_modules/losses.py", "modules/mhim_modules/utils.py", "engines/common_mil.py", "modules/dtfd.py",
+         "modules/clam.py", "modules/topk/__init__.py", "modules/topk/svm.py", "modules/topk/functional.py", "modules/topk/logarithm.py",
+         "modules/topk/utils.py", "modules/topk/polynomial/__init__.py", "modules/topk/polynomial/sp.py", "modules/topk/polynomial/grad.py",
+         "modules/topk/polynomial/multiplication.py", "modules/topk/polynomial/divide_conquer.py"]
 
 
 def main() -> int:

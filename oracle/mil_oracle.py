@@ -722,6 +722,83 @@ def dtfd_forward(sd: SD, x: Tensor, training: bool, group: int = 5, distill: str
     return affine((a2[None] @ pseudo), sd["UClassifier.classifier.fc.weight"], sd["UClassifier.classifier.fc.bias"])
 
 
+def smooth_top1_svm(x: Tensor, y: Tensor, tau: float = 1.0, alpha: float = 1.0, thresh: float = 1e3) -> Tensor:
+    """SmoothTop1SVM(n_classes).forward (modules/topk/svm.py:84-108; functional.py:9-17 hard, :35-42 smooth; utils.py:8-20 delta, :36-42
+    detect_large; polynomial/sp.py:100-106 log_sum_exp).  x [n, C] logits, y [n] int64 targets -> scalar."""
+    import math
+    n, C = x.shape
+    top = x.topk(2, 1).values
+    hard = ((top[:, 0] - top[:, 1]) >= 1 * tau * math.log(thresh)).detach()
+    smooth = ~hard
+    delta = alpha * (y[:, None] != torch.arange(C, device=x.device)[None, :]).to(x.dtype)
+    loss = x.new_zeros(())
+    if bool(smooth.any()):
+        xs = x[smooth] + delta[smooth] - x[smooth].gather(1, y[smooth][:, None])
+        xs = xs / tau
+        mx = xs.max(1).values
+        loss = loss + (tau * (mx + torch.log(torch.exp(xs - mx[:, None]).sum(1)))).sum() / n
+    if bool(hard.any()):
+        xh = x[hard]
+        loss = loss + ((xh + delta[hard]).max(1).values - xh.gather(1, y[hard][:, None]).squeeze(1)).sum() / n
+    return loss
+
+
+def clam_attention_logits(sd: SD, h: Tensor, gate: bool, fc_drop: bool, drop_a: Optional[Tensor] = None, drop_b: Optional[Tensor] = None) -> Tensor:
+    """Attn_Net / Attn_Net_Gated of clam.py:31-80 on h [N, 512] -> raw attention logits [N, K].  The attention net is the last entry of
+    `attention_net` (index 2 without, 3 with the fc Dropout, clam.py:106-126); drop_a / drop_b: pre-scaled keep masks of its Dropout(0.25)s."""
+    pre = f"attention_net.{3 if fc_drop else 2}."
+    if gate:
+        a = torch.tanh(affine(h, sd[pre + "attention_a.0.weight"], sd.get(pre + "attention_a.0.bias")))
+        b = torch.sigmoid(affine(h, sd[pre + "attention_b.0.weight"], sd.get(pre + "attention_b.0.bias")))
+        if drop_a is not None:
+            a, b = a * drop_a, b * drop_b
+        return affine(a * b, sd[pre + "attention_c.weight"], sd.get(pre + "attention_c.bias"))
+    a = torch.tanh(affine(h, sd[pre + "module.0.weight"], sd[pre + "module.0.bias"]))
+    if drop_a is not None:
+        a = a * drop_a
+    last = 3 if drop_a is not None or (pre + "module.3.weight") in sd else 2
+    return affine(a, sd[pre + f"module.{last}.weight"], sd[pre + f"module.{last}.bias"])
+
+
+def clam_forward(sd: SD, x: Tensor, multi_branch: bool, n_classes: int = 2, gate: bool = True, act: str = "relu", k_sample: int = 8,
+                 subtyping: bool = False, label: Optional[int] = None, fc_drop: bool = False, drop_h: Optional[Tensor] = None,
+                 drop_a: Optional[Tensor] = None, drop_b: Optional[Tensor] = None):
+    """CLAM_SB.forward (clam.py:173-241) / CLAM_MB.forward (:278-331) for one bag x [N, D].  Returns (logits [1, C], instance_loss or None,
+    A_raw [K, N]).  label: the bag's class index -> the instance-level branch (:186-209 / :293-311) runs, else it is skipped.
+    fc_drop: the model was built with dropout != 0 (shifts the attention net's index); drop_*: pre-scaled keep masks (None = eval)."""
+    h = apply_act(affine(x, sd["attention_net.0.weight"], sd.get("attention_net.0.bias")), act)
+    if drop_h is not None:
+        h = h * drop_h
+    A_raw = clam_attention_logits(sd, h, gate, fc_drop, drop_a, drop_b).t()                         # [K, N]
+    A = torch.softmax(A_raw, dim=1)
+    inst_loss = None
+    if label is not None:
+        inst_loss = x.new_zeros(())
+        for i in range(n_classes):
+            Wi, bi = sd[f"instance_classifiers.{i}.weight"], sd[f"instance_classifiers.{i}.bias"]
+            Ai = A[i] if multi_branch else A[0]
+            if i == label:                                                                         # in-the-class (:137-154)
+                top_p = torch.topk(Ai, k_sample).indices
+                top_n = torch.topk(-Ai, k_sample).indices
+                logits_i = affine(torch.cat([h[top_p], h[top_n]], 0), Wi, bi)
+                tgt = torch.cat([torch.ones(k_sample, dtype=torch.long, device=h.device), torch.zeros(k_sample, dtype=torch.long, device=h.device)])
+            elif subtyping:                                                                        # out-of-the-class (:157-167)
+                top_p = torch.topk(Ai, k_sample).indices
+                logits_i = affine(h[top_p], Wi, bi)
+                tgt = torch.zeros(k_sample, dtype=torch.long, device=h.device)
+            else:
+                continue
+            inst_loss = inst_loss + smooth_top1_svm(logits_i, tgt)
+        if subtyping:
+            inst_loss = inst_loss / n_classes
+    M = A @ h                                                                                      # [K, 512]
+    if multi_branch:
+        logits = torch.stack([affine(M[c:c + 1], sd[f"classifiers.{c}.weight"], sd[f"classifiers.{c}.bias"])[0, 0] for c in range(n_classes)])[None]
+    else:
+        logits = affine(M, sd["classifiers.weight"], sd.get("classifiers.bias")).max(dim=0).values[None]   # [1, K = 1, C].max(dim=1)
+    return logits, inst_loss, A_raw
+
+
 # ----------------------------------------------------------------------------------------------
 # Analytic ABMIL backward (SURVEY §9.2) -- what the streaming backward kernel implements.
 # ----------------------------------------------------------------------------------------------

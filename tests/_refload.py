@@ -42,6 +42,28 @@ def load_reference():
     return ns
 
 
+def load_clam():
+    """modules/clam.py of the reference (CLAM_SB / CLAM_MB).  Its `topk` package imports `future.builtins.range` (python-future, absent
+    here): a two-line stand-in is registered.  `SmoothTop1SVM(2).cuda()` in the constructors (clam.py:129, :270) needs a CUDA device; on a
+    CPU-only host the loss module's `.cuda()` is replaced by the no-op it is for a buffer-only module, so the classes can be built."""
+    import torch
+    if "future" not in sys.modules:
+        fut, fb = types.ModuleType("future"), types.ModuleType("future.builtins")
+        fb.range = range
+        fut.builtins = fb
+        sys.modules["future"], sys.modules["future.builtins"] = fut, fb
+    load_reference()
+    clam = importlib.import_module("modules.clam")
+    if not torch.cuda.is_available():
+        svm = importlib.import_module("modules.topk.svm")
+
+        def _cpu_cuda(self, device=None):
+            self.get_losses()
+            return self
+        svm._SVMLoss.cuda = _cpu_cuda
+    return clam
+
+
 def zero_dropout(module):
     """Neutralise every nn.Dropout inside a reference instance (MCA/Nystrom hard-code p=0.1)."""
     import torch.nn as nn

@@ -96,6 +96,31 @@ def dtfd_state(seed, D=1024, H=512, Da=128, C=2):
     return sd
 
 
+def clam_state(seed, multi_branch, D=1024, H=512, Da=256, C=2, gate=True, fc_drop=False):
+    """modules/clam.py:106-132 (CLAM_SB) / :245-274 (CLAM_MB): the attention net sits at index 3 of `attention_net` when the model was built
+    with dropout != 0 (a Dropout at index 2), else at 2; its own Dropout(0.25)s then shift the plain net's last Linear to `module.3`."""
+    g, sd = _g(seed), {}
+    K = C if multi_branch else 1
+    a = f"attention_net.{3 if fc_drop else 2}."
+    _lin(sd, g, "attention_net.0", H, D)
+    if gate:
+        _lin(sd, g, a + "attention_a.0", Da, H)
+        _lin(sd, g, a + "attention_b.0", Da, H)
+        _lin(sd, g, a + "attention_c", K, Da)
+    else:
+        _lin(sd, g, a + "module.0", Da, H)
+        _lin(sd, g, a + f"module.{3 if fc_drop else 2}", K, Da)
+    if multi_branch:
+        for c in range(C):
+            _lin(sd, g, f"classifiers.{c}", 1, H)
+    else:
+        _lin(sd, g, "classifiers", C, H)
+    for c in range(C):
+        _lin(sd, g, f"instance_classifiers.{c}", 2, H)
+    sd["instance_loss_fn.labels"] = torch.arange(2)
+    return sd
+
+
 def gated_state(seed, D=1024, H=512, Da=384, C=2):
     g, sd = _g(seed), {}
     _lin(sd, g, "feature.0", H, D)

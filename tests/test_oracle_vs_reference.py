@@ -1,6 +1,7 @@
 """Oracle against the LIVE reference classes (skipped where /root/reference is absent, e.g. the GPU box)."""
 import pytest
 import torch
+import torch.nn.functional as F
 
 import cases
 from _refload import have_reference, load_reference, zero_dropout
@@ -215,3 +216,68 @@ def test_dtfd_train_and_test_forward(R, distill, N):
     ids = list(range(N))
     random.shuffle(ids)
     assert cases.rel_err(O.dtfd_forward(sd, x, False, distill=distill, test_ids=ids), ref) <= 2e-6
+
+
+@pytest.mark.parametrize("mb", [False, True])
+@pytest.mark.parametrize("gate,subtyping,n_cls", [(True, False, 2), (True, True, 3), (False, False, 2)])
+def test_clam_forward_instance_loss_and_gradients(R, mb, gate, subtyping, n_cls):
+    """CLAM_SB / CLAM_MB (modules/clam.py:93-331) incl. the instance-level branch with the SmoothTop1SVM loss (modules/topk/svm.py:84-108): logits,
+    instance loss and EVERY gradient tensor of `CE(logits) + instance_loss` against the live classes (dropout 0; act relu and gelu)."""
+    from _refload import load_clam
+    clam = load_clam()
+    for act, N, seed in (("relu", 300, 3), ("gelu", 1200, 4)):
+        sd = cases.clam_state(seed, mb, C=n_cls, gate=gate)
+        x = cases.make_bag(seed + 10, N, 1024)[0]
+        cls = clam.CLAM_MB if mb else clam.CLAM_SB
+        m = cls(input_dim=1024, gate=gate, n_classes=n_cls, subtyping=subtyping, act=act, dropout=0.0)
+        m.load_state_dict(sd, strict=True)
+        m.eval()
+        lg_ref = m(x[None])
+        lg, _, araw = O.clam_forward(sd, x, mb, n_cls, gate, act, subtyping=subtyping)
+        assert cases.rel_err(lg, lg_ref) <= 2e-6
+        assert cases.rel_err(araw, m(x[None], attention_only=True).reshape(araw.shape)) <= 2e-6
+        m.train()
+        label = torch.tensor([1])
+        lg_ref, il_ref, ps = m(x[None], label=label, instance_eval=True)
+        (F.cross_entropy(lg_ref, label) + il_ref).backward()
+        sdl = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+        lg, il, _ = O.clam_forward(sdl, x, mb, n_cls, gate, act, subtyping=subtyping, label=1)
+        (F.cross_entropy(lg, label) + il).backward()
+        assert ps == N and cases.rel_err(lg, lg_ref) <= 2e-6 and cases.rel_err(il, il_ref) <= 2e-6
+        for k, p_ in m.named_parameters():
+            if p_.grad is None:
+                assert sdl[k].grad is None or float(sdl[k].grad.abs().max()) == 0.0, k
+            elif float(p_.grad.abs().max()) < 1e-6:            # analytically zero (a bias under a softmax over N): rounding noise on both sides
+                assert float(sdl[k].grad.abs().max()) < 1e-6, k
+            else:
+                assert cases.rel_err(sdl[k].grad, p_.grad) <= 2e-5, k
+
+
+def test_smooth_top1_svm_hard_and_smooth_rows(R):
+    """Rows whose top-2 gap exceeds tau * log(1e3) take the hard max-margin form, the others the smooth one (utils.py:36-42)."""
+    from _refload import load_clam
+    load_clam()
+    import importlib
+    svm = importlib.import_module("modules.topk.svm")
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(64, 2, generator=g) * 6
+    y = torch.randint(0, 2, (64,), generator=g)
+    ref = svm.SmoothTop1SVM(2)(x, y)
+    assert cases.rel_err(O.smooth_top1_svm(x, y), ref) <= 1e-6
+    assert bool(((x.max(1).values - x.min(1).values) >= 6.9077).any()) and bool(((x.max(1).values - x.min(1).values) < 6.9077).any())
+
+
+@pytest.mark.parametrize("mb", [False, True])
+@pytest.mark.parametrize("kw", [dict(), dict(dropout=0.25), dict(gate=False, dropout=0.25), dict(size_arg="big", n_classes=4), dict(gate=False)])
+def test_clam_dropin_has_the_reference_state_dict(R, mb, kw):
+    """A reference CLAM checkpoint loads into the drop-in with strict=True (same keys and shapes, `instance_loss_fn.labels` included)."""
+    import mhimk  # noqa: F401
+    from mhimk.modules import clam as mine
+    from _refload import load_clam
+    ref = load_clam()
+    a = (ref.CLAM_MB if mb else ref.CLAM_SB)(input_dim=1024, **kw)
+    b = (mine.CLAM_MB if mb else mine.CLAM_SB)(input_dim=1024, **kw)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys())
+    assert all(sa[k].shape == sb[k].shape and sa[k].dtype == sb[k].dtype for k in sa)
+    b.load_state_dict(sa, strict=True)

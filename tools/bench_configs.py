@@ -158,4 +158,39 @@ def transmil():
 
 
 guarded("transmil", transmil)
+
+
+def clam():
+    # f-3: CLAM_SB training step (instance branch on, dropout 0.25) at N = 10 000, eager / CUDA graph; the oracle's torch ops on the GPU beside it
+    from mhimk.engines import GraphedStep
+    N = 10000
+    m = M.CLAM_SB(input_dim=1024, n_classes=2, dropout=0.25, act="relu").to(dev).train()
+    xb = cases.make_bag(6, N, 1024)[0].to(dev)
+    lab = torch.tensor([1], device=dev)
+    def step(bag, label):
+        m.zero_grad(set_to_none=True)
+        lg, il, _ = m(bag[None], label=label, instance_eval=True)
+        (F.cross_entropy(lg, label) + il).backward()
+    res = {"train_step_ms": gpu_time(lambda: step(xb, lab))}
+    gs = GraphedStep(step)
+    res["train_step_graphed_ms"] = gpu_time(lambda: gs(xb, lab))
+    m.eval()
+    with torch.no_grad():
+        res["eval_fwd_ms"] = gpu_time(lambda: m(xb[None]))
+    sd0 = cases.clam_state(1, False)
+    sdl = {k: v.to(dev).requires_grad_(v.is_floating_point()) for k, v in sd0.items()}
+    arange2 = torch.arange(2)
+    def eager():
+        for v in sdl.values():
+            v.grad = None
+        lg, il, _ = O.clam_forward(sdl, xb, False, label=1)
+        (F.cross_entropy(lg, lab) + il).backward()
+    try:
+        res["eager_torch_cuda_train_step_ms"] = gpu_time(eager, max(2, REPS // 2))
+    except Exception as e:  # noqa: BLE001 - the CPU oracle builds a few index tensors on the host
+        res["eager_torch_cuda_train_step_error"] = str(e)[:120]
+    out["clam_sb_N10000_D1024"] = res
+
+
+guarded("clam", clam)
 print(json.dumps(out, indent=1))
