@@ -19,7 +19,6 @@ state_dict keys are the reference's, `instance_loss_fn.labels` included.
 import math
 
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
@@ -45,10 +44,6 @@ class SmoothTop1SVM(nn.Module):
 
     def forward(self, x, y):
         return self.rows(x, y).sum() / x.shape[0]
-
-
-def _drop(x, layer_drop, training):
-    return layer_drop(x) if (layer_drop is not None and training) else x
 
 
 class Attn_Net(C.MilModule):
@@ -137,34 +132,35 @@ class CLAM_SB(C.MilModule):
         a_raw, _ = self.attention_net[-1](h)
         return h, a_raw
 
-    def _instance_loss(self, a_col, h, i, label):
-        """Instance classifier i on the attention column a_col [N] (clam.py:137-167), selected on the device by `label` [] int64:
-        label == i: k_sample top (target 1) + k_sample bottom (target 0) rows; else, with subtyping, the k_sample top rows with target 0."""
-        k, clf = self.k_sample, self.instance_classifiers[i]
-        col = a_col.detach().contiguous()
-        top_p = ops.topk(col, k, largest=True)
-        inst = h.index_select(0, top_p)
-        if not self.subtyping:
-            inst = torch.cat([inst, h.index_select(0, ops.topk(col, k, largest=False))], dim=0)
-            tgt = torch.cat([self.create_positive_targets(k, h.device), self.create_negative_targets(k, h.device)])
-            loss_in = self.instance_loss_fn(C.lin(clf, inst), tgt)
-            return torch.where(label == i, loss_in, torch.zeros_like(loss_in))
-        top_n = h.index_select(0, ops.topk(col, k, largest=False))
-        logits = C.lin(clf, torch.cat([inst, top_n], dim=0))                     # one launch for both variants; rows [0, k) serve the out-of-class one
-        tgt_in = torch.cat([self.create_positive_targets(k, h.device), self.create_negative_targets(k, h.device)])
-        loss_in = self.instance_loss_fn(logits, tgt_in)
-        loss_out = self.instance_loss_fn(logits[:k], self.create_negative_targets(k, h.device))
-        return torch.where(label == i, loss_in, loss_out)
+    def _instance_losses(self, a_raw, h, label, multi_branch):
+        """Sum over the instance classifiers (clam.py:186-209 / :293-311) for one bag, selected on the device by `label` [] int64: classifier
+        i == label sees the k_sample top rows of its attention column (target 1) and the k_sample bottom rows (target 0, :137-154); the others
+        contribute only with subtyping: their top rows with target 0 (:157-167).  One top-k pair per attention column (the single-branch
+        model ranks ONE column for all classifiers) and ONE Linear launch for all instance classifiers (their weights stacked)."""
+        k, nc, dev = self.k_sample, self.n_classes, h.device
+        cols = range(nc) if multi_branch else (0,)
+        picks = []
+        for c in cols:
+            col = a_raw[:, c].detach().contiguous()
+            picks.append(torch.cat([ops.topk(col, k, largest=True), ops.topk(col, k, largest=False)]))
+        inst = h.index_select(0, torch.cat(picks))                                    # [len(cols) * 2k, 512]
+        W = torch.cat([c.weight for c in self.instance_classifiers], dim=0)           # [2 nc, 512]
+        b = torch.cat([c.bias for c in self.instance_classifiers], dim=0)
+        logits_all = ops.linear_act(inst, W, b, "none", volatile=self.training)      # [len(cols) * 2k, 2 nc]
+        tgt_in = torch.cat([self.create_positive_targets(k, dev), self.create_negative_targets(k, dev)])
+        tgt_out = self.create_negative_targets(k, dev)
+        total = h.new_zeros(())
+        for i in range(nc):
+            r0 = (i if multi_branch else 0) * 2 * k
+            lg = logits_all[r0:r0 + 2 * k, 2 * i:2 * i + 2]
+            loss_in = self.instance_loss_fn(lg, tgt_in)
+            loss_other = self.instance_loss_fn(lg[:k], tgt_out) if self.subtyping else torch.zeros_like(loss_in)
+            total = total + torch.where(label == i, loss_in, loss_other)
+        return total / nc if self.subtyping else total
 
     def _bag(self, x, label, instance_eval, multi_branch):
         h, a_raw = self._embed(x)                                                # [N, 512], [N, K]
-        total = None
-        if instance_eval:
-            total = h.new_zeros(())
-            for i in range(self.n_classes):
-                total = total + self._instance_loss(a_raw[:, i if multi_branch else 0], h, i, label)
-            if self.subtyping:
-                total = total / self.n_classes
+        total = self._instance_losses(a_raw, h, label, multi_branch) if instance_eval else None
         pooled = torch.stack([ops.softmax_pool(a_raw[:, kcol], h)[0] for kcol in range(a_raw.shape[1])], dim=0)     # M [K, 512]
         return pooled, a_raw, total
 
