@@ -1,5 +1,5 @@
 // Masked hard-instance selection on the device (no host round trip).
-//   mil_topk_f32          : radix-select the k-th key, compact the winners in index order, stable LSD radix sort by value
+//   mil_topk_f32          : select the k-th key (two bits per counting pass), compact the winners in index order, stable LSD radix sort by value
 //   mil_mask_from_indices : complement + concatenation -> mask_ids = [kept ascending || masked], keep flags, len_keep
 // One 1024-thread CTA each: the score vector (4 B/instance; 200 KB at N=50k) is L2-resident right after the teacher
 // pass, the work is a handful of passes over it, and a single CTA needs no grid-wide synchronisation.
@@ -51,133 +51,221 @@ __device__ __forceinline__ int64_t suffix_sum256(const int* hist, int64_t* wsum 
   return v;                                                // thread tid < 256 holds suf[255 - tid]
 }
 
+// Lanes of the warp that hold the same 8-bit digit as this lane (0 for a lane that is not `on`): nine ballots.  __match_any_sync on
+// the digit was the cost of the first version of this file -- ~3 000 cycles per call when most lanes differ (tools/time_topk.py:
+// every radix pass cost ~10 k cycles whatever k, the select 1.1 us per 1024 elements and pass).
+__device__ __forceinline__ uint32_t match_digit8(int d, bool on) {
+  uint32_t m = __ballot_sync(0xffffffffu, on);
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool bit = (d >> b) & 1;
+    const uint32_t v = __ballot_sync(0xffffffffu, bit);
+    m &= bit ? v : ~v;
+  }
+  return on ? m : 0u;
+}
+
+// Inclusive scan over the 32 lanes of a warp.
+__device__ __forceinline__ int warp_inclusive_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// Phases (one 1024-thread CTA; the sortable keys of the first `cap` instances are cached in shared memory):
+//   1. T = the k-th largest key, two bits per counting pass (per-thread counters over 16-byte shared-memory loads, packed shuffle sums).
+//   2. compact the winners (key > T, then the first r_ties keys == T) in ascending index order: every thread owns a contiguous
+//      index range, one block-wide scan of the per-thread counts.
+//   3. order the k winners by key, descending, index-ascending among equal keys: k <= 1024 by counting ranks, else a stable LSD radix sort
+//      whose passes are skipped when all winners share the digit.
 __global__ void __launch_bounds__(TK_THREADS) topk_kernel(const float* __restrict__ score, int64_t N, int64_t k, int largest, int64_t cap,
                                                           uint32_t* __restrict__ keyA, uint32_t* __restrict__ keyB,
                                                           int64_t* __restrict__ idxA, int64_t* __restrict__ idxB,
-                                                          int64_t* __restrict__ idx_out) {
+                                                          int64_t* __restrict__ idx_out, long long* __restrict__ stamps) {
   __shared__ int hist[256];
   __shared__ int64_t base[256];
-  __shared__ int cnt_gt[32], cnt_tie[32];
+  __shared__ int s_cnt[32][3];
+  __shared__ unsigned long long s_pk[32];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_wg[32], s_wt[32];
+  __shared__ int s_skip;
   // dynamic shared memory: phases 1-2 cache the sortable keys of the first `cap` instances (4 B each: N = 50 000 fits), phase 3
-  // re-uses the same bytes for the per-warp digit counters of the stable scatter
+  // re-uses the same bytes for the per-(digit, warp) counters of the stable scatter
   extern __shared__ __align__(16) uint32_t dyn[];
   uint32_t* skeys = dyn;
-  int (*wcnt)[256] = reinterpret_cast<int (*)[256]>(dyn);
-  __shared__ uint32_t s_prefix;
-  __shared__ int64_t s_need;
+  int* wc = reinterpret_cast<int*>(dyn);                     // [256 digits][32 warps]
   __shared__ int64_t wsum[8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
+  constexpr uint32_t FULL = 0xffffffffu;
 
+  auto stamp = [&](int j) { if (stamps && tid == 0) stamps[j] = clock64(); };   // phase timeline (tools/time_topk.py); 8 stores per launch
+  stamp(0);
   for (int64_t i = tid; i < min(N, cap); i += TK_THREADS) skeys[i] = sortable_key(score[i], largest);
   __syncthreads();
+  stamp(1);
   auto key_at = [&](int64_t i) -> uint32_t { return i < cap ? skeys[i] : sortable_key(score[i], largest); };
 
-  // ---- 1. radix select: T = key of the k-th element in descending key order; need = how many keys == T to take
-  uint32_t prefix = 0, mask = 0;
-  int64_t need = k;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    if (tid < 256) hist[tid] = 0;
-    __syncthreads();
-    for (int64_t c0 = 0; c0 < N; c0 += TK_THREADS) {          // warp-uniform trip count (match_any needs the full warp)
-      const int64_t i = c0 + tid;
-      int d = 256 + lane;                                      // lanes without a candidate never match anybody
-      if (i < N) {
-        const uint32_t key = key_at(i);
-        if ((key & mask) == prefix) d = (int)((key >> shift) & 255u);
+  // ---- 1. T = key of the k-th element in descending key order, two bits per pass from the top: count the keys >= each of the three
+  // candidates prefix | (1, 2, 3) << shift.  Plain per-thread counters over 16-byte shared-memory loads, shuffle-tree sums -- no warp
+  // collective in the element loop.  (Measured, tools/time_topk.py: an 8-bit radix pass with match_any / nine ballots / REDUX per element
+  // group costs ~1 200 cycles per 1024 elements whichever way the histogram is kept -- the vote / match / redux path of the SM serves the 32
+  // warps one after the other; this loop costs ~110.)
+  uint32_t prefix = 0;                                       // invariant: #{key >= prefix} >= k
+  const int n_cached = (int)min(N, cap), n4 = n_cached >> 2;
+  const bool packed = N < (1ll << 21);
+  const uint4* sk4 = reinterpret_cast<const uint4*>(skeys);
+  for (int shift = 30; shift >= 0; shift -= 2) {
+    const uint32_t c1 = prefix | (1u << shift), c2 = prefix | (2u << shift), c3 = prefix | (3u << shift);
+    int n1 = 0, n2 = 0, n3 = 0;
+    for (int q = tid; q < n4; q += TK_THREADS) {
+      const uint4 v = sk4[q];
+      n1 += (v.x >= c1) + (v.y >= c1) + (v.z >= c1) + (v.w >= c1);
+      n2 += (v.x >= c2) + (v.y >= c2) + (v.z >= c2) + (v.w >= c2);
+      n3 += (v.x >= c3) + (v.y >= c3) + (v.z >= c3) + (v.w >= c3);
+    }
+    for (int64_t i = (int64_t)n4 * 4 + tid; i < N; i += TK_THREADS) {      // the last < 4 cached keys and whatever did not fit the cache
+      const uint32_t key = key_at(i);
+      n1 += key >= c1; n2 += key >= c2; n3 += key >= c3;
+    }
+    // warp sums, then block sums by warp 0 alone: a shuffle costs the SM one issue slot per WARP (32 warps x 30 shuffles per pass were
+    // ~1 000 of the ~1 700 cycles a pass cost), so the three counters travel packed in one 64-bit word (21 bits each; N < 2^21)
+    if (packed) {
+      unsigned long long pk = (unsigned long long)n1 | ((unsigned long long)n2 << 21) | ((unsigned long long)n3 << 42);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) pk += __shfl_xor_sync(FULL, pk, o);
+      if (lane == 0) s_pk[warp] = pk;
+      __syncthreads();
+      if (warp == 0) {
+        unsigned long long tp = s_pk[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tp += __shfl_xor_sync(FULL, tp, o);
+        const int64_t t1 = (int64_t)(tp & 0x1FFFFFull), t2 = (int64_t)((tp >> 21) & 0x1FFFFFull), t3 = (int64_t)(tp >> 42);
+        if (lane == 0) s_prefix = t3 >= k ? c3 : (t2 >= k ? c2 : (t1 >= k ? c1 : prefix));
       }
-      // the CAM scores sit on a few hundred values around 0.5, i.e. in one or two bins: aggregate per warp before the atomic
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
-      if (d < 256 && (peers & lt_mask) == 0) atomicAdd(&hist[d], __popc(peers));
+    } else {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        n1 += __shfl_xor_sync(FULL, n1, o); n2 += __shfl_xor_sync(FULL, n2, o); n3 += __shfl_xor_sync(FULL, n3, o);
+      }
+      if (lane == 0) { s_cnt[warp][0] = n1; s_cnt[warp][1] = n2; s_cnt[warp][2] = n3; }
+      __syncthreads();
+      if (warp == 0) {
+        int64_t t1 = s_cnt[lane][0], t2 = s_cnt[lane][1], t3 = s_cnt[lane][2];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          t1 += __shfl_xor_sync(FULL, t1, o); t2 += __shfl_xor_sync(FULL, t2, o); t3 += __shfl_xor_sync(FULL, t3, o);
+        }
+        if (lane == 0) s_prefix = t3 >= k ? c3 : (t2 >= k ? c2 : (t1 >= k ? c1 : prefix));
+      }
     }
     __syncthreads();
-    {
-      // the selected digit d is the largest one whose suffix count reaches `need`: suf[d] >= need > suf[d+1]
-      const int64_t suf = suffix_sum256(hist, wsum);         // thread t < 256: suf of digit 255 - t
-      if (tid < 256) {
-        const int d = 255 - tid;
-        const int64_t above = suf - hist[d];                 // keys with a larger digit
-        if (suf >= need && above < need) { s_need = need - above; s_prefix = prefix | ((uint32_t)d << shift); }
-      }
-    }
-    __syncthreads();
-    need = s_need;
     prefix = s_prefix;
-    mask |= 255u << shift;
-    __syncthreads();
   }
   const uint32_t T = prefix;
-  const int64_t r_ties = need;   // 1 <= r_ties <= #{key == T}
+  stamp(2);
 
-  // ---- 2. compact winners in ascending index order (ties at T: lowest index first)
-  int64_t run_gt = 0, run_tie = 0;
-  for (int64_t c0 = 0; c0 < N; c0 += TK_THREADS) {
-    const int64_t i = c0 + tid;
-    uint32_t key = 0;
-    bool gt = false, tie = false;
-    if (i < N) {
-      key = key_at(i);
-      gt = key > T;
-      tie = key == T;
-    }
-    const uint32_t bg = __ballot_sync(0xffffffffu, gt), bt = __ballot_sync(0xffffffffu, tie);
-    if (lane == 0) { cnt_gt[warp] = __popc(bg); cnt_tie[warp] = __popc(bt); }
-    __syncthreads();
-    int pg, tg, pt, tt;
-    warp_prefix(cnt_gt, warp, pg, tg);
-    warp_prefix(cnt_tie, warp, pt, tt);
-    const int64_t gt_before = run_gt + pg + __popc(bg & lt_mask);
-    const int64_t tie_before = run_tie + pt + __popc(bt & lt_mask);
-    if (gt || (tie && tie_before < r_ties)) {
-      const int64_t pos = gt_before + min(tie_before, r_ties);
-      keyA[pos] = key;
-      idxA[pos] = i;
-    }
-    run_gt += tg;
-    run_tie += tt;
-    __syncthreads();
+  // ---- 2. compact winners in ascending index order (ties at T: lowest index first); r_ties = how many keys == T to take
+  const int64_t per = (N + TK_THREADS - 1) / TK_THREADS;
+  const int64_t i0 = min(N, (int64_t)tid * per), i1 = min(N, i0 + per);
+  int cg = 0, ct = 0;
+  for (int64_t i = i0; i < i1; ++i) {
+    const uint32_t key = key_at(i);
+    cg += key > T; ct += key == T;
   }
+  const int sg = warp_inclusive_scan(cg, lane), st = warp_inclusive_scan(ct, lane);
+  if (lane == 31) { s_wg[warp] = sg; s_wt[warp] = st; }
+  __syncthreads();
+  const int vg = warp_inclusive_scan(s_wg[lane], lane), vt = warp_inclusive_scan(s_wt[lane], lane);   // every warp scans the 32 warp totals
+  const int64_t n_gt = __shfl_sync(FULL, vg, 31);
+  const int64_t r_ties = k - n_gt;                           // 1 <= r_ties <= #{key == T}
+  int64_t gt_before = (warp ? __shfl_sync(FULL, vg, warp - 1) : 0) + sg - cg;
+  int64_t tie_before = (warp ? __shfl_sync(FULL, vt, warp - 1) : 0) + st - ct;
+  for (int64_t i = i0; i < i1; ++i) {
+    const uint32_t key = key_at(i);
+    if (key > T) {
+      const int64_t pos = gt_before + min(tie_before, r_ties);
+      keyA[pos] = key; idxA[pos] = i;
+      ++gt_before;
+    } else if (key == T) {
+      if (tie_before < r_ties) {
+        const int64_t pos = gt_before + tie_before;
+        keyA[pos] = key; idxA[pos] = i;
+      }
+      ++tie_before;
+    }
+  }
+  __syncthreads();                       // the key cache is dead from here on: its bytes become wc; keyA / idxA are complete
+  stamp(3);
 
-  __syncthreads();                       // the key cache is dead from here on: its bytes become wcnt
-  // ---- 3. stable LSD radix sort of the k winners by key, descending (stability keeps index-ascending among equals)
+  // ---- 3a. k <= 1024: rank sort.  (key, position in the index-ordered winner list) is a total order without ties, so the output slot of
+  // a winner is the number of winners that beat it: every thread counts that for its own winner over the list in shared memory.
+  if (k <= TK_THREADS) {
+    unsigned long long* sv = reinterpret_cast<unsigned long long*>(dyn);
+    unsigned long long mine = 0;
+    if (tid < k) { mine = ((unsigned long long)keyA[tid] << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)tid); sv[tid] = mine; }
+    __syncthreads();
+    if (tid < k) {
+      int r = 0;
+      const int kk = (int)k;
+#pragma unroll 4
+      for (int j = 0; j < kk; ++j) r += sv[j] > mine;
+      idx_out[r] = idxA[tid];
+    }
+    stamp(8);
+    return;
+  }
+  // ---- 3b. stable LSD radix sort of the k winners by key, descending
   uint32_t* kin = keyA; uint32_t* kout = keyB;
   int64_t* iin = idxA; int64_t* iout = idxB;
   for (int shift = 0; shift < 32; shift += 8) {
     if (tid < 256) hist[tid] = 0;
+    if (tid == 0) s_skip = 0;
     __syncthreads();
     for (int64_t c0 = 0; c0 < k; c0 += TK_THREADS) {
       const int64_t i = c0 + tid;
-      const int d = i < k ? (int)((kin[i] >> shift) & 255u) : 256 + lane;
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
-      if (d < 256 && (peers & lt_mask) == 0) atomicAdd(&hist[d], __popc(peers));
+      const int d = i < k ? (int)((kin[i] >> shift) & 255u) : 0;
+      const uint32_t peers = match_digit8(d, i < k);
+      if (i < k && (peers & lt_mask) == 0) atomicAdd(&hist[d], __popc(peers));
     }
     __syncthreads();
+    if (tid < 256 && hist[tid] == k) s_skip = 1;             // every winner has this digit: the pass would not move anything
     {
-      const int64_t suf = suffix_sum256(hist, wsum);
+      const int64_t suf = suffix_sum256(hist, wsum);         // (two barriers inside: s_skip is visible afterwards)
       if (tid < 256) base[255 - tid] = suf - hist[255 - tid];  // descending order: bucket d starts after all larger digits
     }
     __syncthreads();
+    const int skip = s_skip;                                 // block-uniform
+    __syncthreads();                                         // everybody has read it before the next pass clears it
+    if (skip) { stamp(4 + shift / 8); continue; }
     for (int64_t c0 = 0; c0 < k; c0 += TK_THREADS) {
-      for (int j = tid; j < 32 * 256; j += TK_THREADS) (&wcnt[0][0])[j] = 0;
+      for (int j = tid; j < 32 * 256; j += TK_THREADS) wc[j] = 0;
       __syncthreads();
       const int64_t i = c0 + tid;
       const bool on = i < k;
       uint32_t key = 0;
       int64_t id = 0;
-      int d = 256 + lane;                 // inactive lanes never match anybody
+      int d = 0;
       if (on) { key = kin[i]; id = iin[i]; d = (key >> shift) & 255u; }
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t peers = match_digit8(d, on);
       const int rank = __popc(peers & lt_mask);
-      if (on && rank == 0) wcnt[warp][d] = __popc(peers);
+      if (on && rank == 0) wc[d * 32 + warp] = __popc(peers);
       __syncthreads();
-      if (tid < 256) {                    // exclusive prefix over warps for digit tid; hist[] reused as the tile total
-        int run = 0;
-        for (int w = 0; w < 32; ++w) { const int c = wcnt[w][tid]; wcnt[w][tid] = run; run += c; }
-        hist[tid] = run;
+      // exclusive prefix over the warps for every digit: warp w takes digits 8 w .. 8 w + 7, lane = source warp (shuffle scan)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int dd = warp * 8 + q;
+        const int v = wc[dd * 32 + lane];
+        const int inc = warp_inclusive_scan(v, lane);
+        wc[dd * 32 + lane] = inc - v;
+        if (lane == 31) hist[dd] = inc;                      // hist[] reused as the tile total of the digit
       }
       __syncthreads();
       if (on) {
-        const int64_t pos = base[d] + wcnt[warp][d] + rank;
+        const int64_t pos = base[d] + wc[d * 32 + warp] + rank;
         kout[pos] = key;
         iout[pos] = id;
       }
@@ -187,8 +275,10 @@ __global__ void __launch_bounds__(TK_THREADS) topk_kernel(const float* __restric
     }
     uint32_t* tk = kin; kin = kout; kout = tk;
     int64_t* ti = iin; iin = iout; iout = ti;
+    stamp(4 + shift / 8);
   }
   for (int64_t i = tid; i < k; i += TK_THREADS) idx_out[i] = iin[i];
+  stamp(8);
 }
 
 __global__ void __launch_bounds__(TK_THREADS) mask_from_indices_kernel(const int64_t* __restrict__ idx, int64_t k, int64_t N, int64_t cap,
@@ -297,7 +387,8 @@ extern "C" int mil_topk_f32(const float* score, int64_t N, int64_t k, int larges
     MIL_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max));
     attr_set = true;
   }
-  topk_kernel<<<1, TK_THREADS, dyn, (cudaStream_t)stream>>>(score, N, k, largest, (int64_t)(dyn / sizeof(uint32_t)), keyA, keyB, idxA, idxB, idx_out);
+  long long* stamps = (long long*)(((uintptr_t)(keyB + N) + 7) & ~(uintptr_t)7);      // 9 clock stamps in the workspace's 256 spare bytes
+  topk_kernel<<<1, TK_THREADS, dyn, (cudaStream_t)stream>>>(score, N, k, largest, (int64_t)(dyn / sizeof(uint32_t)), keyA, keyB, idxA, idxB, idx_out, stamps);
   MIL_LAUNCH_CHECK();
   return 0;
 }

@@ -111,7 +111,8 @@ def tie_aware_equal(score, idx, ref_idx, k):
     assert all(score[i] >= thr for i in idx.tolist())
 
 
-@pytest.mark.parametrize("N,k", [(1, 1), (5, 1), (1000, 30), (4099, 205), (50000, 1500), (200000, 6000), (3000, 3000), (70000, 70000)])
+@pytest.mark.parametrize("N,k", [(1, 1), (5, 1), (3, 3), (1000, 30), (1000, 8), (4099, 205), (10000, 1024), (10000, 1025), (50000, 1500), (50001, 300),
+                                 (200000, 6000), (200000, 16), (3000, 3000), (70000, 70000)])
 def test_topk_exact_on_tie_free_scores(K, N, k):
     g = torch.Generator().manual_seed(N)
     score = torch.randperm(N, generator=g).float() / N - 0.3          # distinct values, both signs
@@ -121,9 +122,10 @@ def test_topk_exact_on_tie_free_scores(K, N, k):
         assert torch.equal(got, ref)                                     # bit-exact incl. order
 
 
-def test_topk_ties_lowest_index_first(K):
+@pytest.mark.parametrize("N,k", [(50000, 1500), (50000, 700), (3000, 64)])
+def test_topk_ties_lowest_index_first(K, N, k):
+    """k > 1024 orders the winners by the stable radix sort, k <= 1024 by counting ranks: both must put equal scores in index order."""
     g = torch.Generator().manual_seed(3)
-    N, k = 50000, 1500
     score = (0.5 + torch.randint(0, 900, (N,), generator=g).float() * 5.9604645e-08)   # ~900 distinct values around 0.5 (SURVEY 7.3-2)
     got = K.topk(dev(score), k, True).cpu()
     key = score.double() * 1e6 * N - torch.arange(N).double() / 1.0
