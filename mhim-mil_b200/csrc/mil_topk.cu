@@ -16,19 +16,6 @@ __device__ __forceinline__ uint32_t sortable_key(float f, int largest) {
   return largest ? u : ~u;                          // "bigger key" always means "selected first"
 }
 
-// Exclusive prefix over the per-warp counts held in sh[0..31]; returns (prefix for this warp, total).
-__device__ __forceinline__ void warp_prefix(const int* sh, int warp, int& prefix, int& total) {
-  int p = 0, t = 0;
-#pragma unroll
-  for (int w = 0; w < TK_THREADS / 32; ++w) {
-    const int c = sh[w];
-    if (w < warp) p += c;
-    t += c;
-  }
-  prefix = p;
-  total = t;
-}
-
 // Inclusive suffix sums over 256 histogram bins: suf[d] = sum_{d' >= d} hist[d'] for thread d < 256 (all threads must call).
 // Replaces a 256-step single-thread scan (a dependent chain of shared-memory loads: ~10k cycles per radix pass).
 __device__ __forceinline__ int64_t suffix_sum256(const int* hist, int64_t* wsum /*[8]*/) {
@@ -287,7 +274,6 @@ __global__ void __launch_bounds__(TK_THREADS) mask_from_indices_kernel(const int
   __shared__ int cnt[32];
   extern __shared__ __align__(16) uint8_t sflag[];            // keep flags of the first `cap` instances (1 B each)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t lt_mask = (1u << lane) - 1u;
   for (int64_t i = tid; i < min(N, cap); i += TK_THREADS) sflag[i] = 1;
   for (int64_t i = cap + tid; i < N; i += TK_THREADS) keep[i] = 1;
   __syncthreads();
@@ -296,19 +282,22 @@ __global__ void __launch_bounds__(TK_THREADS) mask_from_indices_kernel(const int
     if (v >= 0 && v < N) { if (v < cap) sflag[v] = 0; else keep[v] = 0; }
   }
   __syncthreads();
-  int64_t run = 0;
-  for (int64_t c0 = 0; c0 < N; c0 += TK_THREADS) {
-    const int64_t i = c0 + tid;
-    const bool kp = i < N && (i < cap ? sflag[i] : keep[i]);
-    const uint32_t b = __ballot_sync(0xffffffffu, kp);
-    if (lane == 0) cnt[warp] = __popc(b);
-    __syncthreads();
-    int p, t;
-    warp_prefix(cnt, warp, p, t);
-    if (kp) mask_ids[run + p + __popc(b & lt_mask)] = i;
-    if (i < cap && i < N) keep[i] = kp ? 1 : 0;
-    run += t;
-    __syncthreads();
+  // kept instances in ascending order: every thread owns a contiguous index range, one block-wide scan of the per-thread counts (a
+  // ballot + prefix per 1024-element chunk cost two barriers and a 32-step shared-memory walk per chunk)
+  const int64_t per = (N + TK_THREADS - 1) / TK_THREADS;
+  const int64_t i0 = min(N, (int64_t)tid * per), i1 = min(N, i0 + per);
+  int c = 0;
+  for (int64_t i = i0; i < i1; ++i) c += (i < cap ? sflag[i] : keep[i]) ? 1 : 0;
+  const int sc = warp_inclusive_scan(c, lane);
+  if (lane == 31) cnt[warp] = sc;
+  __syncthreads();
+  const int vw = warp_inclusive_scan(cnt[lane], lane);      // every warp scans the 32 warp totals
+  const int64_t run = __shfl_sync(0xffffffffu, vw, 31);
+  int64_t pos = (warp ? __shfl_sync(0xffffffffu, vw, warp - 1) : 0) + sc - c;
+  for (int64_t i = i0; i < i1; ++i) {
+    const bool kp = (i < cap ? sflag[i] : keep[i]) != 0;
+    if (kp) mask_ids[pos++] = i;
+    if (i < cap) keep[i] = kp ? 1 : 0;
   }
   for (int64_t j = tid; j < k; j += TK_THREADS)
     if (run + j < N) mask_ids[run + j] = idx[j];
