@@ -318,6 +318,13 @@ int mil_adam_step_f32(const mil_adam_seg_t* segs_dev, int n_seg, float lr, doubl
 int mil_umma_selftest_f32(const float* A, const float* B, float* C, int M, int N, int K, int precision,
                           void* ws, size_t ws_bytes, mil_stream_t stream);
 
+/* Test hook for the host-side plan of the fused pass's pair pipeline (no device work, no GPU needed): the i-th work item of CTA pair
+ * `pair` for a bag of N rows x D features.  out9[0..4] = 128-row tile, first and end pipeline stage of its K loop, kind (0 whole tile,
+ * 1 owner / 2 helper of a tail-split tile), index of the exchanged partial; out9[5..8] = number of CTA pairs, parts per split tile,
+ * whole-tile waves, tiles of the split wave.  Returns the number of items of that pair (out9[0..4] untouched when i is out of range),
+ * < 0 on a bad argument.  The SM count is the current device's (148 without one). */
+int mil_pair_plan_item(int64_t N, int D, int precision, int pair, int i, int64_t* out9);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,7 @@ _SIGS = {
     "mil_col_argmax_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "mil_topk_workspace_bytes": (c_size_t, [c_int64]),
     "mil_umma_selftest_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "mil_pair_plan_item": (c_int, [c_int64, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGS)

@@ -66,11 +66,11 @@ struct WorkItem {
   int kind;         // 0 whole tile, 1 owner of a split tile, 2 helper
   int pidx;         // helper: index of its partial; owner: index of its first helper's partial (S - 1 consecutive)
 };
-__device__ __forceinline__ int work_count(const FusedParams& p, int64_t pair_id, int64_t n_pairs, int64_t n_tiles) {
+__host__ __device__ __forceinline__ int work_count(const FusedParams& p, int64_t pair_id, int64_t n_pairs, int64_t n_tiles) {
   if (p.split_s <= 1) return pair_id < n_tiles ? (int)((n_tiles - pair_id + n_pairs - 1) / n_pairs) : 0;
   return p.split_full + (pair_id < (int64_t)p.split_rem * p.split_s ? 1 : 0);
 }
-__device__ __forceinline__ WorkItem work_item(const FusedParams& p, int i, int64_t pair_id, int64_t n_pairs, int KST) {
+__host__ __device__ __forceinline__ WorkItem work_item(const FusedParams& p, int i, int64_t pair_id, int64_t n_pairs, int KST) {
   WorkItem w;
   const bool has_split = p.split_s > 1 && pair_id < (int64_t)p.split_rem * p.split_s;
   const int part = has_split ? (int)pair_id % p.split_s : 0;
@@ -833,6 +833,8 @@ int pair_build_images(const float* W1, int H, int D, const float* Wa, int Da, ui
   return 0;
 }
 
+int pair_plan(FusedParams& p, int precision);
+
 // p: every field of the fused pass filled in by the caller (mil_abmil_fused_fwd_f32), w1_img / wa_img in the pair layout.
 int pair_fused_launch(const float* X, FusedParams p, int precision, cudaStream_t stream) {
   using namespace pairk;
@@ -843,6 +845,19 @@ int pair_fused_launch(const float* X, FusedParams p, int precision, cudaStream_t
   const uint64_t w1_rows = (uint64_t)HMAX * p.D * 2 * NOP / 256, wa_rows = (uint64_t)128 * HMAX * 2 * NOP / 256;
   if ((rc = make_map_2d(&mw1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, p.w1_img, w1_rows, 256, (uint32_t)(pair_ksub(precision, p.D) * NOP * B_OP / 256), 256, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   if ((rc = make_map_2d(&mwa, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, p.wa_img, wa_rows, 256, (uint32_t)(G2B_BUF / 256), 256, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  const int grid = 2 * pair_plan(p, precision);
+#define MIL_CASE(A, T) if (p.act == A && p.att_act == T) return dispatch_prec<A, T>(precision, mx, mw1, mwa, p, grid, stream);
+  MIL_CASE(MIL_ACT_RELU, MIL_ACT_TANH) MIL_CASE(MIL_ACT_GELU, MIL_ACT_TANH)
+  MIL_CASE(MIL_ACT_RELU, MIL_ACT_RELU) MIL_CASE(MIL_ACT_GELU, MIL_ACT_RELU)
+  MIL_CASE(MIL_ACT_RELU, MIL_ACT_GELU) MIL_CASE(MIL_ACT_GELU, MIL_ACT_GELU)
+#undef MIL_CASE
+  set_error("fused pass: unsupported activation pair act=%d att_act=%d (use the composed path)", p.act, p.att_act);
+  return -1;
+}
+
+// Grid and tail-split plan of the pair pipeline for p.N rows: fills p.split_* and returns the number of CTA pairs.
+int pair_plan(FusedParams& p, int precision) {
+  using namespace pairk;
   const int64_t n_tiles = (p.N + BMP - 1) / BMP;
   int pmax = num_sms() / 2;
   const char* e = getenv("MHIMK_GRID");
@@ -865,14 +880,24 @@ int pair_fused_launch(const float* X, FusedParams p, int precision, cudaStream_t
       pairs = p.split_full ? pmax : rem * S;
     }
   }
-  const int grid = 2 * pairs;
-#define MIL_CASE(A, T) if (p.act == A && p.att_act == T) return dispatch_prec<A, T>(precision, mx, mw1, mwa, p, grid, stream);
-  MIL_CASE(MIL_ACT_RELU, MIL_ACT_TANH) MIL_CASE(MIL_ACT_GELU, MIL_ACT_TANH)
-  MIL_CASE(MIL_ACT_RELU, MIL_ACT_RELU) MIL_CASE(MIL_ACT_GELU, MIL_ACT_RELU)
-  MIL_CASE(MIL_ACT_RELU, MIL_ACT_GELU) MIL_CASE(MIL_ACT_GELU, MIL_ACT_GELU)
-#undef MIL_CASE
-  set_error("fused pass: unsupported activation pair act=%d att_act=%d (use the composed path)", p.act, p.att_act);
-  return -1;
+  return pairs;
+}
+
+// Test hook (mil_pair_plan_item): the i-th work item of CTA pair `pair` under the plan for (N, D, precision) on this device's SM count.
+// out[0..4] = tile, first stage, end stage, kind (0 whole tile, 1 owner, 2 helper), partial index; out[5..8] = pairs, split_s, split_full, split_rem.
+int pair_plan_item(int64_t N, int D, int precision, int pair, int i, int64_t* out) {
+  using namespace pairk;
+  FusedParams p;
+  p.N = N; p.D = D;
+  p.split_buf = reinterpret_cast<float*>(1); p.split_flags = reinterpret_cast<int*>(1);      // "the workspace has the exchange area"
+  const int pairs = pair_plan(p, precision);
+  const int64_t n_tiles = (N + BMP - 1) / BMP;
+  const int n_it = pair < pairs ? work_count(p, pair, pairs, n_tiles) : 0;
+  out[5] = pairs; out[6] = p.split_s; out[7] = p.split_full; out[8] = p.split_rem;
+  if (i < 0 || i >= n_it) return n_it;
+  const WorkItem w = work_item(p, i, pair, pairs, D / BK / pair_ksub(precision, D));
+  out[0] = w.tile; out[1] = w.kb; out[2] = w.ke; out[3] = w.kind; out[4] = w.pidx;
+  return n_it;
 }
 
 }  // namespace mil

@@ -844,6 +844,11 @@ extern "C" int mil_abmil_fused_fwd_f32(const float* X, int64_t N, int D, int H, 
   return dispatch_fused(precision, MODE_FUSED, mx, p, grid, stream);
 }
 
+extern "C" int mil_pair_plan_item(int64_t N, int D, int precision, int pair, int i, int64_t* out9) {
+  MIL_CHECK_ARG(out9 && N > 0 && D >= 32 && D % 32 == 0 && precision >= 0 && precision <= 3 && pair >= 0, "mil_pair_plan_item: bad arguments");
+  return pair_plan_item(N, D, precision, pair, i, out9);
+}
+
 extern "C" int mil_umma_selftest_f32(const float* A, const float* B, float* C, int M, int N, int K, int precision, void* ws, size_t ws_bytes,
                                      mil_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;

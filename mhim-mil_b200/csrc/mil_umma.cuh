@@ -550,6 +550,7 @@ inline bool prec_split(int precision) { return precision == MIL_PREC_BF16X3 || p
 inline float prec_wscale(int precision) { return precision == MIL_PREC_FP16X3 ? W_SCALE_FP16X3 : 1.f; }
 int pair_build_images(const float* W1, int H, int D, const float* Wa, int Da, uint8_t* w1_img, uint8_t* wa_img, int precision, cudaStream_t stream);
 int pair_fused_launch(const float* X, FusedParams p, int precision, cudaStream_t stream);
+int pair_plan_item(int64_t N, int D, int precision, int pair, int i, int64_t* out);
 // fills the dropout fields of p from the ABI struct (nullptr / mode 0 = no dropout); <0 on a bad argument
 int set_dropout(FusedParams& p, const mil_dropout_t* drop, int ncols);
 
