@@ -27,7 +27,7 @@ for N in (1000, 10000, 50000):
 # phase timeline of one launch (clock64 stamps the kernel leaves in the workspace's spare bytes): cache | select | compact | 4 sort passes | out
 import ctypes
 L = mhimk._lib.lib()
-for N, k in ((1000, 8), (10000, 300), (50000, 3000)):
+for N, k in ((1000, 8), (10000, 300), (50000, 3000), (200000, 6000)):
     s = torch.rand(N, device="cuda")
     ws = torch.empty(L.mil_topk_workspace_bytes(N), dtype=torch.uint8, device="cuda")
     idx = torch.empty(k, dtype=torch.int64, device="cuda")
